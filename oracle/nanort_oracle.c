@@ -1,0 +1,806 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement ("port") of the nanort hot path.
+ *
+ * This file is the parity oracle for the CUDA path.  Only tests/, the smoke()
+ * entry point and bench.py's cpu_baseline / --impl reference legs may load it;
+ * the product library (nanort_b200/libnanort_b200.so) never links or calls it
+ * and has no CPU fallback.
+ *
+ * It restates, in plain C, the algorithm of /root/reference/nanort.h at commit
+ * 3bbea5e for BVHAccel<float>::Build and BVHAccel<float>::Traverse with the
+ * built-in triangle classes.  All arithmetic is IEEE binary32 with every
+ * operation individually rounded: compile with -ffp-contract=off and without
+ * -ffast-math (oracle/Makefile does).
+ *
+ * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this port
+ * bit-for-bit (nodes, indices, statistics, hit flag, prim_id and the raw bits
+ * of t/u/v) against the unmodified reference compiled into
+ * oracle/_ref/libnanort_ref{,03}.so, and against the committed golden vectors
+ * under tests/golden/ that were produced by that reference.
+ *
+ * Reference map (file:line under /root/reference):
+ *   orc_prim_bbox            TriangleMesh::BoundingBox          nanort.h:934-956
+ *   orc_prim_bbox_center     TriangleMesh::BoundingBoxAndCenter nanort.h:958-971
+ *   orc_range_bbox           ComputeBoundingBox                 nanort.h:1545-1567
+ *   orc_fill_bins            ContributeBinBuffer                nanort.h:1314-1367
+ *   orc_find_cut             FindCutFromBinBuffer               nanort.h:1381-1430
+ *   orc_area                 CalculateSurfaceArea               nanort.h:1278-1283
+ *   orc_pred / orc_partition TriangleSAHPred::operator() nanort.h:897-911 and
+ *                            std::partition (libstdc++ bidirectional variant,
+ *                            bits/stl_algo.h __partition) used at nanort.h:1841
+ *   orc_build_rec            BuildTree                          nanort.h:1759-1890
+ *   orc_build_shallow_rec    BuildShallowTree                   nanort.h:1600-1757
+ *   orc_build                Build (+ parallel join)            nanort.h:1892-2149
+ *   orc_safe_inverse         vsafe_inverse                      nanort.h:414-465
+ *   orc_slab                 IntersectRayAABB<float>            nanort.h:2284-2325
+ *   orc_tri                  TriangleIntersector::Intersect     nanort.h:1054-1150
+ *   orc_prepare              PrepareTraversal                   nanort.h:1163-1201
+ *   orc_traverse_one         Traverse + TestLeafNode            nanort.h:2487-2556, 2372-2407
+ */
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- value types, byte-compatible with the reference ---- */
+typedef struct {
+  float bmin[3];
+  float bmax[3];
+  int32_t flag; /* 1 leaf, 0 branch */
+  int32_t axis;
+  uint32_t data[2]; /* leaf {count, first}; branch {left, right} */
+} orc_node; /* 40 B */
+
+typedef struct {
+  float org[3];
+  float dir[3];
+  float min_t;
+  float max_t;
+  uint32_t type;
+} orc_ray; /* 36 B */
+
+typedef struct {
+  float u, v, t;
+  uint32_t prim_id;
+} orc_hit; /* 16 B */
+
+typedef struct {
+  float cost_t_aabb;
+  uint32_t min_leaf_primitives;
+  uint32_t max_tree_depth;
+  uint32_t bin_size;
+  uint32_t shallow_depth;
+  uint32_t min_primitives_for_parallel_build;
+  uint8_t cache_bbox;
+  uint8_t pad[3];
+} orc_build_options; /* 28 B */
+
+typedef struct {
+  uint32_t prim_ids_range[2];
+  uint32_t skip_prim_id;
+  uint8_t cull_back_face;
+  uint8_t pad[3];
+} orc_trace_options; /* 16 B */
+
+typedef struct {
+  uint32_t max_tree_depth;
+  uint32_t num_leaf_nodes;
+  uint32_t num_branch_nodes;
+} orc_stats;
+
+/* Build mode flags */
+#define ORC_MODE_CPP11 1u    /* shallow tree + joined sub-arrays for n > threshold (nanort.h:1996-2068) */
+#define ORC_MODE_FIXBINS 2u  /* NOT reference behaviour: bins all three axes (guard at nanort.h:1357 widened) */
+
+void orc_default_build_options(orc_build_options *o) {
+  memset(o, 0, sizeof(*o));
+  o->cost_t_aabb = 0.2f;
+  o->min_leaf_primitives = 4;
+  o->max_tree_depth = 256;
+  o->bin_size = 64;
+  o->shallow_depth = 4;
+  o->min_primitives_for_parallel_build = 1024 * 8;
+  o->cache_bbox = 0;
+}
+
+void orc_default_trace_options(orc_trace_options *o) {
+  memset(o, 0, sizeof(*o));
+  o->prim_ids_range[0] = 0;
+  o->prim_ids_range[1] = 0x7FFFFFFFu;
+  o->skip_prim_id = 0xFFFFFFFFu;
+  o->cull_back_face = 0;
+}
+
+void orc_sizes(uint32_t out[5]) {
+  out[0] = (uint32_t)sizeof(orc_node);
+  out[1] = (uint32_t)sizeof(orc_ray);
+  out[2] = (uint32_t)sizeof(orc_hit);
+  out[3] = (uint32_t)sizeof(orc_build_options);
+  out[4] = (uint32_t)sizeof(orc_trace_options);
+}
+
+/* std::min / std::max argument-order semantics (matters for -0.0 and NaN) */
+static inline float stdmin(float a, float b) { return (b < a) ? b : a; }
+static inline float stdmax(float a, float b) { return (a < b) ? b : a; }
+
+/* ------------------------------------------------------------------ geometry */
+typedef struct {
+  const unsigned char *verts;
+  size_t stride;
+  const uint32_t *faces;
+} orc_mesh;
+
+static inline const float *vtx(const orc_mesh *m, uint32_t i) {
+  return (const float *)(m->verts + (size_t)i * m->stride);
+}
+
+static void orc_prim_bbox(const orc_mesh *m, uint32_t prim, float bmin[3], float bmax[3]) {
+  const float *p = vtx(m, m->faces[3 * (size_t)prim]);
+  for (int k = 0; k < 3; k++) bmin[k] = bmax[k] = p[k];
+  for (int c = 1; c < 3; c++) {
+    p = vtx(m, m->faces[3 * (size_t)prim + c]);
+    for (int k = 0; k < 3; k++) {
+      bmin[k] = stdmin(bmin[k], p[k]);
+      bmax[k] = stdmax(bmax[k], p[k]);
+    }
+  }
+}
+
+static void orc_prim_bbox_center(const orc_mesh *m, uint32_t prim, float bmin[3], float bmax[3],
+                                 float ctr[3]) {
+  const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
+  const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
+  const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
+  const float third = 1.0f / 3.0f;
+  for (int k = 0; k < 3; k++) {
+    bmin[k] = stdmin(p0[k], stdmin(p1[k], p2[k]));
+    bmax[k] = stdmax(p0[k], stdmax(p1[k], p2[k]));
+    ctr[k] = ((p0[k] + p1[k]) + p2[k]) * third;
+  }
+}
+
+static void orc_range_bbox(const orc_mesh *m, const uint32_t *idx, uint32_t l, uint32_t r,
+                           float bmin[3], float bmax[3]) {
+  orc_prim_bbox(m, idx[l], bmin, bmax);
+  for (uint32_t i = l + 1; i < r; i++) {
+    float a[3], b[3];
+    orc_prim_bbox(m, idx[i], a, b);
+    for (int k = 0; k < 3; k++) {
+      bmin[k] = stdmin(bmin[k], a[k]);
+      bmax[k] = stdmax(bmax[k], b[k]);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ SAH bins */
+typedef struct {
+  float bmin[3], bmax[3];
+  size_t count;
+  float cost;
+} orc_bin;
+
+static inline float orc_area(const float lo[3], const float hi[3]) {
+  float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  return 2.0f * ((dx * dy + dy * dz) + dz * dx);
+}
+
+static void orc_bins_clear(orc_bin *bins, uint32_t B) {
+  for (uint32_t i = 0; i < 3 * B; i++) {
+    for (int k = 0; k < 3; k++) {
+      bins[i].bmin[k] = FLT_MAX;
+      bins[i].bmax[k] = -FLT_MAX;
+    }
+    bins[i].count = 0;
+    bins[i].cost = 0.0f;
+  }
+}
+
+static void orc_fill_bins(orc_bin *bins, uint32_t B, uint32_t guard, const float nmin[3],
+                          const float nmax[3], const orc_mesh *m, const uint32_t *idx, uint32_t l,
+                          uint32_t r) {
+  float inv[3];
+  const float fB = (float)B;
+  for (int k = 0; k < 3; k++) {
+    float sz = nmax[k] - nmin[k];
+    inv[k] = (sz > 0.0f) ? fB / sz : 0.0f;
+  }
+  orc_bins_clear(bins, B);
+  for (uint32_t i = l; i < r; i++) {
+    float lo[3], hi[3], c[3];
+    orc_prim_bbox_center(m, idx[i], lo, hi, c);
+    for (int j = 0; j < 3; j++) {
+      float q = (c[j] - nmin[j]) * inv[j];
+      int qi = (int)q;
+      if (qi < 0) qi = 0;
+      uint32_t b = (uint32_t)qi;
+      if (b > B - 1) b = B - 1;
+      uint32_t slot = (uint32_t)j * B + b;
+      /* guard == B reproduces the pinned commit: only axis 0 is ever binned
+       * (nanort.h:1357).  guard == 3B is the ORC_MODE_FIXBINS
+       * experiment, never used as the reference. */
+      if (slot < guard) {
+        orc_bin *bn = &bins[slot];
+        bn->count++;
+        for (int k = 0; k < 3; k++) {
+          bn->bmin[k] = stdmin(bn->bmin[k], lo[k]);
+          bn->bmax[k] = stdmax(bn->bmax[k], hi[k]);
+        }
+      }
+    }
+  }
+}
+
+static void orc_find_cut(orc_bin *bins, uint32_t B, const float nmin[3], const float nmax[3],
+                         float cut_pos[3], int *best_axis) {
+  float best[3];
+  for (int j = 0; j < 3; j++) {
+    orc_bin *ax = bins + (size_t)j * B;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    size_t cnt = 0;
+    best[j] = FLT_MAX;
+    /* right-to-left: cost of the right-hand side starting at bin i */
+    for (size_t i = B - 1; i > 0; i--) {
+      for (int k = 0; k < 3; k++) {
+        lo[k] = stdmin(ax[i].bmin[k], lo[k]);
+        hi[k] = stdmax(ax[i].bmax[k], hi[k]);
+      }
+      cnt += ax[i].count;
+      ax[i].cost = (float)cnt * orc_area(lo, hi);
+    }
+    for (int k = 0; k < 3; k++) {
+      lo[k] = FLT_MAX;
+      hi[k] = -FLT_MAX;
+    }
+    cnt = 0;
+    size_t arg = 1;
+    for (size_t i = 0; i + 1 < B; i++) {
+      for (int k = 0; k < 3; k++) {
+        lo[k] = stdmin(ax[i].bmin[k], lo[k]);
+        hi[k] = stdmax(ax[i].bmax[k], hi[k]);
+      }
+      cnt += ax[i].count;
+      float c = (float)cnt * orc_area(lo, hi) + ax[i + 1].cost;
+      if (c < best[j]) {
+        best[j] = c;
+        arg = i + 1;
+      }
+    }
+    cut_pos[j] = (float)arg * ((nmax[j] - nmin[j]) / (float)B) + nmin[j];
+  }
+  int a = 0;
+  if (best[0] > best[1]) a = 1;
+  if (best[a] > best[2]) a = 2;
+  *best_axis = a;
+}
+
+static inline int orc_pred(const orc_mesh *m, uint32_t prim, int axis, float pos) {
+  const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
+  const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
+  const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
+  float s = (p0[axis] + p1[axis]) + p2[axis];
+  return s < pos * 3.0f;
+}
+
+/* two-pointer in-place partition: element order after the call is the one
+ * libstdc++'s std::partition (bidirectional iterators) leaves behind */
+static uint32_t orc_partition(uint32_t *idx, uint32_t l, uint32_t r, const orc_mesh *m, int axis,
+                              float pos) {
+  uint32_t first = l, last = r;
+  for (;;) {
+    for (;;) {
+      if (first == last) return first;
+      if (orc_pred(m, idx[first], axis, pos))
+        ++first;
+      else
+        break;
+    }
+    --last;
+    for (;;) {
+      if (first == last) return first;
+      if (!orc_pred(m, idx[last], axis, pos))
+        --last;
+      else
+        break;
+    }
+    uint32_t t = idx[first];
+    idx[first] = idx[last];
+    idx[last] = t;
+    ++first;
+  }
+}
+
+/* ------------------------------------------------------------------ builder */
+typedef struct {
+  orc_node *v;
+  size_t n, cap;
+} node_vec;
+
+static size_t nv_push(node_vec *a, const orc_node *x) {
+  if (a->n == a->cap) {
+    a->cap = a->cap ? a->cap * 2 : 64;
+    a->v = (orc_node *)realloc(a->v, a->cap * sizeof(orc_node));
+  }
+  a->v[a->n] = *x;
+  return a->n++;
+}
+
+typedef struct {
+  uint32_t l, r, offset;
+} deferred_t;
+
+typedef struct {
+  orc_mesh mesh;
+  orc_build_options opt;
+  uint32_t guard;
+  uint32_t *idx;
+  orc_bin *bins; /* scratch 3*B, reused: recursion only needs it before descending */
+  deferred_t *deferred;
+  size_t n_deferred, cap_deferred;
+} build_ctx;
+
+/* chooses the split of [l,r): returns mid and the axis label the node gets */
+static uint32_t orc_split(build_ctx *c, uint32_t l, uint32_t r, const float bmin[3],
+                          const float bmax[3], int *axis_out) {
+  float cut[3] = {0.0f, 0.0f, 0.0f};
+  int first_axis = 0;
+  uint32_t n = r - l;
+  orc_fill_bins(c->bins, c->opt.bin_size, c->guard, bmin, bmax, &c->mesh, c->idx, l, r);
+  orc_find_cut(c->bins, c->opt.bin_size, bmin, bmax, cut, &first_axis);
+  uint32_t mid = l;
+  int axis = first_axis;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    axis = (first_axis + attempt) % 3;
+    mid = orc_partition(c->idx, l, r, &c->mesh, axis, cut[axis]);
+    if (mid == l || mid == r) {
+      mid = l + (n >> 1); /* object-median fallback; next axis is still tried */
+    } else {
+      break;
+    }
+  }
+  *axis_out = axis;
+  return mid;
+}
+
+static void set_box(orc_node *nd, const float bmin[3], const float bmax[3]) {
+  for (int k = 0; k < 3; k++) {
+    nd->bmin[k] = bmin[k];
+    nd->bmax[k] = bmax[k];
+  }
+}
+
+static uint32_t orc_build_rec(build_ctx *c, orc_stats *st, node_vec *out, uint32_t l, uint32_t r,
+                              uint32_t depth) {
+  uint32_t self = (uint32_t)out->n;
+  if (st->max_tree_depth < depth) st->max_tree_depth = depth;
+  float bmin[3], bmax[3];
+  orc_range_bbox(&c->mesh, c->idx, l, r, bmin, bmax);
+  uint32_t n = r - l;
+  orc_node nd;
+  memset(&nd, 0, sizeof(nd));
+  if (n <= c->opt.min_leaf_primitives || depth >= c->opt.max_tree_depth) {
+    set_box(&nd, bmin, bmax);
+    nd.flag = 1;
+    nd.axis = 0; /* the reference leaves leaf.axis uninitialised; never read */
+    nd.data[0] = n;
+    nd.data[1] = l;
+    nv_push(out, &nd);
+    st->num_leaf_nodes++;
+    return self;
+  }
+  int axis;
+  uint32_t mid = orc_split(c, l, r, bmin, bmax, &axis);
+  nd.axis = axis;
+  nd.flag = 0;
+  nv_push(out, &nd);
+  uint32_t lc = orc_build_rec(c, st, out, l, mid, depth + 1);
+  uint32_t rc = orc_build_rec(c, st, out, mid, r, depth + 1);
+  out->v[self].data[0] = lc;
+  out->v[self].data[1] = rc;
+  set_box(&out->v[self], bmin, bmax);
+  st->num_branch_nodes++;
+  return self;
+}
+
+static uint32_t orc_build_shallow_rec(build_ctx *c, orc_stats *st, node_vec *out, uint32_t l,
+                                      uint32_t r, uint32_t depth, uint32_t max_shallow) {
+  uint32_t self = (uint32_t)out->n;
+  if (st->max_tree_depth < depth) st->max_tree_depth = depth;
+  float bmin[3], bmax[3];
+  orc_range_bbox(&c->mesh, c->idx, l, r, bmin, bmax);
+  uint32_t n = r - l;
+  orc_node nd;
+  memset(&nd, 0, sizeof(nd));
+  if (n <= c->opt.min_leaf_primitives || depth >= c->opt.max_tree_depth) {
+    set_box(&nd, bmin, bmax);
+    nd.flag = 1;
+    nd.data[0] = n;
+    nd.data[1] = l;
+    nv_push(out, &nd);
+    st->num_leaf_nodes++;
+    return self;
+  }
+  if (depth >= max_shallow) {
+    if (c->n_deferred == c->cap_deferred) {
+      c->cap_deferred = c->cap_deferred ? c->cap_deferred * 2 : 32;
+      c->deferred = (deferred_t *)realloc(c->deferred, c->cap_deferred * sizeof(deferred_t));
+    }
+    c->deferred[c->n_deferred].l = l;
+    c->deferred[c->n_deferred].r = r;
+    c->deferred[c->n_deferred].offset = self;
+    c->n_deferred++;
+    nd.flag = -1;
+    nd.axis = -1;
+    nv_push(out, &nd); /* placeholder, overwritten by the join */
+    return self;
+  }
+  int axis;
+  uint32_t mid = orc_split(c, l, r, bmin, bmax, &axis);
+  nd.axis = axis;
+  nd.flag = 0;
+  nv_push(out, &nd);
+  uint32_t lc = orc_build_shallow_rec(c, st, out, l, mid, depth + 1, max_shallow);
+  uint32_t rc = orc_build_shallow_rec(c, st, out, mid, r, depth + 1, max_shallow);
+  out->v[self].data[0] = lc;
+  out->v[self].data[1] = rc;
+  set_box(&out->v[self], bmin, bmax);
+  st->num_branch_nodes++;
+  return self;
+}
+
+/*
+ * Builds the tree.  *nodes_out is malloc'ed (free with orc_free), indices_out
+ * must hold n_prims entries.  Returns the node count, 0 when n_prims == 0
+ * (reference Build returns false, nanort.h:1907-1909).
+ */
+size_t orc_build(const float *verts, size_t stride, const uint32_t *faces, uint32_t n_prims,
+                 const orc_build_options *opts, uint32_t mode, orc_node **nodes_out,
+                 uint32_t *indices_out, orc_stats *stats_out) {
+  build_ctx c;
+  memset(&c, 0, sizeof(c));
+  c.mesh.verts = (const unsigned char *)verts;
+  c.mesh.stride = stride;
+  c.mesh.faces = faces;
+  if (opts)
+    c.opt = *opts;
+  else
+    orc_default_build_options(&c.opt);
+  orc_stats st = {0, 0, 0};
+  *nodes_out = NULL;
+  if (stats_out) *stats_out = st;
+  if (n_prims == 0 || c.opt.bin_size < 2) return 0;
+  c.guard = (mode & ORC_MODE_FIXBINS) ? 3 * c.opt.bin_size : c.opt.bin_size;
+  c.idx = indices_out;
+  for (uint32_t i = 0; i < n_prims; i++) c.idx[i] = i;
+  c.bins = (orc_bin *)malloc(sizeof(orc_bin) * 3 * c.opt.bin_size);
+  node_vec out = {NULL, 0, 0};
+
+  if ((mode & ORC_MODE_CPP11) && n_prims > c.opt.min_primitives_for_parallel_build) {
+    orc_build_shallow_rec(&c, &st, &out, 0, n_prims, 0, c.opt.shallow_depth);
+    /* sub-trees are independent (disjoint index ranges), so building them one
+     * after the other gives the arrays the reference's worker threads produce;
+     * the join below follows nanort.h:2041-2067. */
+    for (size_t s = 0; s < c.n_deferred; s++) {
+      node_vec sub = {NULL, 0, 0};
+      orc_stats ls = {0, 0, 0};
+      orc_build_rec(&c, &ls, &sub, c.deferred[s].l, c.deferred[s].r, c.opt.shallow_depth);
+      uint32_t base = (uint32_t)out.n;
+      for (size_t j = 0; j < sub.n; j++) {
+        if (sub.v[j].flag == 0) {
+          sub.v[j].data[0] += base - 1;
+          sub.v[j].data[1] += base - 1;
+        }
+      }
+      out.v[c.deferred[s].offset] = sub.v[0];
+      for (size_t j = 1; j < sub.n; j++) nv_push(&out, &sub.v[j]);
+      if (ls.max_tree_depth > st.max_tree_depth) st.max_tree_depth = ls.max_tree_depth;
+      st.num_leaf_nodes += ls.num_leaf_nodes;
+      st.num_branch_nodes += ls.num_branch_nodes;
+      free(sub.v);
+    }
+  } else {
+    orc_build_rec(&c, &st, &out, 0, n_prims, 0);
+  }
+  free(c.bins);
+  free(c.deferred);
+  *nodes_out = out.v;
+  if (stats_out) *stats_out = st;
+  return out.n;
+}
+
+void orc_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------ traversal */
+typedef struct {
+  uint64_t nodes_popped; /* nanort.h:2527 */
+  uint64_t prims_tested; /* nanort.h:2397 */
+  uint32_t max_stack;    /* deepest node_stack index reached */
+} orc_counters;
+
+typedef struct {
+  float org[3];
+  float inv[3];
+  int sign[3];
+  int kx, ky, kz;
+  float Sx, Sy, Sz;
+  float t_min;
+  orc_trace_options opt;
+  /* running best */
+  float t, u, v;
+  uint32_t prim;
+} ray_state;
+
+static inline float orc_safe_inverse(float d, int cpp11) {
+  if (fabsf(d) < FLT_EPSILON) {
+    float sgn;
+    if (cpp11)
+      sgn = copysignf(1.0f, d); /* -0.0f -> -inf */
+    else
+      sgn = (d < 0.0f) ? -1.0f : 1.0f; /* -0.0f -> +inf */
+    return INFINITY * sgn;
+  }
+  return 1.0f / d;
+}
+
+static void orc_prepare(ray_state *s, const orc_ray *ray, const orc_trace_options *opt, int cpp11) {
+  for (int k = 0; k < 3; k++) {
+    s->org[k] = ray->org[k];
+    s->sign[k] = ray->dir[k] < 0.0f ? 1 : 0;
+    s->inv[k] = orc_safe_inverse(ray->dir[k], cpp11);
+  }
+  int kz = 0;
+  float m = fabsf(ray->dir[0]);
+  if (m < fabsf(ray->dir[1])) {
+    kz = 1;
+    m = fabsf(ray->dir[1]);
+  }
+  if (m < fabsf(ray->dir[2])) {
+    kz = 2;
+  }
+  int kx = kz + 1 == 3 ? 0 : kz + 1;
+  int ky = kx + 1 == 3 ? 0 : kx + 1;
+  if (ray->dir[kz] < 0.0f) {
+    int t = kx;
+    kx = ky;
+    ky = t;
+  }
+  s->kx = kx;
+  s->ky = ky;
+  s->kz = kz;
+  s->Sx = ray->dir[kx] / ray->dir[kz];
+  s->Sy = ray->dir[ky] / ray->dir[kz];
+  s->Sz = 1.0f / ray->dir[kz];
+  s->t_min = ray->min_t;
+  s->opt = *opt;
+  s->u = 0.0f;
+  s->v = 0.0f;
+}
+
+/* (a > b) ? a : b and (a < b) ? a : b, the reference's safemax / safemin */
+static inline float smax(float a, float b) { return (a > b) ? a : b; }
+static inline float smin(float a, float b) { return (a < b) ? a : b; }
+
+static inline int orc_slab(const ray_state *s, const orc_node *nd, float min_t, float max_t) {
+  float tn[3], tf[3];
+  for (int k = 0; k < 3; k++) {
+    float nearp = s->sign[k] ? nd->bmax[k] : nd->bmin[k];
+    float farp = s->sign[k] ? nd->bmin[k] : nd->bmax[k];
+    tn[k] = (nearp - s->org[k]) * s->inv[k];
+    tf[k] = ((farp - s->org[k]) * s->inv[k]) * 1.00000024f;
+  }
+  float tmin = smax(tn[2], smax(tn[1], smax(tn[0], min_t)));
+  float tmax = smin(tf[2], smin(tf[1], smin(tf[0], max_t)));
+  return tmin <= tmax;
+}
+
+static inline int orc_tri(ray_state *s, const orc_mesh *m, uint32_t prim, float *t_inout) {
+  if (prim < s->opt.prim_ids_range[0] || prim >= s->opt.prim_ids_range[1]) return 0;
+  if (prim == s->opt.skip_prim_id) return 0;
+  const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
+  const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
+  const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
+  float A[3], B[3], C[3];
+  for (int k = 0; k < 3; k++) {
+    A[k] = p0[k] - s->org[k];
+    B[k] = p1[k] - s->org[k];
+    C[k] = p2[k] - s->org[k];
+  }
+  const int kx = s->kx, ky = s->ky, kz = s->kz;
+  const float Ax = A[kx] - s->Sx * A[kz], Ay = A[ky] - s->Sy * A[kz];
+  const float Bx = B[kx] - s->Sx * B[kz], By = B[ky] - s->Sy * B[kz];
+  const float Cx = C[kx] - s->Sx * C[kz], Cy = C[ky] - s->Sy * C[kz];
+  float U = Cx * By - Cy * Bx;
+  float V = Ax * Cy - Ay * Cx;
+  float W = Bx * Ay - By * Ax;
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  if (U < 0.0f || V < 0.0f || W < 0.0f) {
+    if (s->opt.cull_back_face || U > 0.0f || V > 0.0f || W > 0.0f) return 0;
+  }
+  float det = (U + V) + W;
+  if (det == 0.0f) return 0;
+  const float Az = s->Sz * A[kz], Bz = s->Sz * B[kz], Cz = s->Sz * C[kz];
+  const float D = (U * Az + V * Bz) + W * Cz;
+  const float rcp = 1.0f / det;
+  const float tt = D * rcp;
+  if (tt > *t_inout) return 0;
+  if (tt < s->t_min) return 0;
+  *t_inout = tt;
+  s->u = V * rcp;
+  s->v = W * rcp;
+  return 1;
+}
+
+#define ORC_STACK 512
+
+/* returns 1 on hit (hit written), 0 on miss (hit untouched) */
+int orc_traverse_one(const orc_node *nodes, const uint32_t *indices, const float *verts,
+                     size_t stride, const uint32_t *faces, const orc_ray *ray,
+                     const orc_trace_options *topt, int cpp11, orc_hit *hit, orc_counters *ctr) {
+  orc_mesh m = {(const unsigned char *)verts, stride, faces};
+  orc_trace_options dflt;
+  if (!topt) {
+    orc_default_trace_options(&dflt);
+    topt = &dflt;
+  }
+  ray_state s;
+  float hit_t = ray->max_t;
+  s.t = hit_t;
+  s.prim = 0xFFFFFFFFu;
+  orc_prepare(&s, ray, topt, cpp11);
+
+  uint32_t stack[ORC_STACK];
+  int sp = 0;
+  stack[0] = 0;
+  while (sp >= 0) {
+    const orc_node *nd = &nodes[stack[sp]];
+    sp--;
+    if (ctr) ctr->nodes_popped++;
+    if (!orc_slab(&s, nd, ray->min_t, hit_t)) continue;
+    if (nd->flag == 0) {
+      int nearc = s.sign[nd->axis];
+      stack[++sp] = nd->data[1 - nearc];
+      stack[++sp] = nd->data[nearc];
+      if (ctr && (uint32_t)sp > ctr->max_stack) ctr->max_stack = (uint32_t)sp;
+    } else {
+      float t = s.t;
+      int any = 0;
+      for (uint32_t i = 0; i < nd->data[0]; i++) {
+        uint32_t prim = indices[nd->data[1] + i];
+        float lt = t;
+        if (ctr) ctr->prims_tested++;
+        if (orc_tri(&s, &m, prim, &lt)) {
+          t = lt;
+          s.t = t;
+          s.prim = prim;
+          any = 1;
+        }
+      }
+      if (any) hit_t = s.t;
+    }
+  }
+  int is_hit = s.t < ray->max_t;
+  if (is_hit && hit) {
+    hit->t = s.t;
+    hit->u = s.u;
+    hit->v = s.v;
+    hit->prim_id = s.prim;
+  }
+  return is_hit;
+}
+
+typedef struct {
+  const orc_node *nodes;
+  const uint32_t *indices;
+  const float *verts;
+  size_t stride;
+  const uint32_t *faces;
+  const orc_ray *rays;
+  size_t n_rays;
+  orc_hit *hits;
+  uint8_t *mask;
+  const orc_trace_options *topt;
+  int cpp11;
+  int want_counters;
+  size_t *next; /* shared chunk cursor */
+  pthread_mutex_t *mu;
+  size_t n_hits;
+  orc_counters ctr;
+} batch_job;
+
+static void *batch_worker(void *arg) {
+  batch_job *j = (batch_job *)arg;
+  const size_t chunk = 1024;
+  for (;;) {
+    pthread_mutex_lock(j->mu);
+    size_t b = *j->next;
+    *j->next = b + chunk;
+    pthread_mutex_unlock(j->mu);
+    if (b >= j->n_rays) break;
+    size_t e = b + chunk < j->n_rays ? b + chunk : j->n_rays;
+    for (size_t i = b; i < e; i++) {
+      int h = orc_traverse_one(j->nodes, j->indices, j->verts, j->stride, j->faces, &j->rays[i],
+                               j->topt, j->cpp11, &j->hits[i], j->want_counters ? &j->ctr : NULL);
+      if (j->mask) j->mask[i] = (uint8_t)h;
+      j->n_hits += (size_t)h;
+    }
+  }
+  return NULL;
+}
+
+/* hits[i] is written only where mask[i] == 1 (reference semantics, nanort.h:1205-1213) */
+size_t orc_traverse_batch(const orc_node *nodes, const uint32_t *indices, const float *verts,
+                          size_t stride, const uint32_t *faces, const orc_ray *rays, size_t n_rays,
+                          orc_hit *hits, uint8_t *mask, const orc_trace_options *topt, int cpp11,
+                          int n_threads, orc_counters *ctr_out) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  size_t next = 0;
+  pthread_mutex_t mu;
+  pthread_mutex_init(&mu, NULL);
+  batch_job *jobs = (batch_job *)calloc((size_t)n_threads, sizeof(batch_job));
+  pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+  for (int t = 0; t < n_threads; t++) {
+    batch_job *j = &jobs[t];
+    j->nodes = nodes;
+    j->indices = indices;
+    j->verts = verts;
+    j->stride = stride;
+    j->faces = faces;
+    j->rays = rays;
+    j->n_rays = n_rays;
+    j->hits = hits;
+    j->mask = mask;
+    j->topt = topt;
+    j->cpp11 = cpp11;
+    j->want_counters = ctr_out != NULL;
+    j->next = &next;
+    j->mu = &mu;
+  }
+  if (n_threads == 1) {
+    batch_worker(&jobs[0]);
+  } else {
+    for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  }
+  size_t total = 0;
+  orc_counters c = {0, 0, 0};
+  for (int t = 0; t < n_threads; t++) {
+    total += jobs[t].n_hits;
+    c.nodes_popped += jobs[t].ctr.nodes_popped;
+    c.prims_tested += jobs[t].ctr.prims_tested;
+    if (jobs[t].ctr.max_stack > c.max_stack) c.max_stack = jobs[t].ctr.max_stack;
+  }
+  if (ctr_out) *ctr_out = c;
+  free(jobs);
+  free(th);
+  pthread_mutex_destroy(&mu);
+  return total;
+}
+
+/* Re-tests ONE primitive for ONE ray with the reference arithmetic; used by the
+ * parity checker to classify exact-t ties: returns 1 and the
+ * (t,u,v) this primitive alone would report with t_inout = max_t. */
+int orc_test_prim(const float *verts, size_t stride, const uint32_t *faces, const orc_ray *ray,
+                  const orc_trace_options *topt, int cpp11, uint32_t prim, orc_hit *out) {
+  orc_mesh m = {(const unsigned char *)verts, stride, faces};
+  orc_trace_options dflt;
+  if (!topt) {
+    orc_default_trace_options(&dflt);
+    topt = &dflt;
+  }
+  ray_state s;
+  orc_prepare(&s, ray, topt, cpp11);
+  float t = ray->max_t;
+  if (!orc_tri(&s, &m, prim, &t)) return 0;
+  out->t = t;
+  out->u = s.u;
+  out->v = s.v;
+  out->prim_id = prim;
+  return 1;
+}
