@@ -1,0 +1,156 @@
+/*
+ * nanort_b200.h -- the C-ABI boundary of the B200-native nanort hot path.
+ *
+ * nanort itself has no binary interface: its "plugin API" is the set of C++
+ * templates in nanort.h.  This header is the extern "C"
+ * surface that a drop-in nanort.h facade (include/nanort.h in this repository)
+ * binds instead of running the templates on the CPU.  Plain pointers and sizes
+ * only; every record keeps nanort's byte layout:
+ *
+ *   ray   36 B  nanort::Ray<float>                  /root/reference/nanort.h:474-496
+ *   hit   16 B  nanort::TriangleIntersection<float> nanort.h:996-1005  {u, v, t, prim_id}
+ *   node  40 B  nanort::BVHNode<float>              nanort.h:498-550
+ *   build options 28 B  nanort::BVHBuildOptions<float>  nanort.h:559-583
+ *   build stats   16 B  nanort::BVHBuildStatistics      nanort.h:586-599
+ *   trace options 16 B  nanort::BVHTraceOptions         nanort.h:604-624
+ *
+ * All functions return NRT_OK (0) or a negative error code; nrt_last_error()
+ * gives the message of the calling thread's last failure.  There is no CPU
+ * fallback: without a usable CUDA device every entry point fails with
+ * NRT_ERR_CUDA.
+ */
+#ifndef NANORT_B200_H_
+#define NANORT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRT_OK 0
+#define NRT_ERR_INVALID -1  /* bad argument (null pointer, n_prims == 0 -> Build returns false, nanort.h:1907) */
+#define NRT_ERR_CUDA -2     /* CUDA runtime / launch failure, or no device */
+#define NRT_ERR_NOMEM -3
+
+/* nrt_traverse* flags */
+#define NRT_TRAVERSE_FAST 0u         /* private 64-B child-pair layout, near-child-by-distance order      */
+#define NRT_TRAVERSE_CONFORMANCE 1u  /* walk the nanort 40-B node array in the reference's exact order
+                                        (nanort.h:2526-2547): identical winners even for exact-t ties   */
+#define NRT_TRAVERSE_CPP03_INVERSE 2u /* vsafe_inverse sign convention of the C++03 build (nanort.h:440-462:
+                                        -0.0f -> +inf).  Default is the C++11 one (copysign, :418-439)   */
+
+typedef struct nrt_accel nrt_accel; /* opaque: device-resident BVH + host mirrors */
+
+const char *nrt_last_error(void);
+int nrt_device_count(void);
+/* Device used by subsequently created accels of this thread (default 0). */
+int nrt_set_device(int device);
+
+/*
+ * Replaces BVHAccel<float>::Build<TriangleMesh<float>, TriangleSAHPred<float>>
+ * (nanort.h:1892-2149; caller examples/path_tracer/main.cc:752-763).
+ * verts/faces are HOST pointers laid out as TriangleMesh takes them
+ * (nanort.h:925-930): vertex i at (char*)verts + i*stride_bytes, 3 uint32 per
+ * face.  They are copied to the device; unlike the reference the pointers need
+ * not outlive the call.  n_verts == 0 derives max(face index)+1.
+ * build_opts_28B == NULL uses the defaults of nanort.h:574-582.
+ * Returns NRT_ERR_INVALID for n_prims == 0 (reference: Build returns false).
+ */
+int nrt_build(const float *verts, size_t stride_bytes, size_t n_verts, const uint32_t *faces,
+              uint32_t n_prims, const void *build_opts_28B, nrt_accel **out);
+
+/*
+ * Conformance entry: adopt an existing nanort-layout tree (e.g. one built by
+ * the CPU reference; BVHAccel::GetNodes()/GetIndices(), nanort.h:786-787, or
+ * the Dump format nanort.h:2164-2220) so the GPU traverses exactly that tree.
+ */
+int nrt_adopt(const void *nodes_40B, size_t n_nodes, const uint32_t *indices, size_t n_indices,
+              const float *verts, size_t stride_bytes, size_t n_verts, const uint32_t *faces,
+              uint32_t n_prims, nrt_accel **out);
+
+void nrt_free(nrt_accel *a);
+
+/* BVHAccel::GetStatistics (nanort.h:725): {max_tree_depth, num_leaf_nodes, num_branch_nodes, build_secs}.
+ * build_secs is the device time of the build kernels (the reference never fills it, nanort.h:591). */
+int nrt_stats(const nrt_accel *a, void *stats_16B);
+/* BVHAccel::BoundingBox (nanort.h:792-804). */
+int nrt_bounding_box(const nrt_accel *a, float bmin[3], float bmax[3]);
+/* BVHAccel::GetNodes / GetIndices (nanort.h:786-787): host mirror in nanort layout, downloaded on
+ * first use and owned by the accel. */
+int nrt_nodes(nrt_accel *a, const void **nodes_40B, size_t *n_nodes, const uint32_t **indices,
+              size_t *n_indices);
+
+/*
+ * Replaces a loop of BVHAccel<float>::Traverse<TriangleIntersector<float>,
+ * TriangleIntersection<float>> calls (nanort.h:2487-2556; callers
+ * examples/path_tracer/main.cc:854 and :696).  HOST buffers; the call copies
+ * rays up, traverses and copies results back, pipelined in chunks, and returns
+ * when hits/hit_mask are complete.  hit_mask[i] = 1/0 is Traverse's return
+ * value.  hits[i] = {u,v,t,prim_id} for hits; for misses the record is
+ * {0, 0, ray.max_t, 0xFFFFFFFF} (the reference leaves *isect untouched on a
+ * miss, nanort.h:1205-1213 -- the nanort.h facade restores that per ray).
+ * trace_opts_16B == NULL -> defaults of nanort.h:617-623.  hit_mask may be NULL.
+ */
+int nrt_traverse(const nrt_accel *a, const void *rays_36B, size_t n_rays, void *hits_16B,
+                 uint8_t *hit_mask, const void *trace_opts_16B, uint32_t flags);
+
+/* Same with DEVICE pointers on `stream` (a cudaStream_t, NULL = default stream); asynchronous. */
+int nrt_traverse_device(const nrt_accel *a, const void *d_rays_36B, size_t n_rays, void *d_hits_16B,
+                        uint8_t *d_hit_mask, const void *trace_opts_16B, uint32_t flags, void *stream);
+
+/*
+ * Counting variant (not timed anywhere): walks the same rays and returns the totals the roofline
+ * arithmetic needs: boxes tested (one per 40-B nanort node the reference's
+ * Traverse would pop on this tree, nanort.h:2527) and triangles tested (Intersect calls, :2397).
+ */
+int nrt_traverse_count_device(const nrt_accel *a, const void *d_rays_36B, size_t n_rays,
+                              const void *trace_opts_16B, uint32_t flags, uint64_t *boxes_tested,
+                              uint64_t *prims_tested, void *stream);
+
+/* Pinned host memory for ray / hit buffers handed to nrt_traverse (plain memory works too, slower). */
+void *nrt_host_alloc(size_t bytes);
+void nrt_host_free(void *p);
+
+/*
+ * Device-resident wavefront pass for the headline metric: jittered pinhole primary rays (the camera of
+ * examples/path_tracer/main.cc:809-817, 839-849) -> Traverse -> one cosine-hemisphere AO ray per hit
+ * (hit point main.cc:860, geometric normal :306-312 flipped to the viewer :878-881, ONB + cosine
+ * direction :216-250, closest-hit occlusion query as CheckForOccluder :675-701) -> Traverse ->
+ * accumulate visibility.  Pixels are taken from tiles of tile_w x tile_h pixels; tile k belongs to
+ * shard (k % n_shards) -- this is how the work is split across GPUs.
+ */
+typedef struct nrt_ao_params {
+  float cam[12];        /* org, right*sx, up*sy, forward (nanort_b200/scenes.py:look_at) */
+  uint32_t width, height;
+  uint32_t spp;         /* samples per pixel in this call */
+  uint32_t sample0;     /* index of the first sample (for progressive calls) */
+  uint32_t seed;
+  uint32_t tile_w, tile_h;
+  uint32_t shard, n_shards;
+  float ray_min_t, ray_max_t;
+  float ao_min_t, ao_max_t;
+  uint32_t flags;       /* NRT_TRAVERSE_* */
+} nrt_ao_params;
+
+typedef struct nrt_ao_result {
+  uint64_t primary_rays;
+  uint64_t ao_rays;     /* == primary hits */
+  uint64_t ao_hits;     /* occluded AO rays */
+  float traverse_ms;    /* device time spent inside the traversal kernels (CUDA events) */
+  float total_ms;       /* device time of the whole pass */
+  uint32_t launches;    /* kernels launched by this call */
+  uint32_t traverse_launches;
+} nrt_ao_result;
+
+/* d_accum: DEVICE float[width*height] accumulating sum of visibility (1 = unoccluded, 0.0 for primary
+ * misses counted as 1); only this shard's pixels are touched.  Asynchronous w.r.t. the host except for
+ * the final read-back of the counters in *res (res may be NULL to skip that sync). */
+int nrt_render_ao_device(const nrt_accel *a, const nrt_ao_params *p, float *d_accum, nrt_ao_result *res,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANORT_B200_H_ */

@@ -1,0 +1,294 @@
+"""Python host side of the C-ABI (include/nanort_b200.h), mirroring nanort's own interface.
+
+Names and argument meaning follow the reference header (/root/reference/nanort.h):
+`BVHBuildOptions`, `BVHTraceOptions`, `BVHAccel.Build / Traverse / GetNodes / GetIndices /
+GetStatistics / BoundingBox / IsValid` (nanort.h:559-624, 699-860).  `Traverse` takes a whole
+array of 36-byte rays instead of one ray -- the batch form of the per-ray call.
+
+All compute happens in nanort_b200/libnanort_b200.so (hand-written sm_100a CUDA).  There is no CPU
+fallback: if the library or a CUDA device is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .scenes import HIT_DTYPE, NODE_DTYPE, RAY_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnanort_b200.so")
+
+TRAVERSE_FAST = 0
+TRAVERSE_CONFORMANCE = 1
+TRAVERSE_CPP03_INVERSE = 2
+
+BUILD_OPT_DTYPE = np.dtype(
+    [
+        ("cost_t_aabb", "<f4"),
+        ("min_leaf_primitives", "<u4"),
+        ("max_tree_depth", "<u4"),
+        ("bin_size", "<u4"),
+        ("shallow_depth", "<u4"),
+        ("min_primitives_for_parallel_build", "<u4"),
+        ("cache_bbox", "u1"),
+        ("pad", "u1", (3,)),
+    ]
+)
+TRACE_OPT_DTYPE = np.dtype(
+    [("prim_ids_range", "<u4", (2,)), ("skip_prim_id", "<u4"), ("cull_back_face", "u1"), ("pad", "u1", (3,))]
+)
+STATS_DTYPE = np.dtype(
+    [("max_tree_depth", "<u4"), ("num_leaf_nodes", "<u4"), ("num_branch_nodes", "<u4"), ("build_secs", "<f4")]
+)
+
+# every symbol include/nanort_b200.h declares
+EXPORTS = [
+    "nrt_last_error", "nrt_device_count", "nrt_set_device", "nrt_build", "nrt_adopt", "nrt_free", "nrt_stats",
+    "nrt_bounding_box", "nrt_nodes", "nrt_traverse", "nrt_traverse_device", "nrt_traverse_count_device",
+    "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device",
+]
+
+
+class NanortB200Error(RuntimeError):
+    pass
+
+
+class AoParams(C.Structure):
+    _fields_ = [
+        ("cam", C.c_float * 12),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("spp", C.c_uint32), ("sample0", C.c_uint32), ("seed", C.c_uint32),
+        ("tile_w", C.c_uint32), ("tile_h", C.c_uint32),
+        ("shard", C.c_uint32), ("n_shards", C.c_uint32),
+        ("ray_min_t", C.c_float), ("ray_max_t", C.c_float),
+        ("ao_min_t", C.c_float), ("ao_max_t", C.c_float),
+        ("flags", C.c_uint32),
+    ]
+
+
+class AoResult(C.Structure):
+    _fields_ = [
+        ("primary_rays", C.c_uint64), ("ao_rays", C.c_uint64), ("ao_hits", C.c_uint64),
+        ("traverse_ms", C.c_float), ("total_ms", C.c_float),
+        ("launches", C.c_uint32), ("traverse_launches", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NanortB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nanort_b200 has no CPU fallback)"
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u32, u64p = C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint64)
+    L.nrt_last_error.restype = C.c_char_p
+    L.nrt_device_count.restype = C.c_int
+    L.nrt_set_device.argtypes = [C.c_int]
+    L.nrt_build.argtypes = [vp, sz, sz, vp, u32, vp, C.POINTER(vp)]
+    L.nrt_adopt.argtypes = [vp, sz, vp, sz, vp, sz, sz, vp, u32, C.POINTER(vp)]
+    L.nrt_free.argtypes = [vp]
+    L.nrt_free.restype = None
+    L.nrt_stats.argtypes = [vp, vp]
+    L.nrt_bounding_box.argtypes = [vp, vp, vp]
+    L.nrt_nodes.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
+    L.nrt_traverse.argtypes = [vp, vp, sz, vp, vp, vp, u32]
+    L.nrt_traverse_device.argtypes = [vp, vp, sz, vp, vp, vp, u32, vp]
+    L.nrt_traverse_count_device.argtypes = [vp, vp, sz, vp, u32, u64p, u64p, vp]
+    L.nrt_host_alloc.argtypes = [sz]
+    L.nrt_host_alloc.restype = vp
+    L.nrt_host_free.argtypes = [vp]
+    L.nrt_host_free.restype = None
+    L.nrt_render_ao_device.argtypes = [vp, C.POINTER(AoParams), vp, C.POINTER(AoResult), vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise NanortB200Error(f"nanort_b200 error {rc}: {lib().nrt_last_error().decode()}")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def BVHBuildOptions(**kw):
+    """nanort::BVHBuildOptions<float> with the reference defaults (nanort.h:574-582)."""
+    o = np.zeros(1, BUILD_OPT_DTYPE)
+    o["cost_t_aabb"] = 0.2
+    o["min_leaf_primitives"] = 4
+    o["max_tree_depth"] = 256
+    o["bin_size"] = 64
+    o["shallow_depth"] = 4
+    o["min_primitives_for_parallel_build"] = 8192
+    for k, v in kw.items():
+        o[k] = v
+    return o
+
+
+def BVHTraceOptions(**kw):
+    """nanort::BVHTraceOptions with the reference defaults (nanort.h:617-623)."""
+    o = np.zeros(1, TRACE_OPT_DTYPE)
+    o["prim_ids_range"] = (0, 0x7FFFFFFF)
+    o["skip_prim_id"] = 0xFFFFFFFF
+    for k, v in kw.items():
+        o[k] = v
+    return o
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (nrt_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self._ptr = lib().nrt_host_alloc(max(n, 1))
+        if not self._ptr:
+            raise NanortB200Error("nrt_host_alloc failed: " + lib().nrt_last_error().decode())
+        buf = (C.c_char * max(n, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().nrt_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BVHAccel:
+    """nanort::BVHAccel<float> over TriangleMesh / TriangleSAHPred / TriangleIntersector."""
+
+    def __init__(self, device: int | None = None):
+        self._h = None
+        self._device = device
+
+    # -- lifetime
+    def _set_device(self):
+        if self._device is not None:
+            _check(lib().nrt_set_device(int(self._device)))
+
+    def free(self):
+        if self._h:
+            lib().nrt_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def IsValid(self):
+        return self._h is not None
+
+    # -- build
+    def Build(self, num_primitives, vertices, faces, options=None, vertex_stride_bytes=12):
+        """BVHAccel::Build(num_primitives, TriangleMesh(vertices, faces, stride), pred, options)
+        (nanort.h:716-718).  Returns False for num_primitives == 0 like the reference."""
+        self.free()
+        if num_primitives == 0:
+            return False
+        vertices = np.ascontiguousarray(vertices, np.float32)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        self._set_device()
+        h = C.c_void_p()
+        n_verts = vertices.size * 4 // vertex_stride_bytes
+        _check(lib().nrt_build(_p(vertices), vertex_stride_bytes, n_verts, _p(faces), int(num_primitives),
+                               _p(options), C.byref(h)))
+        self._h = h
+        return True
+
+    def Adopt(self, nodes, indices, vertices, faces, vertex_stride_bytes=12):
+        """Conformance entry: traverse an existing nanort-layout tree (nrt_adopt)."""
+        self.free()
+        nodes = np.ascontiguousarray(nodes)
+        assert nodes.dtype.itemsize == 40
+        indices = np.ascontiguousarray(indices, np.uint32)
+        vertices = np.ascontiguousarray(vertices, np.float32)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        self._set_device()
+        h = C.c_void_p()
+        n_verts = vertices.size * 4 // vertex_stride_bytes
+        _check(lib().nrt_adopt(_p(nodes), len(nodes), _p(indices), len(indices), _p(vertices), vertex_stride_bytes,
+                               n_verts, _p(faces), faces.size // 3, C.byref(h)))
+        self._h = h
+        return True
+
+    # -- accessors
+    def GetStatistics(self):
+        s = np.zeros(1, STATS_DTYPE)
+        _check(lib().nrt_stats(self._h, _p(s)))
+        return {k: s[k][0].item() for k in STATS_DTYPE.names}
+
+    def BoundingBox(self):
+        if not self._h:  # nanort.h:793-795
+            m = np.finfo(np.float32).max
+            return np.full(3, m, np.float32), np.full(3, -m, np.float32)
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        _check(lib().nrt_bounding_box(self._h, _p(a), _p(b)))
+        return a, b
+
+    def _mirrors(self):
+        pn, pi = C.c_void_p(), C.c_void_p()
+        nn, ni = C.c_size_t(), C.c_size_t()
+        _check(lib().nrt_nodes(self._h, C.byref(pn), C.byref(nn), C.byref(pi), C.byref(ni)))
+        nodes = np.frombuffer((C.c_char * (nn.value * 40)).from_address(pn.value), NODE_DTYPE)
+        idx = np.frombuffer((C.c_char * (ni.value * 4)).from_address(pi.value), np.uint32)
+        return nodes, idx
+
+    def GetNodes(self):
+        return self._mirrors()[0].copy()
+
+    def GetIndices(self):
+        return self._mirrors()[1].copy()
+
+    # -- traversal
+    def Traverse(self, rays, options=None, flags=TRAVERSE_FAST, hits=None, mask=None):
+        """Batch of BVHAccel::Traverse calls on HOST arrays (nrt_traverse): returns (hits, mask);
+        mask[i] is Traverse's bool, hits[i] = {u,v,t,prim_id} where mask[i] == 1."""
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype.itemsize == 36
+        n = len(rays)
+        if hits is None:
+            hits = np.zeros(n, HIT_DTYPE)
+        if mask is None:
+            mask = np.zeros(n, np.uint8)
+        _check(lib().nrt_traverse(self._h, _p(rays), n, _p(hits), _p(mask), _p(options), int(flags)))
+        return hits, mask
+
+    def TraverseDevice(self, d_rays_ptr, n, d_hits_ptr, d_mask_ptr=None, options=None, flags=TRAVERSE_FAST,
+                       stream=None):
+        """Device-pointer form (nrt_traverse_device); pointers are ints (e.g. torch.Tensor.data_ptr())."""
+        _check(lib().nrt_traverse_device(self._h, C.c_void_p(d_rays_ptr), int(n), C.c_void_p(d_hits_ptr),
+                                         C.c_void_p(d_mask_ptr) if d_mask_ptr else None, _p(options), int(flags),
+                                         C.c_void_p(stream) if stream else None))
+
+    def CountDevice(self, d_rays_ptr, n, options=None, flags=TRAVERSE_FAST, stream=None):
+        """Visit counters for the roofline arithmetic (nrt_traverse_count_device)."""
+        b, p = C.c_uint64(), C.c_uint64()
+        _check(lib().nrt_traverse_count_device(self._h, C.c_void_p(d_rays_ptr), int(n), _p(options), int(flags),
+                                               C.byref(b), C.byref(p), C.c_void_p(stream) if stream else None))
+        return b.value, p.value
+
+    def RenderAO(self, params: AoParams, d_accum_ptr, stream=None, want_result=True):
+        res = AoResult()
+        _check(lib().nrt_render_ao_device(self._h, C.byref(params), C.c_void_p(d_accum_ptr),
+                                          C.byref(res) if want_result else None,
+                                          C.c_void_p(stream) if stream else None))
+        return res

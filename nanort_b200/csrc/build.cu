@@ -1,0 +1,1011 @@
+// Device-wide binned-SAH BVH builder (sm_100a), emitting nanort's own arrays.
+//
+// Replaces (file:line under /root/reference):
+//   BVHAccel<float>::Build / BuildTree / BuildShallowTree  nanort.h:1892-2149, 1759-1890, 1600-1757
+//   ContributeBinBuffer / FindCutFromBinBuffer             nanort.h:1314-1367, 1381-1430
+//   CalculateSurfaceArea                                    nanort.h:1278-1283
+//   TriangleMesh::BoundingBoxAndCenter                      nanort.h:958-971
+//   TriangleSAHPred + std::partition                        nanort.h:897-911, 1841
+//   ComputeBoundingBox*                                     nanort.h:1432-1594
+//
+// Semantics kept: leaf iff n <= min_leaf_primitives || depth >= max_tree_depth; root
+// depth 0; node boxes are the exact min/max of the member triangles; `bin_size` centroid bins per axis
+// over the NODE's box, centroid = (p0+p1+p2)*(1/3); candidate planes are bin boundaries; cost =
+// N_L*area(L) + N_R*area(R), area = 2*(dx*dy + dy*dz + dz*dx); strict `<` argmin along an axis, ties
+// between axes go to the lower axis; data[0] is the child on the lower side; when no plane separates the
+// centroids the range is cut at the median index; nodes come out in depth-first pre-order (the order of
+// the reference's serial BuildTree), indices_ holds original primitive ids.
+// Deliberate differences, both documented in DESIGN.md: all three axes are binned (the pinned commit
+// bins only x because of the guard at nanort.h:1357), and a primitive goes left iff its
+// centroid's BIN is below the chosen boundary (the reference re-evaluates p0+p1+p2 < 3*pos, which can
+// differ from its own binning by one rounding).
+//
+// Structure: (A) level-synchronous passes over all primitives for nodes with more than kSubtree
+// primitives -- block-private shared-memory bins flushed with atomics, one warp per node for the sweep,
+// a device-wide scan + stable scatter for the partition; (B) one CTA per remaining subtree builds it to
+// the leaves entirely in shared memory; (C) pre-order indices are computed in closed form from
+// (leaves to the left, depth, right turns) and the 40-byte nodes are emitted in one pass.
+#include <float.h>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace nrt {
+
+namespace {
+
+constexpr uint32_t kInactive = 0xFFFFFFFFu;
+constexpr uint32_t kMedian = 0xFFFFFFFEu;
+constexpr int kSubtree = 512;     // phase B handles nodes with at most this many primitives
+constexpr int kSubBlock = 128;    // threads per phase-B CTA
+constexpr int kMaxBins = 256;     // bin_size limit of this implementation
+constexpr int kBinWords = 8;      // count, min xyz, max xyz, pad
+
+struct BNode {  // 64 bytes
+  float bmin[3];
+  uint32_t l;
+  float bmax[3];
+  uint32_t r;
+  uint32_t left;   // pool index of the left child (right = left + 1); kInactive for a leaf
+  uint32_t depth;
+  uint32_t rturns;  // right turns on the root path
+  uint32_t axis;
+  uint32_t split_bin;  // left iff bin < split_bin; kMedian = cut at the median index
+  uint32_t nleft;
+  uint32_t slot;  // index in the current level's active list; kInactive otherwise
+  uint32_t pad;
+};
+static_assert(sizeof(BNode) == 64, "BNode");
+
+struct BuildCounters {
+  uint32_t pool;        // nodes allocated
+  uint32_t n_active[2]; // phase-A active lists (ping-pong)
+  uint32_t n_subtrees;
+  uint32_t max_depth;
+  uint32_t n_leaves;
+  uint32_t error;
+  uint32_t pad;
+};
+
+// order-preserving float <-> uint key for atomicMin / atomicMax
+__device__ __forceinline__ uint32_t fkey(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float funkey(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+__device__ __forceinline__ float box_area(float lx, float ly, float lz, float hx, float hy, float hz) {
+  float dx = hx - lx, dy = hy - ly, dz = hz - lz;
+  return 2.0f * ((dx * dy + dy * dz) + dz * dx);
+}
+
+__device__ __forceinline__ int bin_of(float c, float nmin, float inv, int B) {
+  float q = (c - nmin) * inv;
+  int qi = (int)q;  // truncation, as the reference's int(quantized_center[j])
+  qi = qi < 0 ? 0 : qi;
+  return qi > B - 1 ? B - 1 : qi;
+}
+
+__device__ __forceinline__ float inv_extent(float lo, float hi, int B) {
+  float sz = hi - lo;
+  return sz > 0.0f ? (float)B / sz : 0.0f;
+}
+
+// ------------------------------------------------------------------ primitives
+// plo = (bmin.xyz, c.x), phi = (bmax.xyz, c.y), pcz = c.z
+__global__ void prim_setup_kernel(const float *__restrict__ verts, const uint32_t *__restrict__ faces, uint32_t n,
+                                  float4 *__restrict__ plo, float4 *__restrict__ phi, float *__restrict__ pcz,
+                                  uint32_t *__restrict__ scene_keys /*6*/) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (i < n) {
+    uint32_t f0 = faces[3 * (size_t)i], f1 = faces[3 * (size_t)i + 1], f2 = faces[3 * (size_t)i + 2];
+    const float *p0 = verts + 3 * (size_t)f0, *p1 = verts + 3 * (size_t)f1, *p2 = verts + 3 * (size_t)f2;
+    float c[3];
+    const float third = 1.0f / 3.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float a = p0[k], b = p1[k], cc = p2[k];
+      lo[k] = fminf(a, fminf(b, cc));
+      hi[k] = fmaxf(a, fmaxf(b, cc));
+      c[k] = ((a + b) + cc) * third;
+    }
+    plo[i] = make_float4(lo[0], lo[1], lo[2], c[0]);
+    phi[i] = make_float4(hi[0], hi[1], hi[2], c[1]);
+    pcz[i] = c[2];
+  }
+  // scene box: warp reduce, then one atomic per warp and component
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float a = lo[k], b = hi[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xFFFFFFFFu, a, o));
+      b = fmaxf(b, __shfl_xor_sync(0xFFFFFFFFu, b, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(scene_keys + k, fkey(a));
+      atomicMax(scene_keys + 3 + k, fkey(b));
+    }
+  }
+}
+
+__global__ void init_build_kernel(BNode *pool, BuildCounters *ctr, const uint32_t *scene_keys, uint32_t n,
+                                  uint32_t min_leaf, uint32_t max_depth, uint32_t *active0, uint32_t *subtrees) {
+  BNode r;
+  for (int k = 0; k < 3; k++) {
+    r.bmin[k] = funkey(scene_keys[k]);
+    r.bmax[k] = funkey(scene_keys[3 + k]);
+  }
+  r.l = 0;
+  r.r = n;
+  r.left = kInactive;
+  r.depth = 0;
+  r.rturns = 0;
+  r.axis = 0;
+  r.split_bin = 0;
+  r.nleft = 0;
+  r.slot = kInactive;
+  r.pad = 0;
+  ctr->pool = 1;
+  ctr->n_active[0] = ctr->n_active[1] = 0;
+  ctr->n_subtrees = 0;
+  ctr->max_depth = 0;
+  ctr->n_leaves = 0;
+  ctr->error = 0;
+  if (n <= min_leaf || max_depth == 0) {
+    // single leaf
+  } else if (n <= (uint32_t)kSubtree) {
+    subtrees[0] = 0;
+    ctr->n_subtrees = 1;
+  } else {
+    active0[0] = 0;
+    r.slot = 0;
+    ctr->n_active[0] = 1;
+  }
+  pool[0] = r;
+}
+
+__global__ void iota_kernel(uint32_t *a, uint32_t *b, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    a[i] = i;
+    b[i] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ phase A: binning
+// Global bins: [slot][axis][bin][kBinWords] uint32 {count, kmin xyz, kmax xyz, -}
+__global__ void __launch_bounds__(256)
+    bin_large_kernel(const BNode *__restrict__ pool, const uint32_t *__restrict__ node_of,
+                     const uint32_t *__restrict__ idx, const float4 *__restrict__ plo,
+                     const float4 *__restrict__ phi, const float *__restrict__ pcz, uint32_t n, int B,
+                     uint32_t *__restrict__ bins) {
+  extern __shared__ uint32_t sbin[];  // 3*B*kBinWords when the tile lies inside one node
+  const uint32_t tile0 = blockIdx.x * 1024u;
+  const uint32_t tile1 = min(tile0 + 1024u, n);
+  const uint32_t first_node = node_of[tile0];
+  const bool uniform = (first_node == node_of[tile1 - 1]);
+  if (uniform) {
+    BNode nd = pool[first_node];
+    if (nd.slot == kInactive) return;  // whole tile belongs to a finished / phase-B node
+    for (int i = threadIdx.x; i < 3 * B * kBinWords; i += 256) {
+      int w = i & (kBinWords - 1);
+      sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
+    }
+    __syncthreads();
+    float ivx = inv_extent(nd.bmin[0], nd.bmax[0], B), ivy = inv_extent(nd.bmin[1], nd.bmax[1], B),
+          ivz = inv_extent(nd.bmin[2], nd.bmax[2], B);
+    for (uint32_t p = tile0 + threadIdx.x; p < tile1; p += 256) {
+      uint32_t s = idx[p];
+      float4 lo = plo[s], hi = phi[s];
+      float cz = pcz[s];
+      int b3[3] = {bin_of(lo.w, nd.bmin[0], ivx, B), bin_of(hi.w, nd.bmin[1], ivy, B), bin_of(cz, nd.bmin[2], ivz, B)};
+      uint32_t kl[3] = {fkey(lo.x), fkey(lo.y), fkey(lo.z)}, kh[3] = {fkey(hi.x), fkey(hi.y), fkey(hi.z)};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        uint32_t *w = sbin + ((size_t)a * B + b3[a]) * kBinWords;
+        atomicAdd(w, 1u);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          atomicMin(w + 1 + k, kl[k]);
+          atomicMax(w + 4 + k, kh[k]);
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t *g = bins + (size_t)nd.slot * 3 * B * kBinWords;
+    for (int i = threadIdx.x; i < 3 * B; i += 256) {
+      const uint32_t *w = sbin + (size_t)i * kBinWords;
+      if (w[0] == 0u) continue;
+      uint32_t *gw = g + (size_t)i * kBinWords;
+      atomicAdd(gw, w[0]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        atomicMin(gw + 1 + k, w[1 + k]);
+        atomicMax(gw + 4 + k, w[4 + k]);
+      }
+    }
+  } else {
+    for (uint32_t p = tile0 + threadIdx.x; p < tile1; p += 256) {
+      BNode nd = pool[node_of[p]];
+      if (nd.slot == kInactive) continue;
+      uint32_t s = idx[p];
+      float4 lo = plo[s], hi = phi[s];
+      float cz = pcz[s];
+      int b3[3] = {bin_of(lo.w, nd.bmin[0], inv_extent(nd.bmin[0], nd.bmax[0], B), B),
+                   bin_of(hi.w, nd.bmin[1], inv_extent(nd.bmin[1], nd.bmax[1], B), B),
+                   bin_of(cz, nd.bmin[2], inv_extent(nd.bmin[2], nd.bmax[2], B), B)};
+      uint32_t kl[3] = {fkey(lo.x), fkey(lo.y), fkey(lo.z)}, kh[3] = {fkey(hi.x), fkey(hi.y), fkey(hi.z)};
+      uint32_t *g = bins + (size_t)nd.slot * 3 * B * kBinWords;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        uint32_t *w = g + ((size_t)a * B + b3[a]) * kBinWords;
+        atomicAdd(w, 1u);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          atomicMin(w + 1 + k, kl[k]);
+          atomicMax(w + 4 + k, kh[k]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void clear_bins_kernel(uint32_t *bins, size_t words) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < words) {
+    int w = (int)(i & (kBinWords - 1));
+    bins[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
+  }
+}
+
+// ------------------------------------------------------------------ SAH sweep (one warp, one axis)
+struct Box6 {
+  float v[6];  // min xyz, max xyz
+};
+__device__ __forceinline__ void box_empty(Box6 &b) {
+  b.v[0] = b.v[1] = b.v[2] = FLT_MAX;
+  b.v[3] = b.v[4] = b.v[5] = -FLT_MAX;
+}
+__device__ __forceinline__ void box_merge_bin(Box6 &b, const uint32_t *w) {
+  if (w[0] == 0u) return;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b.v[k] = fminf(b.v[k], funkey(w[1 + k]));
+    b.v[3 + k] = fmaxf(b.v[3 + k], funkey(w[4 + k]));
+  }
+}
+__device__ __forceinline__ void box_merge(Box6 &b, const Box6 &o) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    b.v[k] = fminf(b.v[k], o.v[k]);
+    b.v[3 + k] = fmaxf(b.v[3 + k], o.v[3 + k]);
+  }
+}
+
+// For one axis (bins: B x kBinWords words, any address space) finds the boundary i in [1, B-1] that
+// minimises N_L*area(L) + N_R*area(R) with both sides non-empty; first minimum wins.  All 32 lanes call
+// it; cost_l / cost_r are B-float scratch areas (shared).  Returns cost = FLT_MAX when no boundary
+// separates the centroids.
+__device__ void sweep_axis(const uint32_t *bins, int B, float *cost_l, float *cost_r, float &best_cost,
+                           int &best_i) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = (B + 31) / 32;
+  const int b0 = lane * chunk, b1 = min(B, b0 + chunk);
+  // chunk totals
+  Box6 tot;
+  box_empty(tot);
+  uint32_t cnt = 0;
+  for (int b = b0; b < b1; b++) {
+    box_merge_bin(tot, bins + (size_t)b * kBinWords);
+    cnt += bins[(size_t)b * kBinWords];
+  }
+  // exclusive prefix (left) and exclusive suffix (right) of the chunk totals across lanes
+  Box6 pre = tot, suf = tot;
+  uint32_t pcnt = cnt, scnt = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    Box6 t;
+    uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, pcnt, o);
+    for (int k = 0; k < 6; k++) t.v[k] = __shfl_up_sync(0xFFFFFFFFu, pre.v[k], o);
+    if (lane >= o) {
+      box_merge(pre, t);
+      pcnt += tc;
+    }
+    uint32_t uc = __shfl_down_sync(0xFFFFFFFFu, scnt, o);
+    for (int k = 0; k < 6; k++) t.v[k] = __shfl_down_sync(0xFFFFFFFFu, suf.v[k], o);
+    if (lane + o < 32) {
+      box_merge(suf, t);
+      scnt += uc;
+    }
+  }
+  // inclusive -> exclusive
+  Box6 epre, esuf;
+  uint32_t epc = __shfl_up_sync(0xFFFFFFFFu, pcnt, 1), esc = __shfl_down_sync(0xFFFFFFFFu, scnt, 1);
+  for (int k = 0; k < 6; k++) {
+    epre.v[k] = __shfl_up_sync(0xFFFFFFFFu, pre.v[k], 1);
+    esuf.v[k] = __shfl_down_sync(0xFFFFFFFFu, suf.v[k], 1);
+  }
+  if (lane == 0) {
+    box_empty(epre);
+    epc = 0;
+  }
+  if (lane == 31) {
+    box_empty(esuf);
+    esc = 0;
+  }
+  // walk the chunk: cost_l[i] = cost of the left side for boundary i (bins [0,i)); cost_r[i] for [i,B)
+  {
+    Box6 run = epre;
+    uint32_t rc = epc;
+    for (int b = b0; b < b1; b++) {
+      // boundary i = b: left side is everything before bin b
+      cost_l[b] = rc ? (float)rc * box_area(run.v[0], run.v[1], run.v[2], run.v[3], run.v[4], run.v[5]) : -1.0f;
+      box_merge_bin(run, bins + (size_t)b * kBinWords);
+      rc += bins[(size_t)b * kBinWords];
+    }
+    run = esuf;
+    rc = esc;
+    for (int b = b1 - 1; b >= b0; b--) {
+      box_merge_bin(run, bins + (size_t)b * kBinWords);
+      rc += bins[(size_t)b * kBinWords];
+      // boundary i = b: right side is bins [b, B)
+      cost_r[b] = rc ? (float)rc * box_area(run.v[0], run.v[1], run.v[2], run.v[3], run.v[4], run.v[5]) : -1.0f;
+    }
+  }
+  __syncwarp();
+  float bc = FLT_MAX;
+  int bi = 0x7FFFFFFF;
+  for (int i = 1 + lane; i < B; i += 32) {
+    float cl = cost_l[i], cr = cost_r[i];
+    if (cl < 0.0f || cr < 0.0f) continue;  // an empty side never wins (the reference's 0*inf = NaN)
+    float c = cl + cr;
+    if (c < bc) {
+      bc = c;
+      bi = i;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    float oc = __shfl_xor_sync(0xFFFFFFFFu, bc, o);
+    int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+    if (oc < bc || (oc == bc && oi < bi)) {
+      bc = oc;
+      bi = oi;
+    }
+  }
+  best_cost = bc;
+  best_i = bi;
+  __syncwarp();
+}
+
+// union / count of bins [lo, hi) of one axis, all lanes get the result
+__device__ void range_union(const uint32_t *bins, int lo, int hi, Box6 &out, uint32_t &cnt) {
+  const int lane = threadIdx.x & 31;
+  Box6 b;
+  box_empty(b);
+  uint32_t c = 0;
+  for (int i = lo + lane; i < hi; i += 32) {
+    box_merge_bin(b, bins + (size_t)i * kBinWords);
+    c += bins[(size_t)i * kBinWords];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    for (int k = 0; k < 3; k++) {
+      b.v[k] = fminf(b.v[k], __shfl_xor_sync(0xFFFFFFFFu, b.v[k], o));
+      b.v[3 + k] = fmaxf(b.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, b.v[3 + k], o));
+    }
+  }
+  out = b;
+  cnt = c;
+}
+
+// Child bookkeeping shared by phases A and B (one thread).  Returns the class of the child:
+// 0 leaf, 1 subtree (phase B), 2 large (phase A)
+__device__ __forceinline__ int child_class(uint32_t n, uint32_t depth, uint32_t min_leaf, uint32_t max_depth) {
+  if (n <= min_leaf || depth >= max_depth) return 0;
+  return n <= (uint32_t)kSubtree ? 1 : 2;
+}
+
+// ------------------------------------------------------------------ phase A: split (one warp per node)
+__global__ void __launch_bounds__(128)
+    split_large_kernel(BNode *pool, BuildCounters *ctr, const uint32_t *__restrict__ active, int cur,
+                       uint32_t *__restrict__ active_next, uint32_t *__restrict__ subtrees, uint32_t *bins, int B,
+                       uint32_t min_leaf, uint32_t max_depth) {
+  extern __shared__ float scratch[];  // per warp: 2*B floats
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a = blockIdx.x * 4 + warp;
+  if (a >= ctr->n_active[cur]) return;
+  const uint32_t nid = active[a];
+  BNode nd = pool[nid];
+  uint32_t *nb = bins + (size_t)a * 3 * B * kBinWords;
+  float *cl = scratch + (size_t)warp * 2 * B, *cr = cl + B;
+  float cost[3];
+  int cut[3];
+  for (int ax = 0; ax < 3; ax++) sweep_axis(nb + (size_t)ax * B * kBinWords, B, cl, cr, cost[ax], cut[ax]);
+  int ax = 0;
+  if (cost[0] > cost[1]) ax = 1;
+  if (cost[ax] > cost[2]) ax = 2;
+  const uint32_t n = nd.r - nd.l;
+  Box6 lb, rb;
+  uint32_t nl, nr;
+  bool median = !(cost[ax] < FLT_MAX);
+  if (!median) {
+    range_union(nb + (size_t)ax * B * kBinWords, 0, cut[ax], lb, nl);
+    range_union(nb + (size_t)ax * B * kBinWords, cut[ax], B, rb, nr);
+  } else {
+    nl = n >> 1;
+    nr = n - nl;
+    box_empty(lb);
+    box_empty(rb);
+    // the reference labels the node with the last axis it tried: (first + 2) % 3 (nanort.h:1833)
+    ax = (ax + 2) % 3;
+    // children boxes are gathered by the scatter pass into this node's (now free) bin words
+    if (lane < 12) nb[lane] = (lane % 6) < 3 ? 0xFFFFFFFFu : 0u;
+  }
+  if (lane == 0) {
+    uint32_t left = atomicAdd(&ctr->pool, 2u);
+    nd.left = left;
+    nd.axis = (uint32_t)ax;
+    nd.split_bin = median ? kMedian : (uint32_t)cut[ax];
+    nd.nleft = nl;
+    pool[nid] = nd;
+    for (int side = 0; side < 2; side++) {
+      BNode c;
+      const Box6 &bx = side ? rb : lb;
+      for (int k = 0; k < 3; k++) {
+        c.bmin[k] = bx.v[k];
+        c.bmax[k] = bx.v[3 + k];
+      }
+      c.l = side ? nd.l + nl : nd.l;
+      c.r = side ? nd.r : nd.l + nl;
+      c.left = kInactive;
+      c.depth = nd.depth + 1;
+      c.rturns = nd.rturns + (uint32_t)side;
+      c.axis = 0;
+      c.split_bin = 0;
+      c.nleft = 0;
+      c.slot = kInactive;
+      c.pad = 0;
+      int cls = child_class(c.r - c.l, c.depth, min_leaf, max_depth);
+      if (cls == 1) {
+        subtrees[atomicAdd(&ctr->n_subtrees, 1u)] = left + side;
+      } else if (cls == 2) {
+        uint32_t s = atomicAdd(&ctr->n_active[cur ^ 1], 1u);
+        active_next[s] = left + side;
+        c.slot = s;
+      }
+      pool[left + side] = c;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase A: partition
+__global__ void __launch_bounds__(256)
+    flag_large_kernel(const BNode *__restrict__ pool, const uint32_t *__restrict__ node_of,
+                      const uint32_t *__restrict__ idx, const float4 *__restrict__ plo,
+                      const float4 *__restrict__ phi, const float *__restrict__ pcz, uint32_t n, int B,
+                      uint32_t *__restrict__ flags) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const BNode nd = pool[node_of[p]];
+  uint32_t f = 0;
+  if (nd.slot != kInactive) {
+    if (nd.split_bin == kMedian) {
+      f = (p - nd.l) < nd.nleft;
+    } else {
+      uint32_t s = idx[p];
+      float c = nd.axis == 0 ? plo[s].w : (nd.axis == 1 ? phi[s].w : pcz[s]);
+      int b = bin_of(c, nd.bmin[nd.axis], inv_extent(nd.bmin[nd.axis], nd.bmax[nd.axis], B), B);
+      f = (uint32_t)b < nd.split_bin;
+    }
+  }
+  flags[p] = f;
+}
+
+__global__ void __launch_bounds__(256)
+    scatter_large_kernel(const BNode *__restrict__ pool, const uint32_t *__restrict__ node_of,
+                         const uint32_t *__restrict__ idx, const uint32_t *__restrict__ flags,
+                         const uint32_t *__restrict__ scan, uint32_t n, uint32_t *__restrict__ node_of_out,
+                         uint32_t *__restrict__ idx_out, const float4 *__restrict__ plo,
+                         const float4 *__restrict__ phi, uint32_t *bins, int B) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t nid = node_of[p];
+  const BNode nd = pool[nid];
+  if (nd.slot == kInactive) {
+    node_of_out[p] = nid;
+    idx_out[p] = idx[p];
+    return;
+  }
+  const uint32_t before = scan[p] - scan[nd.l];  // lefts among [l, p)
+  const uint32_t f = flags[p];
+  const uint32_t dest = f ? nd.l + before : nd.l + nd.nleft + ((p - nd.l) - before);
+  const uint32_t s = idx[p];
+  idx_out[dest] = s;
+  node_of_out[dest] = nd.left + (f ? 0u : 1u);
+  if (nd.split_bin == kMedian) {
+    // rare: children boxes of a median cut are gathered here (keys in the node's first 12 bin words)
+    uint32_t *w = bins + (size_t)nd.slot * 3 * B * kBinWords + (f ? 0 : 6);
+    float4 lo = plo[s], hi = phi[s];
+    atomicMin(w + 0, fkey(lo.x));
+    atomicMin(w + 1, fkey(lo.y));
+    atomicMin(w + 2, fkey(lo.z));
+    atomicMax(w + 3, fkey(hi.x));
+    atomicMax(w + 4, fkey(hi.y));
+    atomicMax(w + 5, fkey(hi.z));
+  }
+}
+
+__global__ void fix_median_kernel(BNode *pool, const BuildCounters *ctr, const uint32_t *__restrict__ active, int cur,
+                                  const uint32_t *__restrict__ bins, int B) {
+  uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= ctr->n_active[cur]) return;
+  const BNode nd = pool[active[a]];
+  if (nd.split_bin != kMedian) return;
+  const uint32_t *w = bins + (size_t)a * 3 * B * kBinWords;
+  for (int side = 0; side < 2; side++) {
+    BNode *c = pool + nd.left + side;
+    for (int k = 0; k < 3; k++) {
+      c->bmin[k] = funkey(w[side * 6 + k]);
+      c->bmax[k] = funkey(w[side * 6 + 3 + k]);
+    }
+  }
+}
+
+__global__ void reset_count_kernel(BuildCounters *ctr, int which) { ctr->n_active[which] = 0; }
+
+// ------------------------------------------------------------------ phase B: one CTA per subtree
+struct SubShared {
+  float4 plo[kSubtree];
+  float4 phi[kSubtree];
+  float pcz[kSubtree];
+  uint32_t gslot[kSubtree];   // global primitive slot of local primitive i
+  uint16_t ids[kSubtree];     // current order (local ids) of the subtree's range
+  uint16_t tmp[kSubtree];
+  uint32_t stack[kSubtree];   // pool ids of nodes still to split
+  uint32_t scan_warp[kSubBlock / 32];
+  float cost[3];
+  int cut[3];
+  int sp;
+  uint32_t cur;
+  uint32_t nl;
+  uint32_t left;
+  int axis;
+  int median;
+  float cbox[2][6];
+};
+
+__global__ void __launch_bounds__(kSubBlock)
+    subtree_kernel(BNode *pool, BuildCounters *ctr, const uint32_t *__restrict__ subtrees,
+                   uint32_t *__restrict__ idx, const float4 *__restrict__ plo, const float4 *__restrict__ phi,
+                   const float *__restrict__ pcz, int B, uint32_t min_leaf, uint32_t max_depth) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SubShared &S = *reinterpret_cast<SubShared *>(smem_raw);
+  uint32_t *sbin = reinterpret_cast<uint32_t *>(smem_raw + sizeof(SubShared));  // 3*B*kBinWords
+  float *sweep = reinterpret_cast<float *>(sbin + 3 * B * kBinWords);             // 3 warps * 2*B floats
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t root = subtrees[blockIdx.x];
+  const BNode rootn = pool[root];
+  const uint32_t base = rootn.l, total = rootn.r - rootn.l;
+  for (uint32_t i = tid; i < total; i += kSubBlock) {
+    uint32_t s = idx[base + i];
+    S.gslot[i] = s;
+    S.plo[i] = plo[s];
+    S.phi[i] = phi[s];
+    S.pcz[i] = pcz[s];
+    S.ids[i] = (uint16_t)i;
+  }
+  if (tid == 0) {
+    S.stack[0] = root;
+    S.sp = 1;
+  }
+  __syncthreads();
+
+  for (;;) {
+    const int sp_now = S.sp;  // every thread reads it between two barriers, thread 0 updates it after
+    if (sp_now == 0) break;
+    __syncthreads();
+    if (tid == 0) {
+      S.cur = S.stack[sp_now - 1];
+      S.sp = sp_now - 1;
+    }
+    __syncthreads();
+    const uint32_t nid = S.cur;
+    const BNode nd = pool[nid];
+    const uint32_t lo = nd.l - base, n = nd.r - nd.l;
+    // ---- bins
+    for (int i = tid; i < 3 * B * kBinWords; i += kSubBlock) {
+      int w = i & (kBinWords - 1);
+      sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
+    }
+    __syncthreads();
+    const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
+                         inv_extent(nd.bmin[2], nd.bmax[2], B)};
+    for (uint32_t i = tid; i < n; i += kSubBlock) {
+      const uint32_t q = S.ids[lo + i];
+      const float4 l4 = S.plo[q], h4 = S.phi[q];
+      const float c3[3] = {l4.w, h4.w, S.pcz[q]};
+      const uint32_t kl[3] = {fkey(l4.x), fkey(l4.y), fkey(l4.z)}, kh[3] = {fkey(h4.x), fkey(h4.y), fkey(h4.z)};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        uint32_t *w = sbin + ((size_t)a * B + bin_of(c3[a], nd.bmin[a], iv[a], B)) * kBinWords;
+        atomicAdd(w, 1u);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          atomicMin(w + 1 + k, kl[k]);
+          atomicMax(w + 4 + k, kh[k]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- sweep: warp a handles axis a
+    if (warp < 3) {
+      float c;
+      int ci;
+      sweep_axis(sbin + (size_t)warp * B * kBinWords, B, sweep + (size_t)warp * 2 * B, sweep + (size_t)warp * 2 * B + B,
+                 c, ci);
+      if (lane == 0) {
+        S.cost[warp] = c;
+        S.cut[warp] = ci;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int ax = 0;
+      if (S.cost[0] > S.cost[1]) ax = 1;
+      if (S.cost[ax] > S.cost[2]) ax = 2;
+      const bool median = !(S.cost[ax] < FLT_MAX);
+      Box6 lb, rb;
+      uint32_t nl, nr;
+      if (!median) {
+        range_union(sbin + (size_t)ax * B * kBinWords, 0, S.cut[ax], lb, nl);
+        range_union(sbin + (size_t)ax * B * kBinWords, S.cut[ax], B, rb, nr);
+      } else {
+        nl = n >> 1;
+        box_empty(lb);
+        box_empty(rb);
+        // exact boxes of the two halves of the current order
+        for (uint32_t i = lane; i < n; i += 32) {
+          const uint32_t q = S.ids[lo + i];
+          const float4 l4 = S.plo[q], h4 = S.phi[q];
+          Box6 &t = i < nl ? lb : rb;
+          t.v[0] = fminf(t.v[0], l4.x);
+          t.v[1] = fminf(t.v[1], l4.y);
+          t.v[2] = fminf(t.v[2], l4.z);
+          t.v[3] = fmaxf(t.v[3], h4.x);
+          t.v[4] = fmaxf(t.v[4], h4.y);
+          t.v[5] = fmaxf(t.v[5], h4.z);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          for (int k = 0; k < 3; k++) {
+            lb.v[k] = fminf(lb.v[k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[k], o));
+            rb.v[k] = fminf(rb.v[k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[k], o));
+            lb.v[3 + k] = fmaxf(lb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[3 + k], o));
+            rb.v[3 + k] = fmaxf(rb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[3 + k], o));
+          }
+        }
+      }
+      if (lane == 0) {
+        S.axis = median ? (ax + 2) % 3 : ax;
+        S.median = median ? 1 : 0;
+        S.nl = nl;
+        S.left = atomicAdd(&ctr->pool, 2u);
+        for (int k = 0; k < 6; k++) {
+          S.cbox[0][k] = lb.v[k];
+          S.cbox[1][k] = rb.v[k];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- stable partition of ids[lo, lo+n)
+    {
+      const int axis = S.axis;
+      const uint32_t split = S.median ? 0u : (uint32_t)S.cut[S.median ? 0 : (S.axis)];
+      const uint32_t nl = S.nl;
+      // each thread owns a contiguous run so that a block-wide scan of run totals gives stable ranks
+      const uint32_t per = (n + kSubBlock - 1) / kSubBlock;
+      const uint32_t i0 = min(n, tid * per), i1 = min(n, i0 + per);
+      uint32_t myl = 0;
+      for (uint32_t i = i0; i < i1; i++) {
+        const uint32_t q = S.ids[lo + i];
+        bool f;
+        if (S.median) {
+          f = i < nl;
+        } else {
+          const float c = axis == 0 ? S.plo[q].w : (axis == 1 ? S.phi[q].w : S.pcz[q]);
+          f = (uint32_t)bin_of(c, nd.bmin[axis], iv[axis], B) < split;
+        }
+        myl += f ? 1u : 0u;
+      }
+      uint32_t inc = myl;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (lane == 31) S.scan_warp[warp] = inc;
+      __syncthreads();
+      uint32_t woff = 0;
+      for (int w = 0; w < warp; w++) woff += S.scan_warp[w];
+      uint32_t lrank = woff + inc - myl;  // lefts before my run
+      uint32_t rrank = i0 - lrank;        // rights before my run
+      for (uint32_t i = i0; i < i1; i++) {
+        const uint32_t q = S.ids[lo + i];
+        bool f;
+        if (S.median) {
+          f = i < nl;
+        } else {
+          const float c = axis == 0 ? S.plo[q].w : (axis == 1 ? S.phi[q].w : S.pcz[q]);
+          f = (uint32_t)bin_of(c, nd.bmin[axis], iv[axis], B) < split;
+        }
+        if (f)
+          S.tmp[lo + lrank++] = (uint16_t)q;
+        else
+          S.tmp[lo + nl + rrank++] = (uint16_t)q;
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < n; i += kSubBlock) S.ids[lo + i] = S.tmp[lo + i];
+    }
+    // ---- children
+    if (tid == 0) {
+      BNode me = nd;
+      me.left = S.left;
+      me.axis = (uint32_t)S.axis;
+      me.split_bin = S.median ? kMedian : (uint32_t)S.cut[S.axis];
+      me.nleft = S.nl;
+      pool[nid] = me;
+      for (int side = 1; side >= 0; side--) {  // right first, so the left child is split next
+        BNode c;
+        for (int k = 0; k < 3; k++) {
+          c.bmin[k] = S.cbox[side][k];
+          c.bmax[k] = S.cbox[side][3 + k];
+        }
+        c.l = side ? nd.l + S.nl : nd.l;
+        c.r = side ? nd.r : nd.l + S.nl;
+        c.left = kInactive;
+        c.depth = nd.depth + 1;
+        c.rturns = nd.rturns + (uint32_t)side;
+        c.axis = 0;
+        c.split_bin = 0;
+        c.nleft = 0;
+        c.slot = kInactive;
+        c.pad = 0;
+        pool[S.left + side] = c;
+        if (child_class(c.r - c.l, c.depth, min_leaf, max_depth) != 0) S.stack[S.sp++] = S.left + side;
+      }
+    }
+    __syncthreads();
+  }
+  // final order of this subtree's range
+  for (uint32_t i = tid; i < total; i += kSubBlock) idx[base + i] = S.gslot[S.ids[i]];
+}
+
+// ------------------------------------------------------------------ phase C: emission
+__global__ void mark_leaves_kernel(const BNode *__restrict__ pool, uint32_t n_nodes, uint32_t *__restrict__ leaf_start,
+                                   BuildCounters *ctr) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t depth = 0, leaf = 0;
+  if (i < n_nodes) {
+    const BNode nd = pool[i];
+    depth = nd.depth;
+    if (nd.left == kInactive) {
+      leaf_start[nd.l] = 1u;
+      leaf = 1;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    depth = max(depth, __shfl_xor_sync(0xFFFFFFFFu, depth, o));
+    leaf += __shfl_xor_sync(0xFFFFFFFFu, leaf, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&ctr->max_depth, depth);
+    if (leaf) atomicAdd(&ctr->n_leaves, leaf);
+  }
+}
+
+// pre-order index of a node = 2*(leaves starting before its range) - right turns + depth
+__global__ void emit_nodes_kernel(const BNode *__restrict__ pool, uint32_t n_nodes,
+                                  const uint32_t *__restrict__ leaves_before, Node40 *__restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const BNode nd = pool[i];
+  const uint32_t lb = leaves_before[nd.l];
+  const uint32_t pre = 2u * lb - nd.rturns + nd.depth;
+  Node40 o;
+  for (int k = 0; k < 3; k++) {
+    o.bmin[k] = nd.bmin[k];
+    o.bmax[k] = nd.bmax[k];
+  }
+  if (nd.left == kInactive) {
+    o.flag = 1;
+    o.axis = 0;
+    o.data[0] = nd.r - nd.l;
+    o.data[1] = nd.l;
+  } else {
+    o.flag = 0;
+    o.axis = (int32_t)nd.axis;
+    const uint32_t mid = nd.l + nd.nleft;
+    o.data[0] = pre + 1u;
+    o.data[1] = pre + 2u * (leaves_before[mid] - lb);
+  }
+  out[pre] = o;
+}
+
+}  // namespace
+
+#define BUILD_CHECK(expr)       \
+  do {                          \
+    rc = (expr);                \
+    if (rc != NRT_OK) goto done; \
+  } while (0)
+#define BUILD_CUDA(expr)                                        \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) {                                    \
+      rc = cuda_fail(_e, #expr, __FILE__, __LINE__);            \
+      goto done;                                                \
+    }                                                           \
+  } while (0)
+
+int build_on_device(Accel *a, cudaStream_t s) {
+  const uint32_t n = a->n_prims;
+  const BuildOptions28 &opt = a->options;
+  const int B = (int)opt.bin_size;
+  // min_leaf_primitives == 0 would ask for empty leaves (the reference then recurses to max_tree_depth)
+  const uint32_t min_leaf = opt.min_leaf_primitives < 1 ? 1u : opt.min_leaf_primitives;
+  if (B > kMaxBins) {
+    set_error("nrt_build: bin_size > 256 is not supported by the device builder");
+    return NRT_ERR_INVALID;
+  }
+  if (n > 0x7FFFFFF0u) {
+    set_error("nrt_build: too many primitives");
+    return NRT_ERR_INVALID;
+  }
+  int rc = NRT_OK;
+  float4 *d_plo = nullptr, *d_phi = nullptr;
+  float *d_pcz = nullptr;
+  uint32_t *d_idx[2] = {nullptr, nullptr}, *d_nodeof[2] = {nullptr, nullptr};
+  uint32_t *d_flags = nullptr, *d_scan = nullptr, *d_scratch = nullptr, *d_active[2] = {nullptr, nullptr};
+  uint32_t *d_subtrees = nullptr, *d_bins = nullptr, *d_scene = nullptr;
+  BNode *d_pool = nullptr;
+  BuildCounters *d_ctr = nullptr;
+  BuildCounters hc;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  const size_t max_active = (size_t)n / (kSubtree + 1) + 2;   // nodes with > kSubtree prims per level
+  const size_t max_subtrees = (size_t)n / ((size_t)min_leaf + 1) + 2;
+  const size_t bin_words = max_active * 3 * (size_t)B * kBinWords;
+  const uint32_t grid_n = (n + 255) / 256;
+  int cur = 0, which = 0;
+  uint32_t n_active = 0;
+  uint32_t n_nodes = 0;
+  const size_t sub_smem = sizeof(SubShared) + (size_t)3 * B * kBinWords * 4 + (size_t)3 * 2 * B * 4;
+
+  BUILD_CUDA(cudaEventCreate(&ev0));
+  BUILD_CUDA(cudaEventCreate(&ev1));
+  BUILD_CUDA(cudaMalloc(&d_plo, sizeof(float4) * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_phi, sizeof(float4) * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_pcz, sizeof(float) * (size_t)n));
+  for (int i = 0; i < 2; i++) {
+    BUILD_CUDA(cudaMalloc(&d_idx[i], sizeof(uint32_t) * (size_t)n));
+    BUILD_CUDA(cudaMalloc(&d_nodeof[i], sizeof(uint32_t) * (size_t)n));
+    BUILD_CUDA(cudaMalloc(&d_active[i], sizeof(uint32_t) * max_active));
+  }
+  BUILD_CUDA(cudaMalloc(&d_flags, sizeof(uint32_t) * ((size_t)n + 1)));
+  BUILD_CUDA(cudaMalloc(&d_scan, sizeof(uint32_t) * ((size_t)n + 1)));
+  BUILD_CUDA(cudaMalloc(&d_scratch, sizeof(uint32_t) * scan_scratch_words(n + 1)));
+  BUILD_CUDA(cudaMalloc(&d_subtrees, sizeof(uint32_t) * max_subtrees));
+  BUILD_CUDA(cudaMalloc(&d_bins, sizeof(uint32_t) * bin_words));
+  BUILD_CUDA(cudaMalloc(&d_scene, sizeof(uint32_t) * 8));
+  BUILD_CUDA(cudaMalloc(&d_pool, sizeof(BNode) * 2 * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_ctr, sizeof(BuildCounters)));
+  {
+    const uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
+    BUILD_CUDA(cudaMemcpyAsync(d_scene, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  }
+  BUILD_CUDA(cudaEventRecord(ev0, s));
+  prim_setup_kernel<<<grid_n, 256, 0, s>>>(a->d_verts, a->d_faces, n, d_plo, d_phi, d_pcz, d_scene);
+  iota_kernel<<<grid_n, 256, 0, s>>>(d_idx[0], d_nodeof[0], n);
+  init_build_kernel<<<1, 1, 0, s>>>(d_pool, d_ctr, d_scene, n, min_leaf, opt.max_tree_depth,
+                                    d_active[0], d_subtrees);
+  BUILD_CUDA(cudaGetLastError());
+  BUILD_CUDA(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  BUILD_CUDA(cudaStreamSynchronize(s));
+  n_active = hc.n_active[0];
+
+  // ---- phase A
+  BUILD_CUDA(cudaFuncSetAttribute(bin_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  3 * kMaxBins * kBinWords * 4));
+  while (n_active > 0) {
+    const size_t words = (size_t)n_active * 3 * B * kBinWords;
+    clear_bins_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_bins, words);
+    bin_large_kernel<<<(n + 1023) / 1024, 256, (size_t)3 * B * kBinWords * 4, s>>>(
+        d_pool, d_nodeof[which], d_idx[which], d_plo, d_phi, d_pcz, n, B, d_bins);
+    reset_count_kernel<<<1, 1, 0, s>>>(d_ctr, cur ^ 1);
+    split_large_kernel<<<(n_active + 3) / 4, 128, (size_t)4 * 2 * B * 4, s>>>(
+        d_pool, d_ctr, d_active[cur], cur, d_active[cur ^ 1], d_subtrees, d_bins, B, min_leaf,
+        opt.max_tree_depth);
+    flag_large_kernel<<<grid_n, 256, 0, s>>>(d_pool, d_nodeof[which], d_idx[which], d_plo, d_phi, d_pcz, n, B,
+                                             d_flags);
+    BUILD_CUDA(cudaGetLastError());
+    BUILD_CHECK(exclusive_scan_u32_async(d_flags, d_scan, n, d_scratch, s));
+    scatter_large_kernel<<<grid_n, 256, 0, s>>>(d_pool, d_nodeof[which], d_idx[which], d_flags, d_scan, n,
+                                                d_nodeof[which ^ 1], d_idx[which ^ 1], d_plo, d_phi, d_bins, B);
+    fix_median_kernel<<<(n_active + 127) / 128, 128, 0, s>>>(d_pool, d_ctr, d_active[cur], cur, d_bins, B);
+    BUILD_CUDA(cudaGetLastError());
+    which ^= 1;
+    cur ^= 1;
+    BUILD_CUDA(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    BUILD_CUDA(cudaStreamSynchronize(s));
+    n_active = hc.n_active[cur];
+  }
+
+  // ---- phase B
+  if (hc.n_subtrees > 0) {
+    BUILD_CUDA(cudaFuncSetAttribute(subtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem));
+    subtree_kernel<<<hc.n_subtrees, kSubBlock, sub_smem, s>>>(d_pool, d_ctr, d_subtrees, d_idx[which], d_plo, d_phi,
+                                                              d_pcz, B, min_leaf, opt.max_tree_depth);
+    BUILD_CUDA(cudaGetLastError());
+  }
+  BUILD_CUDA(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  BUILD_CUDA(cudaStreamSynchronize(s));
+  n_nodes = hc.pool;
+
+  // ---- phase C
+  BUILD_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * ((size_t)n + 1), s));
+  mark_leaves_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(d_pool, n_nodes, d_flags, d_ctr);
+  BUILD_CUDA(cudaGetLastError());
+  BUILD_CHECK(exclusive_scan_u32_async(d_flags, d_scan, n + 1, d_scratch, s));
+  BUILD_CUDA(cudaMalloc(&a->d_nodes, sizeof(Node40) * (size_t)n_nodes));
+  emit_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(d_pool, n_nodes, d_scan, a->d_nodes);
+  BUILD_CUDA(cudaGetLastError());
+  // indices_: without a pre-sort the primitive slot IS the primitive id
+  a->d_indices = d_idx[which];
+  d_idx[which] = nullptr;
+  BUILD_CUDA(cudaEventRecord(ev1, s));
+  BUILD_CUDA(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  {
+    uint32_t keys[6];
+    BUILD_CUDA(cudaMemcpyAsync(keys, d_scene, sizeof(keys), cudaMemcpyDeviceToHost, s));
+    BUILD_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; k++) {
+      uint32_t kmin = keys[k], kmax = keys[3 + k];
+      uint32_t umin = (kmin & 0x80000000u) ? (kmin ^ 0x80000000u) : ~kmin;
+      uint32_t umax = (kmax & 0x80000000u) ? (kmax ^ 0x80000000u) : ~kmax;
+      memcpy(&a->root_bmin[k], &umin, 4);
+      memcpy(&a->root_bmax[k], &umax, 4);
+    }
+  }
+  {
+    float ms = 0.0f;
+    BUILD_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    a->n_nodes = n_nodes;
+    a->stats.max_tree_depth = hc.max_depth;
+    a->stats.num_leaf_nodes = hc.n_leaves;
+    a->stats.num_branch_nodes = n_nodes - hc.n_leaves;
+    a->stats.build_secs = ms * 1e-3f;
+    a->mirrors_valid = false;
+  }
+
+done:
+  cudaFree(d_plo);
+  cudaFree(d_phi);
+  cudaFree(d_pcz);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(d_idx[i]);
+    cudaFree(d_nodeof[i]);
+    cudaFree(d_active[i]);
+  }
+  cudaFree(d_flags);
+  cudaFree(d_scan);
+  cudaFree(d_scratch);
+  cudaFree(d_subtrees);
+  cudaFree(d_bins);
+  cudaFree(d_scene);
+  cudaFree(d_pool);
+  cudaFree(d_ctr);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  return rc;
+}
+
+}  // namespace nrt

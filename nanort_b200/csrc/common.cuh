@@ -1,0 +1,173 @@
+// Shared types and helpers of the nanort_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/nanort_b200.h"
+
+namespace nrt {
+
+// ---- nanort-layout records (byte-compatible, see include/nanort_b200.h) ----
+struct Node40 {
+  float bmin[3];
+  float bmax[3];
+  int32_t flag;  // 1 leaf, 0 branch
+  int32_t axis;
+  uint32_t data[2];  // leaf {count, first}; branch {left, right}
+};
+static_assert(sizeof(Node40) == 40, "BVHNode<float> layout");
+
+struct Ray36 {
+  float org[3];
+  float dir[3];
+  float min_t, max_t;
+  uint32_t type;
+};
+static_assert(sizeof(Ray36) == 36, "Ray<float> layout");
+
+struct Hit16 {
+  float u, v, t;
+  uint32_t prim_id;
+};
+static_assert(sizeof(Hit16) == 16, "TriangleIntersection<float> layout");
+
+struct BuildOptions28 {
+  float cost_t_aabb;
+  uint32_t min_leaf_primitives;
+  uint32_t max_tree_depth;
+  uint32_t bin_size;
+  uint32_t shallow_depth;
+  uint32_t min_primitives_for_parallel_build;
+  uint8_t cache_bbox;
+  uint8_t pad[3];
+};
+static_assert(sizeof(BuildOptions28) == 28, "BVHBuildOptions<float> layout");
+
+struct BuildStats16 {
+  uint32_t max_tree_depth, num_leaf_nodes, num_branch_nodes;
+  float build_secs;
+};
+static_assert(sizeof(BuildStats16) == 16, "BVHBuildStatistics layout");
+
+struct TraceOptions16 {
+  uint32_t prim_ids_range[2];
+  uint32_t skip_prim_id;
+  uint8_t cull_back_face;
+  uint8_t pad[3];
+};
+static_assert(sizeof(TraceOptions16) == 16, "BVHTraceOptions layout");
+
+// ---- private traversal layout -------------------------------------------------
+// One 64-byte record per BRANCH node holding BOTH child boxes, so one aligned
+// 4 x 16-byte fetch decides both children (the nanort array needs three
+// dependent 40-byte fetches for the same decision).
+//   q0 = c0.lo.xyz, c0.hi.x     q1 = c0.hi.yz, c1.lo.xy
+//   q2 = c1.lo.z, c1.hi.xyz     q3 = ref0, ref1, axis, unused
+// ref >= 0: index of the child's WideNode; ref < 0: leaf, ~ref = first slot in
+// the packed triangle array.  A leaf with no triangles is ref == kEmptyLeaf.
+struct WideNode {
+  float4 q0, q1, q2;
+  int4 q3;
+};
+static_assert(sizeof(WideNode) == 64, "WideNode");
+constexpr int kEmptyLeaf = (int)0x80000000;  // ~0x7FFFFFFF: never a valid slot
+
+// Packed triangle, 48 bytes, in leaf (indices_) order:
+//   v0.xyz, prim_id | v1.xyz, last_in_leaf flag (1/0 as uint bits) | v2.xyz, 0
+struct PackedTri {
+  float4 a, b, c;
+};
+static_assert(sizeof(PackedTri) == 48, "PackedTri");
+
+// ---- accel object ----------------------------------------------------------------
+struct Accel {
+  int device = 0;
+  uint32_t n_prims = 0;
+  size_t n_nodes = 0;
+  size_t n_wide = 0;
+  bool root_is_leaf = false;
+  // device: reference-layout tree + original geometry (conformance walk)
+  Node40 *d_nodes = nullptr;
+  uint32_t *d_indices = nullptr;
+  float *d_verts = nullptr;  // tightly packed float3 (stride 12)
+  size_t n_verts = 0;
+  uint32_t *d_faces = nullptr;
+  // device: private traversal layout
+  WideNode *d_wide = nullptr;
+  PackedTri *d_tris = nullptr;
+  // host mirrors (lazy)
+  std::vector<Node40> h_nodes;
+  std::vector<uint32_t> h_indices;
+  bool mirrors_valid = false;
+  BuildOptions28 options;
+  BuildStats16 stats;
+  float root_bmin[3], root_bmax[3];
+  // scratch reused by the host-pointer API
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  void *d_stage_rays[3] = {nullptr, nullptr, nullptr};
+  void *d_stage_hits[3] = {nullptr, nullptr, nullptr};
+  void *d_stage_mask[3] = {nullptr, nullptr, nullptr};
+  size_t stage_rays = 0;  // capacity in rays of every staging buffer
+  // wavefront pass scratch (render.cu)
+  void *d_wave = nullptr;
+  size_t wave_bytes = 0;
+  // device counter block: [0..7] misc, [8..9] visit counts, [16..47] ring of ray cursors (one per
+  // in-flight traversal launch, so launches on different streams never share a cursor)
+  uint64_t *d_counters = nullptr;
+  mutable std::atomic<uint32_t> cursor_ring{0};
+};
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define NRT_CUDA(expr)                                                     \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess) return nrt::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+inline TraceOptions16 default_trace_options() {
+  TraceOptions16 o;
+  o.prim_ids_range[0] = 0;
+  o.prim_ids_range[1] = 0x7FFFFFFFu;
+  o.skip_prim_id = 0xFFFFFFFFu;
+  o.cull_back_face = 0;
+  o.pad[0] = o.pad[1] = o.pad[2] = 0;
+  return o;
+}
+
+inline BuildOptions28 default_build_options() {
+  BuildOptions28 o;
+  o.cost_t_aabb = 0.2f;
+  o.min_leaf_primitives = 4;
+  o.max_tree_depth = 256;
+  o.bin_size = 64;
+  o.shallow_depth = 4;
+  o.min_primitives_for_parallel_build = 8192;
+  o.cache_bbox = 0;
+  o.pad[0] = o.pad[1] = o.pad[2] = 0;
+  return o;
+}
+
+// ---- kernels / stages implemented in the other translation units -------------------
+// traverse.cu
+int launch_traverse(const Accel *a, const Ray36 *d_rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
+                    const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
+int launch_traverse_count(const Accel *a, const Ray36 *d_rays, size_t n, const TraceOptions16 &opt,
+                          uint32_t flags, uint64_t *d_counts2, cudaStream_t s);
+// SoA wavefront entry used by render.cu: rays as two float4 (org.xyz,min_t | dir.xyz,max_t)
+int launch_traverse_soa(const Accel *a, const float4 *d_org_tmin, const float4 *d_dir_tmax, size_t n,
+                        Hit16 *d_hits, const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
+// layout.cu
+int derive_private_layout(Accel *a, cudaStream_t s);
+// build.cu
+int build_on_device(Accel *a, cudaStream_t s);
+
+int device_sm_count(int device);
+
+}  // namespace nrt

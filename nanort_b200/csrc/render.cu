@@ -1,0 +1,330 @@
+// Device-resident wavefront pass "primary + 1-bounce AO" (the headline metric of BASELINE.json).
+//
+// The reference has no AO example; the pass is composed from pieces of its path tracer
+// (/root/reference/examples/path_tracer/main.cc):
+//   camera ray        main.cc:809-817, 839-849   (jittered pinhole; counter-based hash instead of rand())
+//   hit point         main.cc:860                (P = org + dir * t)
+//   geometric normal  main.cc:306-312 (calcNormal), flipped towards the viewer main.cc:878-881
+//   cosine direction  main.cc:216-250 (orthonormal basis + directionCosTheta)
+//   occlusion query   main.cc:675-701 (CheckForOccluder: a CLOSEST-hit Traverse with max_t = radius;
+//                     nanort has no any-hit, so AO rays do the same full closest-hit work here)
+// Rays live in SoA queues (two float4 per ray); hits are nanort's 16-byte records.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nrt {
+
+namespace {
+
+struct Wave {
+  float4 *org_tmin;   // primary queue
+  float4 *dir_tmax;
+  Hit16 *hits;
+  uint32_t *pix;      // pixel of primary slot (0xFFFFFFFF = slot outside the image)
+  float4 *ao_org_tmin;  // compacted AO queue
+  float4 *ao_dir_tmax;
+  uint32_t *ao_pix;
+  Hit16 *ao_hits;
+};
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32, same as scenes.py:hash_u32
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+
+// scenes.py:rand_ps
+__device__ __forceinline__ float rand_ps(uint32_t pix, uint32_t smp, uint32_t dim, uint32_t seed) {
+  uint32_t h = hash_u32(pix + seed * 0x9E3779B1u);
+  h = hash_u32(h + smp * 0x85EBCA77u + dim * 0xC2B2AE3Du);
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// Slot -> (pixel, sample).  Slots enumerate this shard's tiles; inside a tile the order is
+// sample-major over 8x4 pixel blocks, so the 32 lanes of a warp start as one coherent 8x4 packet.
+__device__ __forceinline__ bool slot_to_pixel(const nrt_ao_params &p, unsigned long long slot, uint32_t &pix,
+                                              uint32_t &smp) {
+  const uint32_t tile_pix = p.tile_w * p.tile_h;
+  const unsigned long long per_tile = (unsigned long long)tile_pix * p.spp;
+  const uint32_t k = (uint32_t)(slot / per_tile);  // k-th tile of this shard
+  const uint32_t rem = (uint32_t)(slot % per_tile);
+  smp = rem / tile_pix;
+  const uint32_t q = rem % tile_pix;
+  const uint32_t bw = p.tile_w / 8;  // 8x4 blocks per tile row
+  const uint32_t blk = q / 32, in = q % 32;
+  const uint32_t bx = blk % bw, by = blk / bw;
+  const uint32_t lx = bx * 8 + (in & 7), ly = by * 4 + (in >> 3);
+  const uint32_t tiles_x = (p.width + p.tile_w - 1) / p.tile_w;
+  const uint32_t tile = k * p.n_shards + p.shard;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  const uint32_t x = tx * p.tile_w + lx, y = ty * p.tile_h + ly;
+  if (x >= p.width || y >= p.height) return false;
+  pix = y * p.width + x;
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+    gen_primary_kernel(nrt_ao_params p, unsigned long long slot0, uint32_t count, Wave w) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint32_t pix, smp;
+  if (!slot_to_pixel(p, slot0 + i, pix, smp)) {
+    w.pix[i] = 0xFFFFFFFFu;
+    w.org_tmin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    w.dir_tmax[i] = make_float4(0.f, 0.f, -1.f, -1.f);  // max_t < min_t: retires at the root
+    return;
+  }
+  smp += p.sample0;
+  const float jx = rand_ps(pix, smp, 0, p.seed), jy = rand_ps(pix, smp, 1, p.seed);
+  const float px = (float)(pix % p.width), py = (float)(pix / p.width);
+  const float sx = (px + jx) / (float)p.width - 0.5f;
+  const float sy = 0.5f - (py + jy) / (float)p.height;
+  float dx = p.cam[3] * sx + p.cam[6] * sy + p.cam[9];
+  float dy = p.cam[4] * sx + p.cam[7] * sy + p.cam[10];
+  float dz = p.cam[5] * sx + p.cam[8] * sy + p.cam[11];
+  const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+  w.pix[i] = pix;
+  w.org_tmin[i] = make_float4(p.cam[0], p.cam[1], p.cam[2], p.ray_min_t);
+  w.dir_tmax[i] = make_float4(dx * inv, dy * inv, dz * inv, p.ray_max_t);
+}
+
+// One AO ray per primary hit, compacted with one atomic per warp; primary misses count as unoccluded.
+__global__ void __launch_bounds__(256)
+    gen_ao_kernel(nrt_ao_params p, unsigned long long slot0, uint32_t count, Wave w,
+                  const float *__restrict__ verts, const uint32_t *__restrict__ faces, float *__restrict__ accum,
+                  unsigned long long *counters /* [0] ao rays of this wave, [1] valid primaries */) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool make = false;
+  float4 o4 = make_float4(0, 0, 0, 0), d4 = make_float4(0, 0, 0, 0);
+  uint32_t pix = 0xFFFFFFFFu;
+  if (i < count) {
+    pix = w.pix[i];
+    if (pix != 0xFFFFFFFFu) {
+      const Hit16 h = w.hits[i];
+      if (h.prim_id == 0xFFFFFFFFu) {
+        atomicAdd(accum + pix, 1.0f);
+      } else {
+        const float4 o = w.org_tmin[i], d = w.dir_tmax[i];
+        const float Px = o.x + d.x * h.t, Py = o.y + d.y * h.t, Pz = o.z + d.z * h.t;
+        const uint32_t f0 = faces[3 * (size_t)h.prim_id], f1 = faces[3 * (size_t)h.prim_id + 1],
+                       f2 = faces[3 * (size_t)h.prim_id + 2];
+        const float *p0 = verts + 3 * (size_t)f0, *p1 = verts + 3 * (size_t)f1, *p2 = verts + 3 * (size_t)f2;
+        const float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
+        const float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
+        float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+        float ln = sqrtf(nx * nx + ny * ny + nz * nz);
+        ln = ln > 0.0f ? 1.0f / ln : 0.0f;
+        nx *= ln;
+        ny *= ln;
+        nz *= ln;
+        if (nx * d.x + ny * d.y + nz * d.z > 0.0f) {
+          nx = -nx;
+          ny = -ny;
+          nz = -nz;
+        }
+        // branch-free orthonormal basis around n
+        const float sg = nz >= 0.0f ? 1.0f : -1.0f;
+        const float a = -1.0f / (sg + nz), b = nx * ny * a;
+        const float t1x = 1.0f + sg * nx * nx * a, t1y = sg * b, t1z = -sg * nx;
+        const float t2x = b, t2y = sg + ny * ny * a, t2z = -ny;
+        const uint32_t smp = p.sample0 + (uint32_t)(((slot0 + i) % ((unsigned long long)p.tile_w * p.tile_h * p.spp)) /
+                                                    (p.tile_w * p.tile_h));
+        const float u1 = rand_ps(pix, smp, 2, p.seed), u2 = rand_ps(pix, smp, 3, p.seed);
+        const float r = sqrtf(u1), ph = 6.28318530718f * u2;
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        const float lx = r * cs, ly = r * sn, lz = sqrtf(fmaxf(0.0f, 1.0f - u1));
+        float wx = t1x * lx + t2x * ly + nx * lz, wy = t1y * lx + t2y * ly + ny * lz,
+              wz = t1z * lx + t2z * ly + nz * lz;
+        const float il = 1.0f / sqrtf(wx * wx + wy * wy + wz * wz);
+        o4 = make_float4(Px, Py, Pz, p.ao_min_t);
+        d4 = make_float4(wx * il, wy * il, wz * il, p.ao_max_t);
+        make = true;
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, make);
+  const unsigned valid = __ballot_sync(0xFFFFFFFFu, pix != 0xFFFFFFFFu);
+  if (m == 0u && valid == 0u) return;
+  unsigned long long base = 0;
+  if (lane == 0) {
+    if (m) base = atomicAdd(counters + 0, (unsigned long long)__popc(m));
+    if (valid) atomicAdd(counters + 1, (unsigned long long)__popc(valid));
+  }
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (make) {
+    const unsigned long long j = base + __popc(m & ((1u << lane) - 1u));
+    w.ao_org_tmin[j] = o4;
+    w.ao_dir_tmax[j] = d4;
+    w.ao_pix[j] = pix;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    accumulate_ao_kernel(Wave w, const unsigned long long *__restrict__ counters, float *__restrict__ accum,
+                         unsigned long long *totals /* [0] ao rays, [1] ao hits, [2] primaries */) {
+  const unsigned long long n = counters[0];
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool occluded = false;
+  if (i < n) {
+    occluded = w.ao_hits[i].prim_id != 0xFFFFFFFFu;
+    if (!occluded) atomicAdd(accum + w.ao_pix[i], 1.0f);
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, occluded);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(totals + 1, (unsigned long long)__popc(m));
+  if (i == 0) {
+    atomicAdd(totals + 0, n);
+    atomicAdd(totals + 2, counters[1]);
+  }
+}
+
+}  // namespace
+
+// launch_traverse_soa needs the ray count on the host; AO counts are produced on the device, so the
+// AO traversal is launched over the wave capacity with a device-side count (see traverse.cu).
+int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const float4 *d_dir_tmax,
+                                 const unsigned long long *d_count, size_t capacity, Hit16 *d_hits,
+                                 const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
+
+}  // namespace nrt
+
+using namespace nrt;
+
+extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp, float *d_accum, nrt_ao_result *res,
+                                    void *stream) {
+  if (!h || !pp || !d_accum) {
+    set_error("nrt_render_ao_device: NULL argument");
+    return NRT_ERR_INVALID;
+  }
+  Accel *a = const_cast<Accel *>(reinterpret_cast<const Accel *>(h));
+  nrt_ao_params p = *pp;
+  if (p.width == 0 || p.height == 0 || p.spp == 0 || p.n_shards == 0 || p.shard >= p.n_shards || p.tile_w == 0 ||
+      p.tile_h == 0 || (p.tile_w % 8) != 0 || (p.tile_h % 4) != 0) {
+    set_error("nrt_render_ao_device: bad parameters (tiles must be multiples of 8x4 pixels)");
+    return NRT_ERR_INVALID;
+  }
+  NRT_CUDA(cudaSetDevice(a->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint32_t tiles_x = (p.width + p.tile_w - 1) / p.tile_w, tiles_y = (p.height + p.tile_h - 1) / p.tile_h;
+  const uint32_t n_tiles = tiles_x * tiles_y;
+  const uint32_t my_tiles = n_tiles > p.shard ? (n_tiles - p.shard + p.n_shards - 1) / p.n_shards : 0;
+  const unsigned long long per_tile = (unsigned long long)p.tile_w * p.tile_h * p.spp;
+  const unsigned long long total_slots = (unsigned long long)my_tiles * per_tile;
+
+  // wave capacity: whole tiles, at most ~8 Mi rays (832 MiB of queues, far beyond the 126 MB L2)
+  const unsigned long long kMaxWave = 8ull << 20;
+  unsigned long long tiles_per_wave = kMaxWave / per_tile;
+  if (tiles_per_wave == 0) tiles_per_wave = 1;
+  const unsigned long long cap = std::min<unsigned long long>(total_slots, tiles_per_wave * per_tile);
+  const size_t per_ray = 2 * sizeof(float4) + sizeof(Hit16) + 4 + 2 * sizeof(float4) + 4 + sizeof(Hit16);
+  const size_t need = (size_t)cap * per_ray + 256;
+  if (a->wave_bytes < need) {
+    cudaFree(a->d_wave);
+    a->d_wave = nullptr;
+    a->wave_bytes = 0;
+    NRT_CUDA(cudaMalloc(&a->d_wave, need));
+    a->wave_bytes = need;
+  }
+  Wave w;
+  {
+    char *b = static_cast<char *>(a->d_wave);
+    w.org_tmin = reinterpret_cast<float4 *>(b);
+    b += cap * sizeof(float4);
+    w.dir_tmax = reinterpret_cast<float4 *>(b);
+    b += cap * sizeof(float4);
+    w.ao_org_tmin = reinterpret_cast<float4 *>(b);
+    b += cap * sizeof(float4);
+    w.ao_dir_tmax = reinterpret_cast<float4 *>(b);
+    b += cap * sizeof(float4);
+    w.hits = reinterpret_cast<Hit16 *>(b);
+    b += cap * sizeof(Hit16);
+    w.ao_hits = reinterpret_cast<Hit16 *>(b);
+    b += cap * sizeof(Hit16);
+    w.pix = reinterpret_cast<uint32_t *>(b);
+    b += cap * 4;
+    w.ao_pix = reinterpret_cast<uint32_t *>(b);
+  }
+  unsigned long long *wave_ctr = reinterpret_cast<unsigned long long *>(a->d_counters) + 2;  // [2],[3]
+  unsigned long long *totals = reinterpret_cast<unsigned long long *>(a->d_counters) + 4;    // [4..6]
+  NRT_CUDA(cudaMemsetAsync(totals, 0, 3 * sizeof(unsigned long long), s));
+
+  TraceOptions16 opt = default_trace_options();
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t e_begin = nullptr, e_end = nullptr;
+  if (res) {
+    NRT_CUDA(cudaEventCreate(&e_begin));
+    NRT_CUDA(cudaEventCreate(&e_end));
+    NRT_CUDA(cudaEventRecord(e_begin, s));
+  }
+  uint32_t launches = 0, trav_launches = 0;
+  int rc = NRT_OK;
+  for (unsigned long long s0 = 0; s0 < total_slots && rc == NRT_OK; s0 += cap) {
+    const uint32_t count = (uint32_t)std::min<unsigned long long>(cap, total_slots - s0);
+    const uint32_t grid = (count + 255) / 256;
+    cudaMemsetAsync(wave_ctr, 0, 2 * sizeof(unsigned long long), s);
+    gen_primary_kernel<<<grid, 256, 0, s>>>(p, s0, count, w);
+    launches++;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
+    if (res) {
+      cudaEventCreate(&t0);
+      cudaEventCreate(&t1);
+      cudaEventCreate(&t2);
+      cudaEventCreate(&t3);
+      ev.push_back(t0);
+      ev.push_back(t1);
+      ev.push_back(t2);
+      ev.push_back(t3);
+      cudaEventRecord(t0, s);
+    }
+    rc = launch_traverse_soa(a, w.org_tmin, w.dir_tmax, count, w.hits, opt, p.flags, s);
+    if (rc != NRT_OK) break;
+    if (res) cudaEventRecord(t1, s);
+    launches++;
+    trav_launches++;
+    gen_ao_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, a->d_verts, a->d_faces, d_accum, wave_ctr);
+    launches++;
+    if (res) cudaEventRecord(t2, s);
+    rc = launch_traverse_soa_devcount(a, w.ao_org_tmin, w.ao_dir_tmax, wave_ctr, count, w.ao_hits, opt, p.flags, s);
+    if (rc != NRT_OK) break;
+    if (res) cudaEventRecord(t3, s);
+    launches++;
+    trav_launches++;
+    accumulate_ao_kernel<<<grid, 256, 0, s>>>(w, wave_ctr, d_accum, totals);
+    launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = NRT_ERR_CUDA;
+  }
+  if (rc == NRT_OK && res) {
+    unsigned long long ht[3] = {0, 0, 0};
+    cudaEventRecord(e_end, s);
+    cudaError_t e = cudaMemcpyAsync(ht, totals, sizeof(ht), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e, "nrt_render_ao_device read-back", __FILE__, __LINE__);
+    } else {
+      res->ao_rays = ht[0];
+      res->ao_hits = ht[1];
+      res->primary_rays = ht[2];
+      float tms = 0.0f, total = 0.0f;
+      for (size_t i = 0; i + 3 < ev.size(); i += 4) {
+        float m1 = 0, m2 = 0;
+        cudaEventElapsedTime(&m1, ev[i], ev[i + 1]);
+        cudaEventElapsedTime(&m2, ev[i + 2], ev[i + 3]);
+        tms += m1 + m2;
+      }
+      cudaEventElapsedTime(&total, e_begin, e_end);
+      res->traverse_ms = tms;
+      res->total_ms = total;
+      res->launches = launches;
+      res->traverse_launches = trav_launches;
+    }
+  }
+  for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  if (e_begin) cudaEventDestroy(e_begin);
+  if (e_end) cudaEventDestroy(e_end);
+  return rc;
+}

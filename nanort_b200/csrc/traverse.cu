@@ -1,0 +1,548 @@
+// Ray traversal kernels (sm_100a).  Compiled with --fmad=false: every float
+// operation below is individually rounded, exactly like the reference's x86-64
+// SSE2 scalar code, so sign decisions on U/V/W and
+// the reported t/u/v are bit-identical to CPU nanort for the same triangle.
+//
+// Replaces (file:line under /root/reference):
+//   BVHAccel<float>::Traverse            nanort.h:2487-2556
+//   BVHAccel<float>::TestLeafNode        nanort.h:2372-2407
+//   IntersectRayAABB<float>              nanort.h:2284-2325
+//   TriangleIntersector::Intersect       nanort.h:1054-1150
+//   TriangleIntersector::PrepareTraversal nanort.h:1163-1201
+//   vsafe_inverse                        nanort.h:414-465
+#include <float.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace nrt {
+
+#define FULL_MASK 0xFFFFFFFFu
+
+// ------------------------------------------------------------------ per-ray constants
+struct RayCtx {
+  float ox, oy, oz;
+  float ix, iy, iz;  // vsafe_inverse(dir)
+  float Sx, Sy, Sz;  // watertight shear constants
+  float t_min;
+  int sx, sy, sz;    // dir < 0
+  int kx, ky, kz;
+};
+
+__device__ __forceinline__ float safe_inverse(float d, bool cpp03) {
+  if (fabsf(d) < FLT_EPSILON) {
+    // C++11 mode: copysign(1, d) -> -0.0f gives -inf; C++03 mode: (d < 0) ? -1 : 1 -> -0.0f gives +inf
+    bool neg = cpp03 ? (d < 0.0f) : (__float_as_uint(d) >> 31) != 0u;
+    return neg ? -CUDART_INF_F : CUDART_INF_F;
+  }
+  return 1.0f / d;
+}
+
+__device__ __forceinline__ float sel3(int k, float x, float y, float z) {
+  return k == 0 ? x : (k == 1 ? y : z);
+}
+
+__device__ __forceinline__ void setup_ray(RayCtx &c, float ox, float oy, float oz, float dx, float dy,
+                                          float dz, float min_t, bool cpp03) {
+  c.ox = ox;
+  c.oy = oy;
+  c.oz = oz;
+  c.sx = dx < 0.0f;
+  c.sy = dy < 0.0f;
+  c.sz = dz < 0.0f;
+  c.ix = safe_inverse(dx, cpp03);
+  c.iy = safe_inverse(dy, cpp03);
+  c.iz = safe_inverse(dz, cpp03);
+  int kz = 0;
+  float m = fabsf(dx);
+  if (m < fabsf(dy)) {
+    kz = 1;
+    m = fabsf(dy);
+  }
+  if (m < fabsf(dz)) kz = 2;
+  int kx = (kz == 2) ? 0 : kz + 1;
+  int ky = (kx == 2) ? 0 : kx + 1;
+  float dkz = sel3(kz, dx, dy, dz);
+  if (dkz < 0.0f) {
+    int t = kx;
+    kx = ky;
+    ky = t;
+  }
+  c.kx = kx;
+  c.ky = ky;
+  c.kz = kz;
+  c.Sx = sel3(kx, dx, dy, dz) / dkz;
+  c.Sy = sel3(ky, dx, dy, dz) / dkz;
+  c.Sz = 1.0f / dkz;
+  c.t_min = min_t;
+}
+
+// Slab test of one box (nanort.h:2284-2325).  fmaxf/fminf drop a NaN operand
+// exactly like the reference's safemax/safemin do for the per-axis value in
+// the first slot; the running value is never NaN.
+__device__ __forceinline__ bool slab(const RayCtx &c, float lox, float loy, float loz, float hix,
+                                     float hiy, float hiz, float min_t, float max_t, float &tnear) {
+  float nx = c.sx ? hix : lox, fx = c.sx ? lox : hix;
+  float ny = c.sy ? hiy : loy, fy = c.sy ? loy : hiy;
+  float nz = c.sz ? hiz : loz, fz = c.sz ? loz : hiz;
+  float tnx = (nx - c.ox) * c.ix;
+  float tny = (ny - c.oy) * c.iy;
+  float tnz = (nz - c.oz) * c.iz;
+  float tfx = ((fx - c.ox) * c.ix) * 1.00000024f;
+  float tfy = ((fy - c.oy) * c.iy) * 1.00000024f;
+  float tfz = ((fz - c.oz) * c.iz) * 1.00000024f;
+  float tmin = fmaxf(tnz, fmaxf(tny, fmaxf(tnx, min_t)));
+  float tmax = fminf(tfz, fminf(tfy, fminf(tfx, max_t)));
+  tnear = tmin;
+  return tmin <= tmax;
+}
+
+struct Best {
+  float t, u, v;
+  uint32_t prim;
+};
+
+// Watertight ray/triangle test, arithmetic order of nanort.h:1073-1147.
+// Accepts t_min <= tt <= best.t (ties replace, like the reference).
+__device__ __forceinline__ bool tri_test(const RayCtx &c, const TraceOptions16 &opt, float4 a, float4 b,
+                                         float4 cc, Best &best) {
+  uint32_t prim = __float_as_uint(a.w);
+  if (prim < opt.prim_ids_range[0] || prim >= opt.prim_ids_range[1]) return false;
+  if (prim == opt.skip_prim_id) return false;
+  float A0 = a.x - c.ox, A1 = a.y - c.oy, A2 = a.z - c.oz;
+  float B0 = b.x - c.ox, B1 = b.y - c.oy, B2 = b.z - c.oz;
+  float C0 = cc.x - c.ox, C1 = cc.y - c.oy, C2 = cc.z - c.oz;
+  float Akz = sel3(c.kz, A0, A1, A2), Bkz = sel3(c.kz, B0, B1, B2), Ckz = sel3(c.kz, C0, C1, C2);
+  float Ax = sel3(c.kx, A0, A1, A2) - c.Sx * Akz;
+  float Ay = sel3(c.ky, A0, A1, A2) - c.Sy * Akz;
+  float Bx = sel3(c.kx, B0, B1, B2) - c.Sx * Bkz;
+  float By = sel3(c.ky, B0, B1, B2) - c.Sy * Bkz;
+  float Cx = sel3(c.kx, C0, C1, C2) - c.Sx * Ckz;
+  float Cy = sel3(c.ky, C0, C1, C2) - c.Sy * Ckz;
+  float U = Cx * By - Cy * Bx;
+  float V = Ax * Cy - Ay * Cx;
+  float W = Bx * Ay - By * Ax;
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    // exact products in binary64, one rounding in the subtraction, one in the narrowing
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  if (U < 0.0f || V < 0.0f || W < 0.0f) {
+    if (opt.cull_back_face || U > 0.0f || V > 0.0f || W > 0.0f) return false;
+  }
+  float det = (U + V) + W;
+  if (det == 0.0f) return false;
+  float Az = c.Sz * Akz, Bz = c.Sz * Bkz, Cz = c.Sz * Ckz;
+  float D = (U * Az + V * Bz) + W * Cz;
+  float rcp = 1.0f / det;
+  float tt = D * rcp;
+  if (tt > best.t) return false;
+  if (tt < c.t_min) return false;
+  best.t = tt;
+  best.u = V * rcp;
+  best.v = W * rcp;
+  best.prim = prim;
+  return true;
+}
+
+__device__ __forceinline__ void write_result(Hit16 *hits, uint8_t *mask, size_t i, const Best &best,
+                                             float max_t) {
+  bool hit = best.t < max_t;  // a hit exactly at max_t is a miss (nanort.h:2552)
+  float4 r;
+  if (hit) {
+    r = make_float4(best.u, best.v, best.t, __uint_as_float(best.prim));
+  } else {
+    r = make_float4(0.0f, 0.0f, max_t, __uint_as_float(0xFFFFFFFFu));
+  }
+  reinterpret_cast<float4 *>(hits)[i] = r;
+  if (mask) mask[i] = hit ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ ray loaders
+struct AosRays {
+  const Ray36 *rays;
+  __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy,
+                                       float &dz, float &tmin, float &tmax) const {
+    const float *p = reinterpret_cast<const float *>(rays + i);
+    ox = __ldg(p + 0);
+    oy = __ldg(p + 1);
+    oz = __ldg(p + 2);
+    dx = __ldg(p + 3);
+    dy = __ldg(p + 4);
+    dz = __ldg(p + 5);
+    tmin = __ldg(p + 6);
+    tmax = __ldg(p + 7);
+  }
+};
+
+struct SoaRays {
+  const float4 *org_tmin;
+  const float4 *dir_tmax;
+  __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy,
+                                       float &dz, float &tmin, float &tmax) const {
+    float4 o = __ldg(org_tmin + i);
+    float4 d = __ldg(dir_tmax + i);
+    ox = o.x;
+    oy = o.y;
+    oz = o.z;
+    tmin = o.w;
+    dx = d.x;
+    dy = d.y;
+    dz = d.z;
+    tmax = d.w;
+  }
+};
+
+// ------------------------------------------------------------------ conformance walk
+// One thread per ray over the nanort 40-byte node array, in the reference's
+// exact order: pop, slab-test against the current best, near child by
+// dir_sign[node.axis], leaf prims in indices_ order (nanort.h:2526-2547).
+constexpr int kConfStack = 512;  // kNANORT_MAX_STACK_DEPTH
+
+template <class Rays, bool COUNT>
+__global__ void __launch_bounds__(128)
+    traverse_conformance_kernel(const Node40 *__restrict__ nodes, const PackedTri *__restrict__ tris,
+                                Rays rays, size_t n, Hit16 *__restrict__ hits, uint8_t *__restrict__ mask,
+                                TraceOptions16 opt, uint32_t flags, unsigned long long *counts,
+                                const unsigned long long *n_ptr) {
+  if (n_ptr) n = (size_t)*n_ptr;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_boxes = 0, n_prims = 0;
+  if (i < n) {
+    float ox, oy, oz, dx, dy, dz, min_t, max_t;
+    rays.load(i, ox, oy, oz, dx, dy, dz, min_t, max_t);
+    RayCtx c;
+    setup_ray(c, ox, oy, oz, dx, dy, dz, min_t, (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0);
+    Best best;
+    best.t = max_t;
+    best.u = 0.0f;
+    best.v = 0.0f;
+    best.prim = 0xFFFFFFFFu;
+    float hit_t = max_t;
+    uint32_t stack[kConfStack];
+    int sp = 0;
+    stack[0] = 0;
+    while (sp >= 0) {
+      const Node40 *nd = nodes + stack[sp];
+      sp--;
+      const float *f = reinterpret_cast<const float *>(nd);
+      float lox = __ldg(f + 0), loy = __ldg(f + 1), loz = __ldg(f + 2);
+      float hix = __ldg(f + 3), hiy = __ldg(f + 4), hiz = __ldg(f + 5);
+      if (COUNT) n_boxes++;
+      float tn;
+      if (!slab(c, lox, loy, loz, hix, hiy, hiz, min_t, hit_t, tn)) continue;
+      int flag = __ldg(&nd->flag);
+      uint32_t d0 = __ldg(&nd->data[0]), d1 = __ldg(&nd->data[1]);
+      if (flag == 0) {
+        int axis = __ldg(&nd->axis);
+        int sgn = axis == 0 ? c.sx : (axis == 1 ? c.sy : c.sz);
+        uint32_t nearc = sgn ? d1 : d0;
+        uint32_t farc = sgn ? d0 : d1;
+        if (sp + 2 < kConfStack) {  // the reference only asserts here (nanort.h:2550)
+          stack[++sp] = farc;
+          stack[++sp] = nearc;
+        }
+      } else {
+        bool any = false;
+        for (uint32_t k = 0; k < d0; k++) {
+          const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)d1 + k);
+          float4 a = __ldg(t), b = __ldg(t + 1), cc = __ldg(t + 2);
+          if (COUNT) n_prims++;
+          if (tri_test(c, opt, a, b, cc, best)) any = true;
+        }
+        if (any) hit_t = best.t;
+      }
+    }
+    if (hits) write_result(hits, mask, i, best, max_t);
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_boxes += __shfl_down_sync(FULL_MASK, n_boxes, o);
+      n_prims += __shfl_down_sync(FULL_MASK, n_prims, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(counts + 0, n_boxes);
+      atomicAdd(counts + 1, n_prims);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fast path
+// Persistent warps pull rays from a global cursor and replace finished rays
+// with new ones once enough lanes of the warp have retired (warp-ballot
+// compaction of the ray pool).  Traversal is while-while with one postponed
+// leaf per lane over the 64-byte child-pair nodes; the per-lane stack keeps
+// (ref, entry distance) so that a popped subtree that now lies behind the
+// current best is skipped without touching memory -- the same visit set the
+// reference obtains by re-testing the box when it is popped (nanort.h:2532).
+// The first kStackSmem stack entries of every lane live in shared memory
+// ([entry][lane] -> bank == lane, conflict free); deeper entries spill to
+// thread-local memory.
+constexpr int kNone = kEmptyLeaf;
+constexpr int kFastBlock = 128;
+constexpr int kStackSmem = 16;
+
+template <int LOCAL_DEPTH>
+struct LaneStack {
+  uint2 *smem;  // &stk[0][threadIdx.x]; stride kFastBlock
+  uint2 local[LOCAL_DEPTH];
+  int sp;
+  __device__ __forceinline__ void push(int ref, float t) {
+    uint2 e = make_uint2((uint32_t)ref, __float_as_uint(t));
+    if (sp < kStackSmem)
+      smem[sp * kFastBlock] = e;
+    else if (sp - kStackSmem < LOCAL_DEPTH)
+      local[sp - kStackSmem] = e;
+    sp++;
+  }
+  __device__ __forceinline__ uint2 pop_raw() {
+    sp--;
+    if (sp < kStackSmem) return smem[sp * kFastBlock];
+    if (sp - kStackSmem < LOCAL_DEPTH) return local[sp - kStackSmem];
+    return make_uint2((uint32_t)kNone, 0u);
+  }
+};
+
+template <class Rays, int LOCAL_DEPTH, bool COUNT>
+__global__ void __launch_bounds__(kFastBlock)
+    traverse_fast_kernel(const WideNode *__restrict__ wide, const PackedTri *__restrict__ tris, Rays rays,
+                         size_t n, Hit16 *__restrict__ hits, uint8_t *__restrict__ mask, TraceOptions16 opt,
+                         uint32_t flags, unsigned long long *cursor, unsigned long long *counts,
+                         int refill_min, const unsigned long long *n_ptr) {
+  __shared__ uint2 stk[kStackSmem][kFastBlock];
+  if (n_ptr) n = (size_t)*n_ptr;  // ray count produced on the device (compacted AO queue)
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
+
+  LaneStack<LOCAL_DEPTH> st;
+  st.smem = &stk[0][threadIdx.x];
+  st.sp = 0;
+
+  RayCtx c;
+  Best best;
+  float max_t = 0.0f, min_t = 0.0f;
+  long long ray_idx = -1;
+  int cur = kNone, leaf = kNone;
+  bool exhausted = false;
+  unsigned long long n_boxes = 0, n_prims = 0;
+
+  for (;;) {
+    // ---- replace retired rays
+    unsigned dead = __ballot_sync(FULL_MASK, ray_idx < 0);
+    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= refill_min)) {
+      int cnt = __popc(dead);
+      int leader = __ffs(dead) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(cursor, (unsigned long long)cnt);
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
+      if (ray_idx < 0) {
+        unsigned long long mine = base + (unsigned long long)__popc(dead & lt_mask);
+        if (mine < (unsigned long long)n) {
+          float ox, oy, oz, dx, dy, dz;
+          rays.load((size_t)mine, ox, oy, oz, dx, dy, dz, min_t, max_t);
+          setup_ray(c, ox, oy, oz, dx, dy, dz, min_t, cpp03);
+          best.t = max_t;
+          best.u = 0.0f;
+          best.v = 0.0f;
+          best.prim = 0xFFFFFFFFu;
+          ray_idx = (long long)mine;
+          st.sp = 0;
+          cur = 0;  // root pair
+          leaf = kNone;
+          if (COUNT) n_boxes += 1;  // the root box the reference pops first
+        }
+      }
+    }
+    if (__all_sync(FULL_MASK, ray_idx < 0)) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- inner nodes: until every lane holds a leaf (or nothing)
+    while (__any_sync(FULL_MASK, cur >= 0)) {
+      if (cur >= 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
+        float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+        int4 q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        float t0, t1;
+        bool h0 = slab(c, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, min_t, best.t, t0);
+        bool h1 = slab(c, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, min_t, best.t, t1);
+        if (COUNT) n_boxes += 2;
+        h0 = h0 && (q3.x != kNone);
+        h1 = h1 && (q3.y != kNone);
+        int next = kNone;
+        if (h0 && h1) {
+          bool swap = t1 < t0;
+          int nearr = swap ? q3.y : q3.x;
+          int farr = swap ? q3.x : q3.y;
+          st.push(farr, swap ? t0 : t1);
+          next = nearr;
+        } else if (h0) {
+          next = q3.x;
+        } else if (h1) {
+          next = q3.y;
+        } else {
+          // pop, skipping entries that now start behind the best hit
+          while (st.sp > 0) {
+            uint2 e = st.pop_raw();
+            if (__uint_as_float(e.y) <= best.t) {
+              next = (int)e.x;
+              break;
+            }
+          }
+        }
+        cur = next;
+        if (cur < 0 && cur != kNone && leaf == kNone) {
+          // postpone the first leaf and keep descending
+          leaf = cur;
+          cur = kNone;
+          while (st.sp > 0) {
+            uint2 e = st.pop_raw();
+            if (__uint_as_float(e.y) <= best.t) {
+              cur = (int)e.x;
+              break;
+            }
+          }
+        }
+      }
+    }
+
+    // ---- leaves
+    while (__any_sync(FULL_MASK, leaf != kNone)) {
+      if (leaf != kNone) {
+        const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)(~leaf));
+        for (;;) {
+          float4 a = __ldg(t), b = __ldg(t + 1), cc = __ldg(t + 2);
+          if (COUNT) n_prims++;
+          tri_test(c, opt, a, b, cc, best);
+          if (__float_as_uint(b.w) != 0u) break;  // last triangle of this leaf
+          t += 3;
+        }
+        leaf = kNone;
+        if (cur < 0 && cur != kNone) {
+          leaf = cur;
+          cur = kNone;
+          while (st.sp > 0) {
+            uint2 e = st.pop_raw();
+            if (__uint_as_float(e.y) <= best.t) {
+              cur = (int)e.x;
+              break;
+            }
+          }
+        }
+      }
+    }
+
+    // ---- retire
+    if (ray_idx >= 0 && cur == kNone && leaf == kNone) {
+      // cur == kNone with a non-empty stack can only mean all remaining entries were culled above
+      if (hits) write_result(hits, mask, (size_t)ray_idx, best, max_t);
+      ray_idx = -1;
+    }
+  }
+
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_boxes += __shfl_down_sync(FULL_MASK, n_boxes, o);
+      n_prims += __shfl_down_sync(FULL_MASK, n_prims, o);
+    }
+    if (lane == 0) {
+      atomicAdd(counts + 0, n_boxes);
+      atomicAdd(counts + 1, n_prims);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+static int g_sm_count[64] = {0};
+int device_sm_count(int device) {
+  if (device < 0 || device >= 64) return 148;
+  if (g_sm_count[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+    g_sm_count[device] = v;
+  }
+  return g_sm_count[device];
+}
+
+template <class Rays, bool COUNT>
+static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
+                       const TraceOptions16 &opt, uint32_t flags, unsigned long long *d_counts, cudaStream_t s,
+                       const unsigned long long *n_ptr = nullptr) {
+  unsigned long long *cursor =
+      reinterpret_cast<unsigned long long *>(a->d_counters) + 16 + (a->cursor_ring.fetch_add(1) & 31u);
+  NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+  int sms = device_sm_count(a->device);
+  // wide-node stack depth never exceeds the tree depth
+  bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
+  int blocks_per_sm = 8;
+  size_t warps_needed = (n + 31) / 32;
+  size_t grid = (size_t)sms * blocks_per_sm;
+  size_t need_blocks = (warps_needed + (kFastBlock / 32) - 1) / (kFastBlock / 32);
+  if (grid > need_blocks) grid = need_blocks;
+  if (grid == 0) grid = 1;
+  const int refill_min = 8;
+  if (deep) {
+    traverse_fast_kernel<Rays, 512 - kStackSmem, COUNT><<<(unsigned)grid, kFastBlock, 0, s>>>(
+        a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, refill_min, n_ptr);
+  } else {
+    traverse_fast_kernel<Rays, 48, COUNT><<<(unsigned)grid, kFastBlock, 0, s>>>(
+        a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, refill_min, n_ptr);
+  }
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+template <class Rays, bool COUNT>
+static int launch_conf(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
+                       const TraceOptions16 &opt, uint32_t flags, unsigned long long *d_counts, cudaStream_t s,
+                       const unsigned long long *n_ptr = nullptr) {
+  size_t grid = (n + 127) / 128;
+  if (grid == 0) return NRT_OK;
+  traverse_conformance_kernel<Rays, COUNT><<<(unsigned)grid, 128, 0, s>>>(a->d_nodes, a->d_tris, rays, n, d_hits,
+                                                                       d_mask, opt, flags, d_counts, n_ptr);
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+int launch_traverse(const Accel *a, const Ray36 *d_rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
+                    const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  if (n == 0) return NRT_OK;
+  AosRays r{d_rays};
+  if (flags & NRT_TRAVERSE_CONFORMANCE) return launch_conf<AosRays, false>(a, r, n, d_hits, d_mask, opt, flags, nullptr, s);
+  return launch_fast<AosRays, false>(a, r, n, d_hits, d_mask, opt, flags, nullptr, s);
+}
+
+int launch_traverse_soa(const Accel *a, const float4 *d_org_tmin, const float4 *d_dir_tmax, size_t n,
+                        Hit16 *d_hits, const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  if (n == 0) return NRT_OK;
+  SoaRays r{d_org_tmin, d_dir_tmax};
+  if (flags & NRT_TRAVERSE_CONFORMANCE) return launch_conf<SoaRays, false>(a, r, n, d_hits, nullptr, opt, flags, nullptr, s);
+  return launch_fast<SoaRays, false>(a, r, n, d_hits, nullptr, opt, flags, nullptr, s);
+}
+
+// `capacity` bounds the count stored at d_count (grid sizing only).
+int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const float4 *d_dir_tmax,
+                                 const unsigned long long *d_count, size_t capacity, Hit16 *d_hits,
+                                 const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  if (capacity == 0) return NRT_OK;
+  SoaRays r{d_org_tmin, d_dir_tmax};
+  if (flags & NRT_TRAVERSE_CONFORMANCE)
+    return launch_conf<SoaRays, false>(a, r, capacity, d_hits, nullptr, opt, flags, nullptr, s, d_count);
+  return launch_fast<SoaRays, false>(a, r, capacity, d_hits, nullptr, opt, flags, nullptr, s, d_count);
+}
+
+int launch_traverse_count(const Accel *a, const Ray36 *d_rays, size_t n, const TraceOptions16 &opt,
+                          uint32_t flags, uint64_t *d_counts2, cudaStream_t s) {
+  NRT_CUDA(cudaMemsetAsync(d_counts2, 0, 2 * sizeof(uint64_t), s));
+  if (n == 0) return NRT_OK;
+  AosRays r{d_rays};
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(d_counts2);
+  if (flags & NRT_TRAVERSE_CONFORMANCE) return launch_conf<AosRays, true>(a, r, n, nullptr, nullptr, opt, flags, cnt, s);
+  return launch_fast<AosRays, true>(a, r, n, nullptr, nullptr, opt, flags, cnt, s);
+}
+
+}  // namespace nrt

@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing: rays are sharded by image tile, the BVH is replicated, and the only exchange is
+the final framebuffer gather.  One process per GPU; torch.distributed carries the
+collective (NCCL on GPUs, gloo in the CPU tests).
+
+Tile k (row-major over the tile grid) belongs to shard k % n_shards -- the same rule as
+csrc/render.cu:slot_to_pixel, which this module mirrors on the host for the gather."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_tiles(width, height, tile_w, tile_h, shard, n_shards):
+    tiles_x = (width + tile_w - 1) // tile_w
+    tiles_y = (height + tile_h - 1) // tile_h
+    return np.arange(shard, tiles_x * tiles_y, n_shards, dtype=np.int64), tiles_x
+
+
+def shard_pixels(width, height, tile_w, tile_h, shard, n_shards):
+    """Flat pixel indices (y*width+x) owned by `shard`, tile-major / row-major inside the tile."""
+    tiles, tiles_x = shard_tiles(width, height, tile_w, tile_h, shard, n_shards)
+    ly, lx = np.meshgrid(np.arange(tile_h), np.arange(tile_w), indexing="ij")
+    x = (tiles % tiles_x)[:, None] * tile_w + lx.reshape(-1)[None, :]
+    y = (tiles // tiles_x)[:, None] * tile_h + ly.reshape(-1)[None, :]
+    ok = (x < width) & (y < height)
+    return (y * width + x)[ok]
+
+
+def shard_ray_count(width, height, tile_w, tile_h, shard, n_shards, spp):
+    return int(len(shard_pixels(width, height, tile_w, tile_h, shard, n_shards))) * int(spp)
+
+
+class FramebufferGather:
+    """all_gather of every rank's own pixels (packed, padded to the largest shard) + scatter into the frame.
+    Built once per (image, tiling, world); `gather(local_frame)` returns the full frame on every rank."""
+
+    def __init__(self, width, height, tile_w, tile_h, world_size, rank, device):
+        import torch
+
+        self.world, self.rank = world_size, rank
+        self.n_pix = width * height
+        px = [shard_pixels(width, height, tile_w, tile_h, r, world_size) for r in range(world_size)]
+        self.pad = max(len(p) for p in px)
+        self.mine = torch.as_tensor(px[rank], dtype=torch.int64, device=device)
+        self.all_idx = [torch.as_tensor(p, dtype=torch.int64, device=device) for p in px]
+        self.send = torch.zeros(self.pad, dtype=torch.float32, device=device)
+        self.recv = torch.zeros(self.pad * world_size, dtype=torch.float32, device=device)
+        self.bytes_per_rank = self.pad * 4
+
+    def gather(self, local_frame):
+        import torch
+        import torch.distributed as dist
+
+        flat = local_frame.reshape(-1)
+        self.send[: len(self.mine)] = flat[self.mine]
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.recv, self.send)
+        else:
+            self.recv.copy_(self.send)
+        out = torch.zeros(self.n_pix, dtype=torch.float32, device=flat.device)
+        for r in range(self.world):
+            out[self.all_idx[r]] = self.recv[r * self.pad: r * self.pad + len(self.all_idx[r])]
+        return out

@@ -47,6 +47,17 @@ def rand01(index: np.ndarray, dim: int, seed: int) -> np.ndarray:
     return ((h >> 8).astype(np.float32)) * np.float32(1.0 / 16777216.0)
 
 
+def rand_ps(pix: np.ndarray, smp: np.ndarray, dim: int, seed: int) -> np.ndarray:
+    """Uniform float32 in [0,1) keyed by (pixel, sample, dimension, seed); all arithmetic wraps at 32 bits.
+    Same function as csrc/render.cu:rand_ps."""
+    M = 0xFFFFFFFF
+    pix = np.asarray(pix, dtype=np.uint64) & M
+    smp = np.asarray(smp, dtype=np.uint64) & M
+    h = hash_u32((pix + ((seed * 0x9E3779B1) & M)) & M).astype(np.uint64)
+    h = hash_u32((h + ((smp * 0x85EBCA77) & M) + ((dim * 0xC2B2AE3D) & M)) & M)
+    return ((h >> 8).astype(np.float32)) * np.float32(1.0 / 16777216.0)
+
+
 # ----------------------------------------------------------------------------- meshes
 def _quad(v, f, a, b, c, d):
     base = len(v)
@@ -247,9 +258,8 @@ def primary_rays(cam, width, height, spp=1, seed=1, pixels=None, sample0=0, min_
     pixels = np.asarray(pixels, np.int64)
     pix = np.repeat(pixels, spp)
     smp = np.tile(np.arange(sample0, sample0 + spp, dtype=np.int64), len(pixels))
-    key = pix * 4096 + smp
-    jx = rand01(key, 0, seed)
-    jy = rand01(key, 1, seed)
+    jx = rand_ps(pix, smp, 0, seed)
+    jy = rand_ps(pix, smp, 1, seed)
     px = (pix % width).astype(np.float32)
     py = (pix // width).astype(np.float32)
     sx = (px + jx) / np.float32(width) - np.float32(0.5)
