@@ -1,0 +1,493 @@
+// nanort.h -- drop-in facade of lighttransport/nanort's header API whose BVH build and ray traversal run
+// on an NVIDIA B200 through the C-ABI of include/nanort_b200.h (libnanort_b200.so).
+//
+// This file is NOT the reference header and shares no code with it.  It re-declares, with the same
+// names, member order and defaults, the part of the API surface that the hot path needs (SURVEY.md
+// section 8b; file:line below are /root/reference/nanort.h):
+//
+//   nanort::Ray<float>                       :474-496   36 bytes
+//   nanort::BVHNode<float>                   :498-550   40 bytes
+//   nanort::BVHBuildOptions<float>           :559-583   28 bytes
+//   nanort::BVHBuildStatistics               :586-599
+//   nanort::BVHTraceOptions                  :604-624   16 bytes
+//   nanort::TriangleSAHPred<float>           :863-919
+//   nanort::TriangleMesh<float>              :922-991
+//   nanort::TriangleIntersection<float>      :996-1005  16 bytes
+//   nanort::TriangleIntersector<float, H>    :1014-1229 (constructors + geometry accessors)
+//   nanort::BVHAccel<float>                  :698-860   Build / Traverse / GetStatistics / GetNodes /
+//                                                        GetIndices / BoundingBox / IsValid / Dump / Load
+//
+// so that a caller written against nanort -- e.g. the loop of examples/path_tracer/main.cc:742-763 and
+// :839-854 -- compiles unchanged and links against -lnanort_b200.  Extension: BVHAccel::TraverseBatch, the
+// batched form of Traverse that a wavefront renderer should use (one call per bounce, not per ray).
+//
+// Only float and the built-in triangle classes are supported (custom Prim/Pred/Intersector models would
+// need device-side user code).  There is no CPU fallback: without a CUDA device Build
+// returns false and Traverse reports a miss after printing nrt_last_error() to stderr.
+#ifndef NANORT_H_
+#define NANORT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <type_traits>
+#include <vector>
+
+#include "nanort_b200.h"
+
+namespace nanort {
+
+// ---- ray type flags (carried in Ray::type, never read by the kernel) -- :86-94
+typedef enum {
+  RAY_TYPE_NONE = 0x0,
+  RAY_TYPE_PRIMARY = 0x1,
+  RAY_TYPE_SECONDARY = 0x2,
+  RAY_TYPE_DIFFUSE = 0x4,
+  RAY_TYPE_REFLECTION = 0x8,
+  RAY_TYPE_REFRACTION = 0x10
+} RayType;
+
+// ---- small 3-vector + helpers of the public namespace -- :321-412
+template <typename T = float>
+class real3 {
+ public:
+  real3() { v[0] = v[1] = v[2] = T(0); }
+  explicit real3(T s) { v[0] = v[1] = v[2] = s; }
+  real3(T x, T y, T z) {
+    v[0] = x;
+    v[1] = y;
+    v[2] = z;
+  }
+  explicit real3(const T *p) {
+    v[0] = p[0];
+    v[1] = p[1];
+    v[2] = p[2];
+  }
+  T x() const { return v[0]; }
+  T y() const { return v[1]; }
+  T z() const { return v[2]; }
+  T operator[](int i) const { return v[i]; }
+  T &operator[](int i) { return v[i]; }
+  real3 operator+(const real3 &o) const { return real3(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
+  real3 operator-(const real3 &o) const { return real3(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+  real3 operator*(const real3 &o) const { return real3(v[0] * o.v[0], v[1] * o.v[1], v[2] * o.v[2]); }
+  real3 operator/(const real3 &o) const { return real3(v[0] / o.v[0], v[1] / o.v[1], v[2] / o.v[2]); }
+  real3 operator*(T s) const { return real3(v[0] * s, v[1] * s, v[2] * s); }
+  real3 operator-() const { return real3(-v[0], -v[1], -v[2]); }
+  real3 &operator+=(const real3 &o) {
+    v[0] += o.v[0];
+    v[1] += o.v[1];
+    v[2] += o.v[2];
+    return *this;
+  }
+  T v[3];
+};
+template <typename T>
+inline real3<T> operator*(T s, const real3<T> &a) {
+  return a * s;
+}
+template <typename T>
+inline T vdot(const real3<T> &a, const real3<T> &b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+template <typename T>
+inline real3<T> vcross(const real3<T> &a, const real3<T> &b) {
+  return real3<T>(a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]);
+}
+template <typename T>
+inline T vlength(const real3<T> &a) {
+  return std::sqrt(vdot(a, a));
+}
+template <typename T>
+inline real3<T> vnormalize(const real3<T> &a) {
+  T l = vlength(a);
+  return l > T(0) ? a * (T(1) / l) : a;
+}
+
+// ---- value types ----------------------------------------------------------------------------
+template <typename T = float>
+class Ray {
+ public:
+  Ray() : min_t(T(0)), max_t(std::numeric_limits<T>::max()), type(RAY_TYPE_NONE) {
+    org[0] = org[1] = org[2] = T(0);
+    dir[0] = dir[1] = T(0);
+    dir[2] = T(-1);
+  }
+  T org[3];
+  T dir[3];
+  T min_t;
+  T max_t;
+  unsigned int type;
+};
+
+template <typename T = float>
+class BVHNode {
+ public:
+  T bmin[3];
+  T bmax[3];
+  int flag;  // 1 = leaf, 0 = branch
+  int axis;
+  unsigned int data[2];  // leaf {count, first index}; branch {left, right}
+};
+
+template <typename T = float>
+struct BVHBuildOptions {
+  T cost_t_aabb;
+  unsigned int min_leaf_primitives;
+  unsigned int max_tree_depth;
+  unsigned int bin_size;
+  unsigned int shallow_depth;
+  unsigned int min_primitives_for_parallel_build;
+  bool cache_bbox;
+  unsigned char pad[3];
+  BVHBuildOptions()
+      : cost_t_aabb(T(0.2)),
+        min_leaf_primitives(4),
+        max_tree_depth(256),
+        bin_size(64),
+        shallow_depth(4),
+        min_primitives_for_parallel_build(1024 * 8),
+        cache_bbox(false) {
+    pad[0] = pad[1] = pad[2] = 0;
+  }
+};
+
+class BVHBuildStatistics {
+ public:
+  unsigned int max_tree_depth;
+  unsigned int num_leaf_nodes;
+  unsigned int num_branch_nodes;
+  float build_secs;  // device time of the build kernels (the reference never fills this field)
+  BVHBuildStatistics() : max_tree_depth(0), num_leaf_nodes(0), num_branch_nodes(0), build_secs(0.0f) {}
+};
+
+class BVHTraceOptions {
+ public:
+  unsigned int prim_ids_range[2];
+  unsigned int skip_prim_id;
+  bool cull_back_face;
+  unsigned char pad[3];
+  BVHTraceOptions() {
+    prim_ids_range[0] = 0;
+    prim_ids_range[1] = 0x7FFFFFFF;
+    skip_prim_id = static_cast<unsigned int>(-1);
+    cull_back_face = false;
+    pad[0] = pad[1] = pad[2] = 0;
+  }
+};
+
+static_assert(sizeof(Ray<float>) == 36, "nanort::Ray<float> layout");
+static_assert(sizeof(BVHNode<float>) == 40, "nanort::BVHNode<float> layout");
+static_assert(sizeof(BVHBuildOptions<float>) == 28, "nanort::BVHBuildOptions<float> layout");
+static_assert(sizeof(BVHBuildStatistics) == 16, "nanort::BVHBuildStatistics layout");
+static_assert(sizeof(BVHTraceOptions) == 16, "nanort::BVHTraceOptions layout");
+
+// ---- built-in triangle classes ----------------------------------------------------------------
+namespace detail {
+template <typename T>
+inline const T *vertex_at(const T *base, size_t i, size_t stride_bytes) {
+  return reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(base) + i * stride_bytes);
+}
+}  // namespace detail
+
+template <typename T = float>
+class TriangleSAHPred {
+ public:
+  TriangleSAHPred(const T *vertices, const unsigned int *faces, size_t vertex_stride_bytes)
+      : axis_(0), pos_(T(0)), vertices_(vertices), faces_(faces), vertex_stride_bytes_(vertex_stride_bytes) {}
+  void Set(int axis, T pos) const {
+    axis_ = axis;
+    pos_ = pos;
+  }
+  // left iff the centroid (times three) lies below the plane
+  bool operator()(unsigned int i) const {
+    const T *a = detail::vertex_at(vertices_, faces_[3 * i + 0], vertex_stride_bytes_);
+    const T *b = detail::vertex_at(vertices_, faces_[3 * i + 1], vertex_stride_bytes_);
+    const T *c = detail::vertex_at(vertices_, faces_[3 * i + 2], vertex_stride_bytes_);
+    return (a[axis_] + b[axis_] + c[axis_]) < pos_ * T(3);
+  }
+  const T *GetVertices() const { return vertices_; }
+  const unsigned int *GetFaces() const { return faces_; }
+  size_t GetVertexStrideBytes() const { return vertex_stride_bytes_; }
+
+ private:
+  mutable int axis_;
+  mutable T pos_;
+  const T *vertices_;
+  const unsigned int *faces_;
+  size_t vertex_stride_bytes_;
+};
+
+template <typename T = float>
+class TriangleMesh {
+ public:
+  TriangleMesh(const T *vertices, const unsigned int *faces, const size_t vertex_stride_bytes)
+      : vertices_(vertices), faces_(faces), vertex_stride_bytes_(vertex_stride_bytes) {}
+
+  void BoundingBox(real3<T> *bmin, real3<T> *bmax, unsigned int prim_index) const {
+    for (int c = 0; c < 3; c++) {
+      const T *p = detail::vertex_at(vertices_, faces_[3 * prim_index + c], vertex_stride_bytes_);
+      for (int k = 0; k < 3; k++) {
+        if (c == 0 || p[k] < (*bmin)[k]) (*bmin)[k] = p[k];
+        if (c == 0 || p[k] > (*bmax)[k]) (*bmax)[k] = p[k];
+      }
+    }
+  }
+  void BoundingBoxAndCenter(real3<T> *bmin, real3<T> *bmax, real3<T> *center, unsigned int prim_index) const {
+    BoundingBox(bmin, bmax, prim_index);
+    const T *a = detail::vertex_at(vertices_, faces_[3 * prim_index + 0], vertex_stride_bytes_);
+    const T *b = detail::vertex_at(vertices_, faces_[3 * prim_index + 1], vertex_stride_bytes_);
+    const T *c = detail::vertex_at(vertices_, faces_[3 * prim_index + 2], vertex_stride_bytes_);
+    for (int k = 0; k < 3; k++) (*center)[k] = ((a[k] + b[k]) + c[k]) * (T(1) / T(3));
+  }
+
+  const T *vertices_;
+  const unsigned int *faces_;
+  const size_t vertex_stride_bytes_;
+
+  const T *GetVertices() const { return vertices_; }
+  const unsigned int *GetFaces() const { return faces_; }
+  size_t GetVertexStrideBytes() const { return vertex_stride_bytes_; }
+};
+
+template <typename T = float>
+class TriangleIntersection {
+ public:
+  T u;
+  T v;
+  T t;
+  unsigned int prim_id;
+};
+static_assert(sizeof(TriangleIntersection<float>) == 16, "nanort::TriangleIntersection<float> layout");
+
+// The watertight ray/triangle test itself runs on the device (csrc/traverse.cu:tri_test); this class only
+// carries the geometry pointers, exactly as the reference's constructors take them.
+template <typename T = float, class H = TriangleIntersection<T> >
+class TriangleIntersector {
+ public:
+  template <class M>
+  explicit TriangleIntersector(const M &m)
+      : vertices_(m.GetVertices()), faces_(m.GetFaces()), vertex_stride_bytes_(m.GetVertexStrideBytes()) {}
+  template <class M>
+  explicit TriangleIntersector(const M *m)
+      : vertices_(m->GetVertices()), faces_(m->GetFaces()), vertex_stride_bytes_(m->GetVertexStrideBytes()) {}
+  TriangleIntersector(const T *vertices, const unsigned int *faces, const size_t vertex_stride_bytes)
+      : vertices_(vertices), faces_(faces), vertex_stride_bytes_(vertex_stride_bytes) {}
+
+  const T *GetVertices() const { return vertices_; }
+  const unsigned int *GetFaces() const { return faces_; }
+  size_t GetVertexStrideBytes() const { return vertex_stride_bytes_; }
+
+ private:
+  const T *vertices_;
+  const unsigned int *faces_;
+  const size_t vertex_stride_bytes_;
+};
+
+// ---- BVHAccel ------------------------------------------------------------------------------------
+template <typename T>
+class BVHAccel {
+  static_assert(std::is_same<T, float>::value, "nanort_b200: only BVHAccel<float> runs on the GPU");
+};
+
+template <>
+class BVHAccel<float> {
+ public:
+  BVHAccel() : n_prims_(0) {}
+  ~BVHAccel() {}
+
+  /// Builds the BVH on the device.  Returns false for num_primitives == 0 (like the reference) and when no
+  /// CUDA device is usable.
+  template <class Prim, class Pred>
+  bool Build(const unsigned int num_primitives, const Prim &p, const Pred &pred,
+             const BVHBuildOptions<float> &options = BVHBuildOptions<float>()) {
+    static_assert(std::is_same<Prim, TriangleMesh<float> >::value && std::is_same<Pred, TriangleSAHPred<float> >::value,
+                  "nanort_b200: Build runs on the GPU for TriangleMesh<float> + TriangleSAHPred<float> only");
+    (void)pred;
+    handle_.reset();
+    nodes_.clear();
+    indices_.clear();
+    mirrors_ = false;
+    stats_ = BVHBuildStatistics();
+    options_ = options;
+    n_prims_ = 0;
+    if (num_primitives == 0) return false;
+    nrt_accel *h = NULL;
+    int rc = nrt_build(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), num_primitives, &options, &h);
+    if (rc != NRT_OK) {
+      fprintf(stderr, "nanort_b200: Build failed: %s\n", nrt_last_error());
+      return false;
+    }
+    handle_ = std::shared_ptr<nrt_accel>(h, nrt_free);
+    n_prims_ = num_primitives;
+    nrt_stats(h, &stats_);
+    return true;
+  }
+
+  BVHBuildStatistics GetStatistics() const { return stats_; }
+
+  /// One ray, synchronously -- source compatible with the reference, but every call is a full host<->device
+  /// round trip.  Renderers should batch with TraverseBatch.
+  template <class I, class H>
+  bool Traverse(const Ray<float> &ray, const I &intersector, H *isect,
+                const BVHTraceOptions &options = BVHTraceOptions()) const {
+    if (!Ready(intersector)) return false;
+    TriangleIntersection<float> rec;
+    unsigned char hit = 0;
+    if (nrt_traverse(handle_.get(), &ray, 1, &rec, &hit, &options, NRT_TRAVERSE_FAST) != NRT_OK) {
+      fprintf(stderr, "nanort_b200: Traverse failed: %s\n", nrt_last_error());
+      return false;
+    }
+    if (hit && isect) {  // *isect stays untouched on a miss, as in the reference
+      isect->t = rec.t;
+      isect->u = rec.u;
+      isect->v = rec.v;
+      isect->prim_id = rec.prim_id;
+    }
+    return hit != 0;
+  }
+
+  /// Extension: n rays at once.  hits[i] is valid where hit_mask[i] != 0 (miss records are
+  /// {0, 0, ray.max_t, 0xFFFFFFFF}).  Returns the number of hits, or (size_t)-1 on error.
+  /// `flags`: NRT_TRAVERSE_FAST or NRT_TRAVERSE_CONFORMANCE (reference visiting order).
+  template <class I>
+  size_t TraverseBatch(const Ray<float> *rays, size_t n, const I &intersector, TriangleIntersection<float> *hits,
+                       unsigned char *hit_mask, const BVHTraceOptions &options = BVHTraceOptions(),
+                       unsigned int flags = NRT_TRAVERSE_FAST) const {
+    if (!Ready(intersector)) return static_cast<size_t>(-1);
+    std::vector<unsigned char> tmp;
+    if (!hit_mask) {
+      tmp.resize(n);
+      hit_mask = tmp.data();
+    }
+    if (nrt_traverse(handle_.get(), rays, n, hits, hit_mask, &options, flags) != NRT_OK) {
+      fprintf(stderr, "nanort_b200: TraverseBatch failed: %s\n", nrt_last_error());
+      return static_cast<size_t>(-1);
+    }
+    size_t c = 0;
+    for (size_t i = 0; i < n; i++) c += hit_mask[i] ? 1 : 0;
+    return c;
+  }
+
+  const std::vector<BVHNode<float> > &GetNodes() const {
+    Mirror();
+    return nodes_;
+  }
+  const std::vector<unsigned int> &GetIndices() const {
+    Mirror();
+    return indices_;
+  }
+
+  void BoundingBox(float bmin[3], float bmax[3]) const {
+    if (!IsValid()) {
+      bmin[0] = bmin[1] = bmin[2] = std::numeric_limits<float>::max();
+      bmax[0] = bmax[1] = bmax[2] = -std::numeric_limits<float>::max();
+      return;
+    }
+    if (handle_) {
+      nrt_bounding_box(handle_.get(), bmin, bmax);
+    } else {
+      for (int k = 0; k < 3; k++) {
+        bmin[k] = nodes_[0].bmin[k];
+        bmax[k] = nodes_[0].bmax[k];
+      }
+    }
+  }
+
+  bool IsValid() const { return handle_ || !nodes_.empty(); }
+
+  /// Raw dump in the reference's format (size_t count; nodes; size_t count; indices).
+  bool Dump(FILE *fp) const {
+    Mirror();
+    size_t n = nodes_.size(), m = indices_.size();
+    if (fwrite(&n, sizeof(size_t), 1, fp) != 1) return false;
+    if (n && fwrite(nodes_.data(), sizeof(BVHNode<float>), n, fp) != n) return false;
+    if (fwrite(&m, sizeof(size_t), 1, fp) != 1) return false;
+    if (m && fwrite(indices_.data(), sizeof(unsigned int), m, fp) != m) return false;
+    return true;
+  }
+  bool Dump(const char *filename) const {
+    FILE *fp = fopen(filename, "wb");
+    if (!fp) return false;
+    bool ok = Dump(fp);
+    fclose(fp);
+    return ok;
+  }
+  /// Loads a dumped tree (e.g. one built by CPU nanort).  The device copy is created by the first Traverse,
+  /// which brings the geometry pointers, as in the reference where Load restores nodes/indices only.
+  bool Load(FILE *fp) {
+    handle_.reset();
+    nodes_.clear();
+    indices_.clear();
+    mirrors_ = false;
+    size_t n = 0, m = 0;
+    if (fread(&n, sizeof(size_t), 1, fp) != 1 || n == 0) return false;
+    nodes_.resize(n);
+    if (fread(nodes_.data(), sizeof(BVHNode<float>), n, fp) != n) return false;
+    if (fread(&m, sizeof(size_t), 1, fp) != 1) return false;
+    indices_.resize(m);
+    if (m && fread(indices_.data(), sizeof(unsigned int), m, fp) != m) return false;
+    mirrors_ = true;
+    n_prims_ = static_cast<unsigned int>(m);
+    return true;
+  }
+  bool Load(const char *filename) {
+    FILE *fp = fopen(filename, "rb");
+    if (!fp) return false;
+    bool ok = Load(fp);
+    fclose(fp);
+    return ok;
+  }
+
+  /// Escape hatch for code that wants the device-pointer entry points of nanort_b200.h.
+  const nrt_accel *NativeHandle() const { return handle_.get(); }
+
+ private:
+  template <class I>
+  bool Ready(const I &isec) const {
+    if (handle_) return true;
+    if (nodes_.empty()) return false;
+    // a Load()ed tree: adopt it now that the intersector supplies the geometry
+    unsigned int max_prim = 0;
+    for (size_t i = 0; i < indices_.size(); i++) max_prim = indices_[i] > max_prim ? indices_[i] : max_prim;
+    nrt_accel *h = NULL;
+    int rc = nrt_adopt(nodes_.data(), nodes_.size(), indices_.data(), indices_.size(), isec.GetVertices(),
+                       isec.GetVertexStrideBytes(), 0, isec.GetFaces(), static_cast<uint32_t>(indices_.size()), &h);
+    (void)max_prim;
+    if (rc != NRT_OK) {
+      fprintf(stderr, "nanort_b200: adopting the loaded tree failed: %s\n", nrt_last_error());
+      return false;
+    }
+    handle_ = std::shared_ptr<nrt_accel>(h, nrt_free);
+    nrt_stats(h, &stats_);
+    return true;
+  }
+  void Mirror() const {
+    if (mirrors_ || !handle_) return;
+    const void *pn = NULL;
+    const uint32_t *pi = NULL;
+    size_t nn = 0, ni = 0;
+    if (nrt_nodes(handle_.get(), &pn, &nn, &pi, &ni) != NRT_OK) return;
+    nodes_.resize(nn);
+    if (nn) memcpy(nodes_.data(), pn, nn * sizeof(BVHNode<float>));
+    indices_.assign(pi, pi + ni);
+    mirrors_ = true;
+  }
+
+  mutable std::shared_ptr<nrt_accel> handle_;  // copies of a BVHAccel share the (immutable) device tree
+  mutable std::vector<BVHNode<float> > nodes_;
+  mutable std::vector<unsigned int> indices_;
+  mutable bool mirrors_ = false;
+  BVHBuildOptions<float> options_;
+  mutable BVHBuildStatistics stats_;
+  unsigned int n_prims_;
+};
+
+}  // namespace nanort
+
+#endif  // NANORT_H_

@@ -150,6 +150,14 @@ typedef struct nrt_ao_result {
 int nrt_render_ao_device(const nrt_accel *a, const nrt_ao_params *p, float *d_accum, nrt_ao_result *res,
                          void *stream);
 
+/* Workload export for benchmarks and parity tests: runs the same pass and additionally writes the two ray
+ * queues as 36-byte nanort::Ray records (DEVICE buffers sized for the shard's slot count): primary ray of
+ * slot i at d_primary_rays_36B[i], AO rays appended in queue order.  The exported arrays are what
+ * bench.py feeds to nrt_traverse (host-buffer arm) and to the CPU reference, so that all arms trace the
+ * very same rays. */
+int nrt_ao_workload_device(const nrt_accel *a, const nrt_ao_params *p, float *d_accum, void *d_primary_rays_36B,
+                           void *d_ao_rays_36B, uint64_t *n_primary, uint64_t *n_ao, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

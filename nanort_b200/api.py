@@ -47,7 +47,7 @@ STATS_DTYPE = np.dtype(
 EXPORTS = [
     "nrt_last_error", "nrt_device_count", "nrt_set_device", "nrt_build", "nrt_adopt", "nrt_free", "nrt_stats",
     "nrt_bounding_box", "nrt_nodes", "nrt_traverse", "nrt_traverse_device", "nrt_traverse_count_device",
-    "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device",
+    "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device",
 ]
 
 
@@ -109,6 +109,7 @@ def lib():
     L.nrt_host_free.argtypes = [vp]
     L.nrt_host_free.restype = None
     L.nrt_render_ao_device.argtypes = [vp, C.POINTER(AoParams), vp, C.POINTER(AoResult), vp]
+    L.nrt_ao_workload_device.argtypes = [vp, C.POINTER(AoParams), vp, vp, vp, u64p, u64p, vp]
     _lib = L
     return L
 
@@ -285,6 +286,14 @@ class BVHAccel:
         _check(lib().nrt_traverse_count_device(self._h, C.c_void_p(d_rays_ptr), int(n), _p(options), int(flags),
                                                C.byref(b), C.byref(p), C.c_void_p(stream) if stream else None))
         return b.value, p.value
+
+    def ExportAOWorkload(self, params: AoParams, d_accum_ptr, d_primary_ptr, d_ao_ptr, stream=None):
+        """Same pass, also writing both ray queues as 36-byte rays (nrt_ao_workload_device)."""
+        n_p, n_a = C.c_uint64(), C.c_uint64()
+        _check(lib().nrt_ao_workload_device(self._h, C.byref(params), C.c_void_p(d_accum_ptr),
+                                            C.c_void_p(d_primary_ptr), C.c_void_p(d_ao_ptr), C.byref(n_p),
+                                            C.byref(n_a), C.c_void_p(stream) if stream else None))
+        return n_p.value, n_a.value
 
     def RenderAO(self, params: AoParams, d_accum_ptr, stream=None, want_result=True):
         res = AoResult()

@@ -183,6 +183,27 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// AoS copy of a SoA queue as 36-byte nanort::Ray records (workload export for the host-buffer arms)
+__global__ void __launch_bounds__(256)
+    soa_to_aos_kernel(const float4 *__restrict__ org_tmin, const float4 *__restrict__ dir_tmax,
+                      const unsigned long long *n_ptr, unsigned long long n, Ray36 *__restrict__ out, uint32_t type) {
+  if (n_ptr) n = *n_ptr;
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 o = org_tmin[i], d = dir_tmax[i];
+  Ray36 r;
+  r.org[0] = o.x;
+  r.org[1] = o.y;
+  r.org[2] = o.z;
+  r.dir[0] = d.x;
+  r.dir[1] = d.y;
+  r.dir[2] = d.z;
+  r.min_t = o.w;
+  r.max_t = d.w;
+  r.type = type;
+  out[i] = r;
+}
+
 }  // namespace
 
 // launch_traverse_soa needs the ray count on the host; AO counts are produced on the device, so the
@@ -195,8 +216,10 @@ int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const
 
 using namespace nrt;
 
-extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp, float *d_accum, nrt_ao_result *res,
-                                    void *stream) {
+// dump_primary / dump_ao (optional, device): AoS copies of the two ray queues, primary rays at their slot
+// index, AO rays appended in queue order; *n_ao_out receives the AO count (forces a sync per wave).
+static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_accum, nrt_ao_result *res, void *stream,
+                       Ray36 *dump_primary, Ray36 *dump_ao, uint64_t *n_ao_out) {
   if (!h || !pp || !d_accum) {
     set_error("nrt_render_ao_device: NULL argument");
     return NRT_ERR_INVALID;
@@ -262,6 +285,7 @@ extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp,
     NRT_CUDA(cudaEventRecord(e_begin, s));
   }
   uint32_t launches = 0, trav_launches = 0;
+  unsigned long long dumped_ao = 0;
   int rc = NRT_OK;
   for (unsigned long long s0 = 0; s0 < total_slots && rc == NRT_OK; s0 += cap) {
     const uint32_t count = (uint32_t)std::min<unsigned long long>(cap, total_slots - s0);
@@ -281,6 +305,10 @@ extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp,
       ev.push_back(t3);
       cudaEventRecord(t0, s);
     }
+    if (dump_primary) {
+      soa_to_aos_kernel<<<grid, 256, 0, s>>>(w.org_tmin, w.dir_tmax, nullptr, count, dump_primary + s0, 1u);
+      launches++;
+    }
     rc = launch_traverse_soa(a, w.org_tmin, w.dir_tmax, count, w.hits, opt, p.flags, s);
     if (rc != NRT_OK) break;
     if (res) cudaEventRecord(t1, s);
@@ -289,6 +317,14 @@ extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp,
     gen_ao_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, a->d_verts, a->d_faces, d_accum, wave_ctr);
     launches++;
     if (res) cudaEventRecord(t2, s);
+    if (dump_ao) {
+      unsigned long long n_wave = 0;
+      soa_to_aos_kernel<<<grid, 256, 0, s>>>(w.ao_org_tmin, w.ao_dir_tmax, wave_ctr, 0, dump_ao + dumped_ao, 2u);
+      launches++;
+      cudaMemcpyAsync(&n_wave, wave_ctr, sizeof(n_wave), cudaMemcpyDeviceToHost, s);
+      cudaStreamSynchronize(s);
+      dumped_ao += n_wave;
+    }
     rc = launch_traverse_soa_devcount(a, w.ao_org_tmin, w.ao_dir_tmax, wave_ctr, count, w.ao_hits, opt, p.flags, s);
     if (rc != NRT_OK) break;
     if (res) cudaEventRecord(t3, s);
@@ -326,5 +362,25 @@ extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp,
   for (cudaEvent_t e : ev) cudaEventDestroy(e);
   if (e_begin) cudaEventDestroy(e_begin);
   if (e_end) cudaEventDestroy(e_end);
+  if (n_ao_out) *n_ao_out = dumped_ao;
+  return rc;
+}
+
+extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp, float *d_accum, nrt_ao_result *res,
+                                    void *stream) {
+  return run_ao_pass(h, pp, d_accum, res, stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int nrt_ao_workload_device(const nrt_accel *h, const nrt_ao_params *pp, float *d_accum,
+                                      void *d_primary_rays_36B, void *d_ao_rays_36B, uint64_t *n_primary,
+                                      uint64_t *n_ao, void *stream) {
+  if (!d_primary_rays_36B || !d_ao_rays_36B) {
+    set_error("nrt_ao_workload_device: NULL ray buffer");
+    return NRT_ERR_INVALID;
+  }
+  nrt_ao_result res;
+  int rc = run_ao_pass(h, pp, d_accum, &res, stream, static_cast<Ray36 *>(d_primary_rays_36B),
+                       static_cast<Ray36 *>(d_ao_rays_36B), n_ao);
+  if (rc == NRT_OK && n_primary) *n_primary = res.primary_rays;
   return rc;
 }
