@@ -51,8 +51,9 @@ __global__ void wide_nodes_kernel(const Node40 *__restrict__ nodes, uint32_t n, 
       // the whole tree is one leaf: a pair whose second child is empty
       WideNode w;
       w.q0 = make_float4(nd.bmin[0], nd.bmin[1], nd.bmin[2], nd.bmax[0]);
-      w.q1 = make_float4(nd.bmax[1], nd.bmax[2], 0.f, 0.f);
-      w.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      // the empty second child carries an inverted box: it can never pass the slab test
+      w.q1 = make_float4(nd.bmax[1], nd.bmax[2], 3.402823466e38f, 3.402823466e38f);
+      w.q2 = make_float4(3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
       w.q3 = make_int4(nd.data[0] ? ~(int)nd.data[1] : kEmptyLeaf, kEmptyLeaf, 0, 0);
       wide[0] = w;
     }

@@ -456,6 +456,213 @@ __global__ void __launch_bounds__(kFastBlock)
   }
 }
 
+// ------------------------------------------------------------------ fast path, second generation
+// Same algorithm and the same arithmetic as traverse_fast_kernel; restructured after the round-1 ncu
+// capture (profiles/r01_*): the kernel is issue bound with ~29 % of the issued instructions being
+// control flow (BRA/BSSY/BSYNC/ISETP) and 18 (primary) / 12 (AO) of 32 lanes active.  Changes:
+//   * triangle test without early returns (one predicate at the end; only the fp64 fallback branches)
+//   * empty children carry an inverted box, so no reference checks in the node step
+//   * child selection by selects, one predicated push
+//   * the stack is addressed as a __shared__ array (LDS/STS instead of generic LD/ST)
+//   * policy knobs: lanes that must have retired before a refill, lanes that must still be descending
+//     for the node phase to continue, CTA size / minimum CTAs per SM
+template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_>
+struct FastPolicy {
+  static constexpr int kBlock = BLOCK_;
+  static constexpr int kMinBlocks = MINB_;
+  static constexpr int kRefillMin = REFILL_MIN_;
+  static constexpr int kNodeExit = NODE_EXIT_;  // leave the node phase when fewer lanes than this descend
+};
+
+__device__ __forceinline__ void tri_test2(const RayCtx &c, const TraceOptions16 &opt, float4 a, float4 b, float4 cc,
+                                          Best &best) {
+  const uint32_t prim = __float_as_uint(a.w);
+  bool rej = (prim < opt.prim_ids_range[0]) | (prim >= opt.prim_ids_range[1]) | (prim == opt.skip_prim_id);
+  const float A0 = a.x - c.ox, A1 = a.y - c.oy, A2 = a.z - c.oz;
+  const float B0 = b.x - c.ox, B1 = b.y - c.oy, B2 = b.z - c.oz;
+  const float C0 = cc.x - c.ox, C1 = cc.y - c.oy, C2 = cc.z - c.oz;
+  const float Akz = sel3(c.kz, A0, A1, A2), Bkz = sel3(c.kz, B0, B1, B2), Ckz = sel3(c.kz, C0, C1, C2);
+  const float Ax = sel3(c.kx, A0, A1, A2) - c.Sx * Akz;
+  const float Ay = sel3(c.ky, A0, A1, A2) - c.Sy * Akz;
+  const float Bx = sel3(c.kx, B0, B1, B2) - c.Sx * Bkz;
+  const float By = sel3(c.ky, B0, B1, B2) - c.Sy * Bkz;
+  const float Cx = sel3(c.kx, C0, C1, C2) - c.Sx * Ckz;
+  const float Cy = sel3(c.ky, C0, C1, C2) - c.Sy * Ckz;
+  float U = Cx * By - Cy * Bx;
+  float V = Ax * Cy - Ay * Cx;
+  float W = Bx * Ay - By * Ax;
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {  // rare: exact edge / vertex hits
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  const bool neg = (U < 0.0f) | (V < 0.0f) | (W < 0.0f);
+  const bool pos = (U > 0.0f) | (V > 0.0f) | (W > 0.0f);
+  rej |= neg & ((opt.cull_back_face != 0) | pos);
+  const float det = (U + V) + W;
+  rej |= (det == 0.0f);
+  const float Az = c.Sz * Akz, Bz = c.Sz * Bkz, Cz = c.Sz * Ckz;
+  const float D = (U * Az + V * Bz) + W * Cz;
+  const float rcp = 1.0f / det;
+  const float tt = D * rcp;
+  rej |= (tt > best.t) | (tt < c.t_min);
+  if (!rej) {
+    best.t = tt;
+    best.u = V * rcp;
+    best.v = W * rcp;
+    best.prim = prim;
+  }
+}
+
+template <class Rays, int LOCAL_DEPTH, bool COUNT, class P>
+__global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
+    traverse_fast2_kernel(const WideNode *__restrict__ wide, const PackedTri *__restrict__ tris, Rays rays, size_t n,
+                          Hit16 *__restrict__ hits, uint8_t *__restrict__ mask, TraceOptions16 opt, uint32_t flags,
+                          unsigned long long *cursor, unsigned long long *counts, const unsigned long long *n_ptr) {
+  constexpr int BLOCK = P::kBlock;
+  __shared__ uint2 stk[kStackSmem * BLOCK];
+  if (n_ptr) n = (size_t)*n_ptr;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
+
+  uint2 lstk[LOCAL_DEPTH];
+  int sp = 0;
+  RayCtx c;
+  Best best;
+  float max_t = 0.0f, min_t = 0.0f;
+  long long ray_idx = -1;
+  int cur = kNone, leaf = kNone;
+  bool exhausted = false;
+  unsigned long long n_boxes = 0, n_prims = 0;
+
+  auto push = [&](int ref, float t) {
+    const uint2 e = make_uint2((uint32_t)ref, __float_as_uint(t));
+    if (sp < kStackSmem)
+      stk[sp * BLOCK + tid] = e;
+    else if (sp - kStackSmem < LOCAL_DEPTH)
+      lstk[sp - kStackSmem] = e;
+    sp++;
+  };
+  // next stack entry that does not start behind the current best, or kNone
+  auto pop = [&]() -> int {
+    while (sp > 0) {
+      --sp;
+      uint2 e;
+      if (sp < kStackSmem)
+        e = stk[sp * BLOCK + tid];
+      else if (sp - kStackSmem < LOCAL_DEPTH)
+        e = lstk[sp - kStackSmem];
+      else
+        continue;
+      if (__uint_as_float(e.y) <= best.t) return (int)e.x;
+    }
+    return kNone;
+  };
+
+  for (;;) {
+    // ---- replace retired rays
+    const unsigned dead = __ballot_sync(FULL_MASK, ray_idx < 0);
+    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= P::kRefillMin)) {
+      const int cnt = __popc(dead);
+      const int leader = __ffs(dead) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(cursor, (unsigned long long)cnt);
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
+      if (ray_idx < 0) {
+        const unsigned long long mine = base + (unsigned long long)__popc(dead & lt_mask);
+        if (mine < (unsigned long long)n) {
+          float ox, oy, oz, dx, dy, dz;
+          rays.load((size_t)mine, ox, oy, oz, dx, dy, dz, min_t, max_t);
+          setup_ray(c, ox, oy, oz, dx, dy, dz, min_t, cpp03);
+          best.t = max_t;
+          best.u = 0.0f;
+          best.v = 0.0f;
+          best.prim = 0xFFFFFFFFu;
+          ray_idx = (long long)mine;
+          sp = 0;
+          cur = 0;
+          leaf = kNone;
+          if (COUNT) n_boxes += 1;
+        }
+      }
+    }
+    if (__all_sync(FULL_MASK, ray_idx < 0)) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- inner nodes
+    for (;;) {
+      const unsigned desc = __ballot_sync(FULL_MASK, cur >= 0);
+      if (desc == 0u) break;
+      if (P::kNodeExit > 1 && __popc(desc) < P::kNodeExit &&
+          __any_sync(FULL_MASK, leaf != kNone))  // few lanes still descend while others wait with leaves
+        break;
+      if (cur >= 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
+        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        float t0, t1;
+        const bool h0 = slab(c, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, min_t, best.t, t0);
+        const bool h1 = slab(c, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, min_t, best.t, t1);
+        if (COUNT) n_boxes += 2;
+        const bool both = h0 & h1;
+        const bool swap = t1 < t0;
+        const int nearr = swap ? q3.y : q3.x;
+        const int farr = swap ? q3.x : q3.y;
+        if (both) push(farr, swap ? t0 : t1);
+        int next = both ? nearr : (h0 ? q3.x : q3.y);
+        if (!(h0 | h1)) next = pop();
+        if (next < 0 && next != kNone && leaf == kNone) {  // postpone the first leaf, keep descending
+          leaf = next;
+          next = pop();
+        }
+        cur = next;
+      }
+    }
+
+    // ---- leaves
+    for (;;) {
+      if (!__any_sync(FULL_MASK, leaf != kNone)) break;
+      if (leaf != kNone) {
+        const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)(~leaf));
+        for (;;) {
+          const float4 a = __ldg(t), b = __ldg(t + 1), cc = __ldg(t + 2);
+          if (COUNT) n_prims++;
+          tri_test2(c, opt, a, b, cc, best);
+          if (__float_as_uint(b.w) != 0u) break;
+          t += 3;
+        }
+        leaf = kNone;
+        if (cur < 0 && cur != kNone) {
+          leaf = cur;
+          cur = pop();
+        }
+      }
+    }
+
+    // ---- retire
+    if (ray_idx >= 0 && cur == kNone && leaf == kNone) {
+      if (hits) write_result(hits, mask, (size_t)ray_idx, best, max_t);
+      ray_idx = -1;
+    }
+  }
+
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_boxes += __shfl_down_sync(FULL_MASK, n_boxes, o);
+      n_prims += __shfl_down_sync(FULL_MASK, n_prims, o);
+    }
+    if (lane == 0) {
+      atomicAdd(counts + 0, n_boxes);
+      atomicAdd(counts + 1, n_prims);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 static int g_sm_count[64] = {0};
 int device_sm_count(int device) {
@@ -468,6 +675,24 @@ int device_sm_count(int device) {
   return g_sm_count[device];
 }
 
+template <class Rays, int LOCAL_DEPTH, bool COUNT, class P>
+static cudaError_t launch_fast2(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
+                                const TraceOptions16 &opt, uint32_t flags, unsigned long long *cursor,
+                                unsigned long long *d_counts, const unsigned long long *n_ptr, cudaStream_t s) {
+  const int sms = device_sm_count(a->device);
+  const size_t warps_per_block = P::kBlock / 32;
+  size_t grid = (size_t)sms * P::kMinBlocks;
+  const size_t need_blocks = ((n + 31) / 32 + warps_per_block - 1) / warps_per_block;
+  if (grid > need_blocks) grid = need_blocks;
+  if (grid == 0) grid = 1;
+  traverse_fast2_kernel<Rays, LOCAL_DEPTH, COUNT, P><<<(unsigned)grid, P::kBlock, 0, s>>>(
+      a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, n_ptr);
+  return cudaGetLastError();
+}
+
+// Default policy (chosen from the sweep in profiles/r01_variant_sweep.md)
+typedef FastPolicy<128, 8, 8, 0> DefaultPolicy;
+
 template <class Rays, bool COUNT>
 static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
                        const TraceOptions16 &opt, uint32_t flags, unsigned long long *d_counts, cudaStream_t s,
@@ -475,24 +700,53 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
   unsigned long long *cursor =
       reinterpret_cast<unsigned long long *>(a->d_counters) + 16 + (a->cursor_ring.fetch_add(1) & 31u);
   NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
-  int sms = device_sm_count(a->device);
   // wide-node stack depth never exceeds the tree depth
-  bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
-  int blocks_per_sm = 8;
-  size_t warps_needed = (n + 31) / 32;
-  size_t grid = (size_t)sms * blocks_per_sm;
-  size_t need_blocks = (warps_needed + (kFastBlock / 32) - 1) / (kFastBlock / 32);
-  if (grid > need_blocks) grid = need_blocks;
-  if (grid == 0) grid = 1;
-  const int refill_min = 8;
+  const bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
+  const uint32_t variant = (flags >> 8) & 0xFFu;  // experiment selector (tools/trav_sweep.py); 0 = default
+  cudaError_t e = cudaSuccess;
   if (deep) {
-    traverse_fast_kernel<Rays, 512 - kStackSmem, COUNT><<<(unsigned)grid, kFastBlock, 0, s>>>(
-        a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, refill_min, n_ptr);
+    e = launch_fast2<Rays, 512 - kStackSmem, COUNT, DefaultPolicy>(a, rays, n, d_hits, d_mask, opt, flags, cursor,
+                                                                    d_counts, n_ptr, s);
+  } else if (variant == 0 || COUNT) {
+    e = launch_fast2<Rays, 48, COUNT, DefaultPolicy>(a, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, n_ptr, s);
   } else {
-    traverse_fast_kernel<Rays, 48, COUNT><<<(unsigned)grid, kFastBlock, 0, s>>>(
-        a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, refill_min, n_ptr);
+#define NRT_VARIANT(id, ...)                                                                                        \
+  case id:                                                                                                          \
+    e = launch_fast2<Rays, 48, false, FastPolicy<__VA_ARGS__> >(a, rays, n, d_hits, d_mask, opt, flags, cursor,      \
+                                                                d_counts, n_ptr, s);                                \
+    break;
+    switch (variant) {
+      NRT_VARIANT(1, 128, 8, 8, 0)
+      NRT_VARIANT(2, 128, 8, 1, 0)
+      NRT_VARIANT(3, 128, 8, 4, 0)
+      NRT_VARIANT(4, 128, 8, 16, 0)
+      NRT_VARIANT(5, 128, 8, 8, 8)
+      NRT_VARIANT(6, 128, 8, 8, 16)
+      NRT_VARIANT(7, 128, 8, 8, 4)
+      NRT_VARIANT(8, 64, 16, 8, 0)
+      NRT_VARIANT(9, 256, 4, 8, 0)
+      NRT_VARIANT(10, 128, 6, 8, 0)
+      NRT_VARIANT(11, 128, 10, 8, 0)
+      NRT_VARIANT(12, 128, 8, 12, 12)
+      NRT_VARIANT(13, 128, 8, 4, 24)
+      case 255: {  // first-generation kernel, kept for A/B runs
+        const int sms = device_sm_count(a->device);
+        size_t grid = (size_t)sms * 8;
+        const size_t need_blocks = ((n + 31) / 32 + 3) / 4;
+        if (grid > need_blocks) grid = need_blocks;
+        if (grid == 0) grid = 1;
+        traverse_fast_kernel<Rays, 48, false><<<(unsigned)grid, kFastBlock, 0, s>>>(
+            a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, 8, n_ptr);
+        e = cudaGetLastError();
+        break;
+      }
+      default:
+        set_error("nrt_traverse: unknown kernel variant in flags");
+        return NRT_ERR_INVALID;
+    }
+#undef NRT_VARIANT
   }
-  NRT_CUDA(cudaGetLastError());
+  NRT_CUDA(e);
   return NRT_OK;
 }
 

@@ -1,0 +1,178 @@
+// Wavefront pieces shared by render.cu (stand-alone stage kernels) and traverse.cu (the same stages fused
+// into the traversal kernel's retire step): ray queues, counter-based RNG, slot -> pixel mapping, AO ray
+// construction.  Reference pieces restated here (file:line under /root/reference/examples/path_tracer):
+//   hit point main.cc:860, geometric normal main.cc:306-312 flipped to the viewer main.cc:878-881,
+//   orthonormal basis + cosine direction main.cc:216-250, occlusion query main.cc:675-701.
+#pragma once
+#include "common.cuh"
+
+namespace nrt {
+
+struct Wave {
+  float4 *org_tmin;  // primary queue (SoA): org.xyz, min_t
+  float4 *dir_tmax;  //                      dir.xyz, max_t
+  Hit16 *hits;
+  uint32_t *pix;        // pixel of a primary slot (0xFFFFFFFF = slot outside the image)
+  float4 *ao_org_tmin;  // compacted AO queue
+  float4 *ao_dir_tmax;
+  uint32_t *ao_pix;
+  Hit16 *ao_hits;
+};
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32, same as scenes.py:hash_u32
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+
+// scenes.py:rand_ps
+__device__ __forceinline__ float rand_ps(uint32_t pix, uint32_t smp, uint32_t dim, uint32_t seed) {
+  uint32_t h = hash_u32(pix + seed * 0x9E3779B1u);
+  h = hash_u32(h + smp * 0x85EBCA77u + dim * 0xC2B2AE3Du);
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// Slot -> (pixel, sample).  Slots enumerate this shard's tiles; inside a tile the order is sample-major over
+// 8x4 pixel blocks, so the 32 lanes of a warp start as one coherent 8x4 packet.
+__device__ __forceinline__ bool slot_to_pixel(const nrt_ao_params &p, unsigned long long slot, uint32_t &pix,
+                                              uint32_t &smp) {
+  const uint32_t tile_pix = p.tile_w * p.tile_h;
+  const unsigned long long per_tile = (unsigned long long)tile_pix * p.spp;
+  const uint32_t k = (uint32_t)(slot / per_tile);  // k-th tile of this shard
+  const uint32_t rem = (uint32_t)(slot % per_tile);
+  smp = rem / tile_pix;
+  const uint32_t q = rem % tile_pix;
+  const uint32_t bw = p.tile_w / 8;  // 8x4 blocks per tile row
+  const uint32_t blk = q / 32, in = q % 32;
+  const uint32_t bx = blk % bw, by = blk / bw;
+  const uint32_t lx = bx * 8 + (in & 7), ly = by * 4 + (in >> 3);
+  const uint32_t tiles_x = (p.width + p.tile_w - 1) / p.tile_w;
+  const uint32_t tile = k * p.n_shards + p.shard;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  const uint32_t x = tx * p.tile_w + lx, y = ty * p.tile_h + ly;
+  if (x >= p.width || y >= p.height) return false;
+  pix = y * p.width + x;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t slot_sample(const nrt_ao_params &p, unsigned long long slot) {
+  const uint32_t tile_pix = p.tile_w * p.tile_h;
+  return p.sample0 + (uint32_t)((slot % ((unsigned long long)tile_pix * p.spp)) / tile_pix);
+}
+
+// One cosine-hemisphere AO ray from a primary hit.
+__device__ __forceinline__ void make_ao_ray(const nrt_ao_params &p, uint32_t pix, uint32_t smp, float4 o, float4 d,
+                                            float t, uint32_t prim, const float *__restrict__ verts,
+                                            const uint32_t *__restrict__ faces, float4 &o4, float4 &d4) {
+  const float Px = o.x + d.x * t, Py = o.y + d.y * t, Pz = o.z + d.z * t;
+  const uint32_t f0 = faces[3 * (size_t)prim], f1 = faces[3 * (size_t)prim + 1], f2 = faces[3 * (size_t)prim + 2];
+  const float *p0 = verts + 3 * (size_t)f0, *p1 = verts + 3 * (size_t)f1, *p2 = verts + 3 * (size_t)f2;
+  const float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
+  const float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
+  float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+  float ln = sqrtf(nx * nx + ny * ny + nz * nz);
+  ln = ln > 0.0f ? 1.0f / ln : 0.0f;
+  nx *= ln;
+  ny *= ln;
+  nz *= ln;
+  if (nx * d.x + ny * d.y + nz * d.z > 0.0f) {
+    nx = -nx;
+    ny = -ny;
+    nz = -nz;
+  }
+  // branch-free orthonormal basis around n
+  const float sg = nz >= 0.0f ? 1.0f : -1.0f;
+  const float a = -1.0f / (sg + nz), b = nx * ny * a;
+  const float t1x = 1.0f + sg * nx * nx * a, t1y = sg * b, t1z = -sg * nx;
+  const float t2x = b, t2y = sg + ny * ny * a, t2z = -ny;
+  const float u1 = rand_ps(pix, smp, 2, p.seed), u2 = rand_ps(pix, smp, 3, p.seed);
+  const float r = sqrtf(u1), ph = 6.28318530718f * u2;
+  float sn, cs;
+  sincosf(ph, &sn, &cs);
+  const float lx = r * cs, ly = r * sn, lz = sqrtf(fmaxf(0.0f, 1.0f - u1));
+  const float wx = t1x * lx + t2x * ly + nx * lz, wy = t1y * lx + t2y * ly + ny * lz, wz = t1z * lx + t2z * ly + nz * lz;
+  const float il = 1.0f / sqrtf(wx * wx + wy * wy + wz * wz);
+  o4 = make_float4(Px, Py, Pz, p.ao_min_t);
+  d4 = make_float4(wx * il, wy * il, wz * il, p.ao_max_t);
+}
+
+// ---- retire-step functors of traverse_fast2_kernel.  Called by ALL 32 lanes of a warp (`retiring` says
+// whether this lane's ray just finished), so they may use full-mask warp votes.
+struct StoreHitsEpilogue {
+  Hit16 *hits;
+  uint8_t *mask;
+  __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
+                                             float max_t) const {
+    if (retiring && hits) {
+      const bool hit = t < max_t;  // a hit exactly at max_t is a miss (nanort.h:2552)
+      float4 r = hit ? make_float4(u, v, t, __uint_as_float(prim)) : make_float4(0.0f, 0.0f, max_t, __uint_as_float(0xFFFFFFFFu));
+      reinterpret_cast<float4 *>(hits)[ray_idx] = r;
+      if (mask) mask[ray_idx] = hit ? 1 : 0;
+    }
+  }
+};
+
+// primary rays: a hit spawns its AO ray straight into the compacted AO queue, a miss adds 1 to its pixel
+struct PrimaryToAoEpilogue {
+  nrt_ao_params p;
+  unsigned long long slot0;
+  Wave w;
+  const float *verts;
+  const uint32_t *faces;
+  float *accum;
+  unsigned long long *counters;  // [0] AO rays of this wave
+  __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
+                                             float max_t) const {
+    (void)u;
+    (void)v;
+    bool make = false;
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4;
+    uint32_t pix = 0xFFFFFFFFu;
+    if (retiring) {
+      pix = w.pix[ray_idx];
+      if (pix != 0xFFFFFFFFu) {
+        if (t < max_t) {
+          make_ao_ray(p, pix, slot_sample(p, slot0 + ray_idx), w.org_tmin[ray_idx], w.dir_tmax[ray_idx], t, prim,
+                      verts, faces, o4, d4);
+          make = true;
+        } else {
+          atomicAdd(accum + pix, 1.0f);
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, make);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counters, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (make) {
+      const unsigned long long j = base + __popc(m & ((1u << lane) - 1u));
+      w.ao_org_tmin[j] = o4;
+      w.ao_dir_tmax[j] = d4;
+      w.ao_pix[j] = pix;
+    }
+  }
+};
+
+// AO rays: an unoccluded ray adds 1 to its pixel; nothing else is written
+struct AoAccumulateEpilogue {
+  const uint32_t *ao_pix;
+  float *accum;
+  unsigned long long *totals;  // [1] occluded AO rays
+  __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
+                                             float max_t) const {
+    (void)u;
+    (void)v;
+    (void)prim;
+    const bool occluded = retiring && (t < max_t);
+    if (retiring && !occluded) atomicAdd(accum + ao_pix[ray_idx], 1.0f);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, occluded);
+    if (m != 0u && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(totals + 1, (unsigned long long)__popc(m));
+  }
+};
+
+}  // namespace nrt
