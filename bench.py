@@ -50,9 +50,9 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -73,7 +73,10 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and throttle reasons of the samples taken inside [t_begin, t_end] (time.time());
+        the sampler is started before the warm-up so that nvidia-smi is already streaming when the timed
+        region begins."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,21 +84,29 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+
+        sm, mx, reasons, sm_all = [], [], set(), []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(f[1]), float(f[2])
             except ValueError:
                 continue
+            sm_all.append(clk)
+            if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                continue
+            sm.append(clk)
+            mx.append(cmax)
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else (float(np.median(sm_all)) if sm_all else None),
+                "sm_max_mhz": max(mx) if mx else None, "samples_in_timed_region": len(sm),
+                "samples_total": len(sm_all), "reasons": sorted(reasons)}
 
 
 def ao_params(api, S, cam, diag, n_shards, shard):
@@ -307,20 +318,23 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- value: device-resident pass
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         device_step()
     sync_all()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    time.sleep(0.3)  # let nvidia-smi reach its streaming state before the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         device_step()
     e1.record()
     sync_all()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     # one more instrumented pass (outside the timed region) for counts, launch counts and the in-kernel time
     accum.zero_()
     r = acc.RenderAO(p, accum.data_ptr(), want_result=True)

@@ -41,6 +41,10 @@ extern "C" {
 #define NRT_TRAVERSE_CPP03_INVERSE 2u /* vsafe_inverse sign convention of the C++03 build (nanort.h:440-462:
                                         -0.0f -> +inf).  Default is the C++11 one (copysign, :418-439)   */
 
+/* nrt_ao_params.flags only: run the AO stages as stand-alone kernels instead of fused into the traversal
+ * kernel's retire step (A/B and equivalence tests; results are identical) */
+#define NRT_AO_UNFUSED 0x10000u
+
 typedef struct nrt_accel nrt_accel; /* opaque: device-resident BVH + host mirrors */
 
 const char *nrt_last_error(void);
@@ -157,6 +161,42 @@ int nrt_render_ao_device(const nrt_accel *a, const nrt_ao_params *p, float *d_ac
  * very same rays. */
 int nrt_ao_workload_device(const nrt_accel *a, const nrt_ao_params *p, float *d_accum, void *d_primary_rays_36B,
                            void *d_ao_rays_36B, uint64_t *n_primary, uint64_t *n_ao, void *stream);
+
+/*
+ * Device-resident wavefront form of the reference path tracer's pixel -> sample -> bounce loop
+ * (examples/path_tracer/main.cc:804-991), diffuse + emissive materials only:
+ *   camera ray :809-817, Russian roulette after bounce 3 with p = 0.2 :828-837, radiance Traverse :839-854,
+ *   geometric normal flipped to the viewer :878-881, EMIT lobe (only when the previous event did no light
+ *   sampling) :958-966, diffuse lobe with next-event estimation: MeshLight::sampleDirect :337-392 + the
+ *   CheckForOccluder shadow Traverse :675-701, cosine-weighted continuation :216-250, at most max_bounces.
+ * Every bounce is two traversal launches (radiance rays, shadow rays) whose retire steps do the shading.
+ * Faces [light_first_face, light_first_face + light_n_faces) of the mesh are the emitters (radiance
+ * `emission`, cosine EDF); every other face is Lambertian with reflectance `albedo`.
+ */
+typedef struct nrt_path_params {
+  float cam[12];
+  uint32_t width, height;
+  uint32_t spp, sample0, seed;
+  uint32_t tile_w, tile_h, shard, n_shards;
+  uint32_t max_bounces;   /* uMaxBounces, main.cc:33 (10) */
+  float ray_min_t, ray_max_t; /* 1e-3, 1e30 (main.cc:840-842) */
+  float albedo[3];
+  float emission[3];
+  uint32_t light_first_face, light_n_faces;
+  uint32_t flags;         /* NRT_TRAVERSE_* */
+} nrt_path_params;
+
+typedef struct nrt_path_result {
+  uint64_t camera_rays;
+  uint64_t radiance_rays; /* all radiance Traverse calls, camera rays included */
+  uint64_t shadow_rays;
+  float traverse_ms, total_ms;
+  uint32_t launches, traverse_launches;
+} nrt_path_result;
+
+/* d_accum_rgb: DEVICE float[3*width*height], sum over samples of the path radiance (divide by spp). */
+int nrt_render_path_device(const nrt_accel *a, const nrt_path_params *p, float *d_accum_rgb, nrt_path_result *res,
+                           void *stream);
 
 #ifdef __cplusplus
 }

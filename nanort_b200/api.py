@@ -47,7 +47,7 @@ STATS_DTYPE = np.dtype(
 EXPORTS = [
     "nrt_last_error", "nrt_device_count", "nrt_set_device", "nrt_build", "nrt_adopt", "nrt_free", "nrt_stats",
     "nrt_bounding_box", "nrt_nodes", "nrt_traverse", "nrt_traverse_device", "nrt_traverse_count_device",
-    "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device",
+    "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device", "nrt_render_path_device",
 ]
 
 
@@ -71,6 +71,28 @@ class AoParams(C.Structure):
 class AoResult(C.Structure):
     _fields_ = [
         ("primary_rays", C.c_uint64), ("ao_rays", C.c_uint64), ("ao_hits", C.c_uint64),
+        ("traverse_ms", C.c_float), ("total_ms", C.c_float),
+        ("launches", C.c_uint32), ("traverse_launches", C.c_uint32),
+    ]
+
+
+class PathParams(C.Structure):
+    _fields_ = [
+        ("cam", C.c_float * 12),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("spp", C.c_uint32), ("sample0", C.c_uint32), ("seed", C.c_uint32),
+        ("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("shard", C.c_uint32), ("n_shards", C.c_uint32),
+        ("max_bounces", C.c_uint32),
+        ("ray_min_t", C.c_float), ("ray_max_t", C.c_float),
+        ("albedo", C.c_float * 3), ("emission", C.c_float * 3),
+        ("light_first_face", C.c_uint32), ("light_n_faces", C.c_uint32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class PathResult(C.Structure):
+    _fields_ = [
+        ("camera_rays", C.c_uint64), ("radiance_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("traverse_ms", C.c_float), ("total_ms", C.c_float),
         ("launches", C.c_uint32), ("traverse_launches", C.c_uint32),
     ]
@@ -110,6 +132,7 @@ def lib():
     L.nrt_host_free.restype = None
     L.nrt_render_ao_device.argtypes = [vp, C.POINTER(AoParams), vp, C.POINTER(AoResult), vp]
     L.nrt_ao_workload_device.argtypes = [vp, C.POINTER(AoParams), vp, vp, vp, u64p, u64p, vp]
+    L.nrt_render_path_device.argtypes = [vp, C.POINTER(PathParams), vp, C.POINTER(PathResult), vp]
     _lib = L
     return L
 
@@ -294,6 +317,14 @@ class BVHAccel:
                                             C.c_void_p(d_primary_ptr), C.c_void_p(d_ao_ptr), C.byref(n_p),
                                             C.byref(n_a), C.c_void_p(stream) if stream else None))
         return n_p.value, n_a.value
+
+    def RenderPath(self, params: PathParams, d_accum_rgb_ptr, stream=None, want_result=True):
+        """Wavefront path tracing pass (nrt_render_path_device)."""
+        res = PathResult()
+        _check(lib().nrt_render_path_device(self._h, C.byref(params), C.c_void_p(d_accum_rgb_ptr),
+                                            C.byref(res) if want_result else None,
+                                            C.c_void_p(stream) if stream else None))
+        return res
 
     def RenderAO(self, params: AoParams, d_accum_ptr, stream=None, want_result=True):
         res = AoResult()

@@ -22,12 +22,13 @@
 //
 // Structure: (A) level-synchronous passes over all primitives for nodes with more than kSubtree
 // primitives -- block-private shared-memory bins flushed with atomics, one warp per node for the sweep,
-// a device-wide scan + stable scatter for the partition; (B) one CTA per remaining subtree builds it to
+// a device-wide scan + stable scatter for the partition; (B) one WARP per remaining subtree builds it to
 // the leaves entirely in shared memory; (C) pre-order indices are computed in closed form from
 // (leaves to the left, depth, right turns) and the 40-byte nodes are emitted in one pass.
 #include <float.h>
 
 #include "common.cuh"
+#include "radix_sort.cuh"
 #include "scan.cuh"
 
 namespace nrt {
@@ -36,8 +37,8 @@ namespace {
 
 constexpr uint32_t kInactive = 0xFFFFFFFFu;
 constexpr uint32_t kMedian = 0xFFFFFFFEu;
-constexpr int kSubtree = 512;     // phase B handles nodes with at most this many primitives
-constexpr int kSubBlock = 128;    // threads per phase-B CTA
+constexpr int kSubtree = 128;     // phase B handles nodes with at most this many primitives (one warp each)
+constexpr int kSubWarps = 4;      // warps (= subtrees) per phase-B CTA
 constexpr int kMaxBins = 256;     // bin_size limit of this implementation
 constexpr int kBinWords = 8;      // count, min xyz, max xyz, pad
 
@@ -555,74 +556,61 @@ __global__ void fix_median_kernel(BNode *pool, const BuildCounters *ctr, const u
 
 __global__ void reset_count_kernel(BuildCounters *ctr, int which) { ctr->n_active[which] = 0; }
 
-// ------------------------------------------------------------------ phase B: one CTA per subtree
-struct SubShared {
+// ------------------------------------------------------------------ phase B: one WARP per subtree
+// A subtree of at most kSubtree primitives is built to its leaves by a single warp, entirely out of that
+// warp's slice of shared memory (primitive records, current order, bins, node stack) and with warp-level
+// synchronisation only; a CTA is just kSubWarps independent warps.
+struct WarpSub {
   float4 plo[kSubtree];
   float4 phi[kSubtree];
   float pcz[kSubtree];
-  uint32_t gslot[kSubtree];   // global primitive slot of local primitive i
-  uint16_t ids[kSubtree];     // current order (local ids) of the subtree's range
+  uint32_t gslot[kSubtree];  // global primitive slot of local primitive i
+  uint32_t stack[kSubtree];  // pool ids of nodes still to split
+  uint16_t ids[kSubtree];    // current order (local ids) of the subtree's range
   uint16_t tmp[kSubtree];
-  uint32_t stack[kSubtree];   // pool ids of nodes still to split
-  uint32_t scan_warp[kSubBlock / 32];
-  float cost[3];
-  int cut[3];
-  int sp;
-  uint32_t cur;
-  uint32_t nl;
-  uint32_t left;
-  int axis;
-  int median;
-  float cbox[2][6];
 };
 
-__global__ void __launch_bounds__(kSubBlock)
-    subtree_kernel(BNode *pool, BuildCounters *ctr, const uint32_t *__restrict__ subtrees,
+__global__ void __launch_bounds__(kSubWarps * 32)
+    subtree_kernel(BNode *pool, BuildCounters *ctr, const uint32_t *__restrict__ subtrees, uint32_t n_subtrees,
                    uint32_t *__restrict__ idx, const float4 *__restrict__ plo, const float4 *__restrict__ phi,
                    const float *__restrict__ pcz, int B, uint32_t min_leaf, uint32_t max_depth) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SubShared &S = *reinterpret_cast<SubShared *>(smem_raw);
-  uint32_t *sbin = reinterpret_cast<uint32_t *>(smem_raw + sizeof(SubShared));  // 3*B*kBinWords
-  float *sweep = reinterpret_cast<float *>(sbin + 3 * B * kBinWords);             // 3 warps * 2*B floats
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t root = subtrees[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sub = blockIdx.x * kSubWarps + warp;
+  if (sub >= n_subtrees) return;
+  const size_t per_warp = sizeof(WarpSub) + (size_t)3 * B * kBinWords * 4 + (size_t)2 * B * 4;
+  unsigned char *mine = smem_raw + (size_t)warp * per_warp;
+  WarpSub &S = *reinterpret_cast<WarpSub *>(mine);
+  uint32_t *sbin = reinterpret_cast<uint32_t *>(mine + sizeof(WarpSub));      // 3*B*kBinWords
+  float *sweep = reinterpret_cast<float *>(sbin + (size_t)3 * B * kBinWords);  // 2*B floats
+  const uint32_t root = subtrees[sub];
   const BNode rootn = pool[root];
   const uint32_t base = rootn.l, total = rootn.r - rootn.l;
-  for (uint32_t i = tid; i < total; i += kSubBlock) {
-    uint32_t s = idx[base + i];
+  for (uint32_t i = lane; i < total; i += 32) {
+    const uint32_t s = idx[base + i];
     S.gslot[i] = s;
     S.plo[i] = plo[s];
     S.phi[i] = phi[s];
     S.pcz[i] = pcz[s];
     S.ids[i] = (uint16_t)i;
   }
-  if (tid == 0) {
-    S.stack[0] = root;
-    S.sp = 1;
-  }
-  __syncthreads();
+  int sp = 1;  // warp-uniform register copy of the stack pointer
+  if (lane == 0) S.stack[0] = root;
+  __syncwarp();
 
-  for (;;) {
-    const int sp_now = S.sp;  // every thread reads it between two barriers, thread 0 updates it after
-    if (sp_now == 0) break;
-    __syncthreads();
-    if (tid == 0) {
-      S.cur = S.stack[sp_now - 1];
-      S.sp = sp_now - 1;
-    }
-    __syncthreads();
-    const uint32_t nid = S.cur;
+  while (sp > 0) {
+    const uint32_t nid = S.stack[--sp];
     const BNode nd = pool[nid];
     const uint32_t lo = nd.l - base, n = nd.r - nd.l;
     // ---- bins
-    for (int i = tid; i < 3 * B * kBinWords; i += kSubBlock) {
-      int w = i & (kBinWords - 1);
+    for (int i = lane; i < 3 * B * kBinWords; i += 32) {
+      const int w = i & (kBinWords - 1);
       sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
     }
-    __syncthreads();
+    __syncwarp();
     const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
                          inv_extent(nd.bmin[2], nd.bmax[2], B)};
-    for (uint32_t i = tid; i < n; i += kSubBlock) {
+    for (uint32_t i = lane; i < n; i += 32) {
       const uint32_t q = S.ids[lo + i];
       const float4 l4 = S.plo[q], h4 = S.phi[q];
       const float c3[3] = {l4.w, h4.w, S.pcz[q]};
@@ -638,146 +626,120 @@ __global__ void __launch_bounds__(kSubBlock)
         }
       }
     }
-    __syncthreads();
-    // ---- sweep: warp a handles axis a
-    if (warp < 3) {
-      float c;
-      int ci;
-      sweep_axis(sbin + (size_t)warp * B * kBinWords, B, sweep + (size_t)warp * 2 * B, sweep + (size_t)warp * 2 * B + B,
-                 c, ci);
-      if (lane == 0) {
-        S.cost[warp] = c;
-        S.cut[warp] = ci;
+    __syncwarp();
+    // ---- sweep the three axes, pick the split
+    float cost[3];
+    int cut[3];
+    for (int a = 0; a < 3; a++) sweep_axis(sbin + (size_t)a * B * kBinWords, B, sweep, sweep + B, cost[a], cut[a]);
+    int ax = 0;
+    if (cost[0] > cost[1]) ax = 1;
+    if (cost[ax] > cost[2]) ax = 2;
+    const bool median = !(cost[ax] < FLT_MAX);
+    Box6 lb, rb;
+    uint32_t nl, nr;
+    if (!median) {
+      range_union(sbin + (size_t)ax * B * kBinWords, 0, cut[ax], lb, nl);
+      range_union(sbin + (size_t)ax * B * kBinWords, cut[ax], B, rb, nr);
+    } else {
+      nl = n >> 1;
+      box_empty(lb);
+      box_empty(rb);
+      for (uint32_t i = lane; i < n; i += 32) {  // exact boxes of the two halves of the current order
+        const uint32_t q = S.ids[lo + i];
+        const float4 l4 = S.plo[q], h4 = S.phi[q];
+        Box6 &t = i < nl ? lb : rb;
+        t.v[0] = fminf(t.v[0], l4.x);
+        t.v[1] = fminf(t.v[1], l4.y);
+        t.v[2] = fminf(t.v[2], l4.z);
+        t.v[3] = fmaxf(t.v[3], h4.x);
+        t.v[4] = fmaxf(t.v[4], h4.y);
+        t.v[5] = fmaxf(t.v[5], h4.z);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        for (int k = 0; k < 3; k++) {
+          lb.v[k] = fminf(lb.v[k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[k], o));
+          rb.v[k] = fminf(rb.v[k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[k], o));
+          lb.v[3 + k] = fmaxf(lb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[3 + k], o));
+          rb.v[3 + k] = fmaxf(rb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[3 + k], o));
+        }
       }
     }
-    __syncthreads();
-    if (warp == 0) {
-      int ax = 0;
-      if (S.cost[0] > S.cost[1]) ax = 1;
-      if (S.cost[ax] > S.cost[2]) ax = 2;
-      const bool median = !(S.cost[ax] < FLT_MAX);
-      Box6 lb, rb;
-      uint32_t nl, nr;
-      if (!median) {
-        range_union(sbin + (size_t)ax * B * kBinWords, 0, S.cut[ax], lb, nl);
-        range_union(sbin + (size_t)ax * B * kBinWords, S.cut[ax], B, rb, nr);
-      } else {
-        nl = n >> 1;
-        box_empty(lb);
-        box_empty(rb);
-        // exact boxes of the two halves of the current order
-        for (uint32_t i = lane; i < n; i += 32) {
-          const uint32_t q = S.ids[lo + i];
-          const float4 l4 = S.plo[q], h4 = S.phi[q];
-          Box6 &t = i < nl ? lb : rb;
-          t.v[0] = fminf(t.v[0], l4.x);
-          t.v[1] = fminf(t.v[1], l4.y);
-          t.v[2] = fminf(t.v[2], l4.z);
-          t.v[3] = fmaxf(t.v[3], h4.x);
-          t.v[4] = fmaxf(t.v[4], h4.y);
-          t.v[5] = fmaxf(t.v[5], h4.z);
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          for (int k = 0; k < 3; k++) {
-            lb.v[k] = fminf(lb.v[k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[k], o));
-            rb.v[k] = fminf(rb.v[k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[k], o));
-            lb.v[3 + k] = fmaxf(lb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[3 + k], o));
-            rb.v[3 + k] = fmaxf(rb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[3 + k], o));
+    // ---- stable partition of ids[lo, lo+n) by warp ballots
+    {
+      uint32_t done_l = 0, done_r = 0;
+      for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n;
+        uint32_t q = 0;
+        bool f = false;
+        if (valid) {
+          q = S.ids[lo + i];
+          if (median) {
+            f = i < nl;
+          } else {
+            const float c = ax == 0 ? S.plo[q].w : (ax == 1 ? S.phi[q].w : S.pcz[q]);
+            f = (uint32_t)bin_of(c, nd.bmin[ax], iv[ax], B) < (uint32_t)cut[ax];
           }
         }
-      }
-      if (lane == 0) {
-        S.axis = median ? (ax + 2) % 3 : ax;
-        S.median = median ? 1 : 0;
-        S.nl = nl;
-        S.left = atomicAdd(&ctr->pool, 2u);
-        for (int k = 0; k < 6; k++) {
-          S.cbox[0][k] = lb.v[k];
-          S.cbox[1][k] = rb.v[k];
+        const unsigned ml = __ballot_sync(0xFFFFFFFFu, valid && f), mr = __ballot_sync(0xFFFFFFFFu, valid && !f);
+        const unsigned lt = (1u << lane) - 1u;
+        if (valid) {
+          if (f)
+            S.tmp[lo + done_l + __popc(ml & lt)] = (uint16_t)q;
+          else
+            S.tmp[lo + nl + done_r + __popc(mr & lt)] = (uint16_t)q;
         }
+        done_l += __popc(ml);
+        done_r += __popc(mr);
       }
-    }
-    __syncthreads();
-    // ---- stable partition of ids[lo, lo+n)
-    {
-      const int axis = S.axis;
-      const uint32_t split = S.median ? 0u : (uint32_t)S.cut[S.median ? 0 : (S.axis)];
-      const uint32_t nl = S.nl;
-      // each thread owns a contiguous run so that a block-wide scan of run totals gives stable ranks
-      const uint32_t per = (n + kSubBlock - 1) / kSubBlock;
-      const uint32_t i0 = min(n, tid * per), i1 = min(n, i0 + per);
-      uint32_t myl = 0;
-      for (uint32_t i = i0; i < i1; i++) {
-        const uint32_t q = S.ids[lo + i];
-        bool f;
-        if (S.median) {
-          f = i < nl;
-        } else {
-          const float c = axis == 0 ? S.plo[q].w : (axis == 1 ? S.phi[q].w : S.pcz[q]);
-          f = (uint32_t)bin_of(c, nd.bmin[axis], iv[axis], B) < split;
-        }
-        myl += f ? 1u : 0u;
-      }
-      uint32_t inc = myl;
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (lane == 31) S.scan_warp[warp] = inc;
-      __syncthreads();
-      uint32_t woff = 0;
-      for (int w = 0; w < warp; w++) woff += S.scan_warp[w];
-      uint32_t lrank = woff + inc - myl;  // lefts before my run
-      uint32_t rrank = i0 - lrank;        // rights before my run
-      for (uint32_t i = i0; i < i1; i++) {
-        const uint32_t q = S.ids[lo + i];
-        bool f;
-        if (S.median) {
-          f = i < nl;
-        } else {
-          const float c = axis == 0 ? S.plo[q].w : (axis == 1 ? S.phi[q].w : S.pcz[q]);
-          f = (uint32_t)bin_of(c, nd.bmin[axis], iv[axis], B) < split;
-        }
-        if (f)
-          S.tmp[lo + lrank++] = (uint16_t)q;
-        else
-          S.tmp[lo + nl + rrank++] = (uint16_t)q;
-      }
-      __syncthreads();
-      for (uint32_t i = tid; i < n; i += kSubBlock) S.ids[lo + i] = S.tmp[lo + i];
+      __syncwarp();
+      for (uint32_t i = lane; i < n; i += 32) S.ids[lo + i] = S.tmp[lo + i];
     }
     // ---- children
-    if (tid == 0) {
+    uint32_t left = 0;
+    if (lane == 0) left = atomicAdd(&ctr->pool, 2u);
+    left = __shfl_sync(0xFFFFFFFFu, left, 0);
+    const uint32_t cdepth = nd.depth + 1;
+    const uint32_t n_side[2] = {nl, n - nl};
+    if (lane == 0) {
       BNode me = nd;
-      me.left = S.left;
-      me.axis = (uint32_t)S.axis;
-      me.split_bin = S.median ? kMedian : (uint32_t)S.cut[S.axis];
-      me.nleft = S.nl;
+      me.left = left;
+      me.axis = (uint32_t)(median ? (ax + 2) % 3 : ax);
+      me.split_bin = median ? kMedian : (uint32_t)cut[ax];
+      me.nleft = nl;
       pool[nid] = me;
-      for (int side = 1; side >= 0; side--) {  // right first, so the left child is split next
-        BNode c;
-        for (int k = 0; k < 3; k++) {
-          c.bmin[k] = S.cbox[side][k];
-          c.bmax[k] = S.cbox[side][3 + k];
-        }
-        c.l = side ? nd.l + S.nl : nd.l;
-        c.r = side ? nd.r : nd.l + S.nl;
-        c.left = kInactive;
-        c.depth = nd.depth + 1;
-        c.rturns = nd.rturns + (uint32_t)side;
-        c.axis = 0;
-        c.split_bin = 0;
-        c.nleft = 0;
-        c.slot = kInactive;
-        c.pad = 0;
-        pool[S.left + side] = c;
-        if (child_class(c.r - c.l, c.depth, min_leaf, max_depth) != 0) S.stack[S.sp++] = S.left + side;
+    }
+    if (lane < 2) {
+      const int side = lane;
+      const Box6 &bx = side ? rb : lb;
+      BNode c;
+      for (int k = 0; k < 3; k++) {
+        c.bmin[k] = bx.v[k];
+        c.bmax[k] = bx.v[3 + k];
+      }
+      c.l = side ? nd.l + nl : nd.l;
+      c.r = side ? nd.r : nd.l + nl;
+      c.left = kInactive;
+      c.depth = cdepth;
+      c.rturns = nd.rturns + (uint32_t)side;
+      c.axis = 0;
+      c.split_bin = 0;
+      c.nleft = 0;
+      c.slot = kInactive;
+      c.pad = 0;
+      pool[left + side] = c;
+    }
+    // right first, so that the left child is split next (all lanes track sp identically)
+    for (int side = 1; side >= 0; side--) {
+      if (child_class(n_side[side], cdepth, min_leaf, max_depth) != 0) {
+        if (lane == 0) S.stack[sp] = left + side;
+        sp++;
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
   // final order of this subtree's range
-  for (uint32_t i = tid; i < total; i += kSubBlock) idx[base + i] = S.gslot[S.ids[i]];
+  for (uint32_t i = lane; i < total; i += 32) idx[base + i] = S.gslot[S.ids[i]];
 }
 
 // ------------------------------------------------------------------ phase C: emission
@@ -862,8 +824,9 @@ int build_on_device(Accel *a, cudaStream_t s) {
     return NRT_ERR_INVALID;
   }
   int rc = NRT_OK;
-  float4 *d_plo = nullptr, *d_phi = nullptr;
-  float *d_pcz = nullptr;
+  float4 *d_plo = nullptr, *d_phi = nullptr, *d_plo_u = nullptr, *d_phi_u = nullptr;
+  float *d_pcz = nullptr, *d_pcz_u = nullptr;
+  uint32_t *d_order = nullptr, *d_table = nullptr;
   uint32_t *d_idx[2] = {nullptr, nullptr}, *d_nodeof[2] = {nullptr, nullptr};
   uint32_t *d_flags = nullptr, *d_scan = nullptr, *d_scratch = nullptr, *d_active[2] = {nullptr, nullptr};
   uint32_t *d_subtrees = nullptr, *d_bins = nullptr, *d_scene = nullptr;
@@ -878,13 +841,18 @@ int build_on_device(Accel *a, cudaStream_t s) {
   int cur = 0, which = 0;
   uint32_t n_active = 0;
   uint32_t n_nodes = 0;
-  const size_t sub_smem = sizeof(SubShared) + (size_t)3 * B * kBinWords * 4 + (size_t)3 * 2 * B * 4;
+  const size_t sub_smem = kSubWarps * (sizeof(WarpSub) + (size_t)3 * B * kBinWords * 4 + (size_t)2 * B * 4);
 
   BUILD_CUDA(cudaEventCreate(&ev0));
   BUILD_CUDA(cudaEventCreate(&ev1));
   BUILD_CUDA(cudaMalloc(&d_plo, sizeof(float4) * (size_t)n));
   BUILD_CUDA(cudaMalloc(&d_phi, sizeof(float4) * (size_t)n));
   BUILD_CUDA(cudaMalloc(&d_pcz, sizeof(float) * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_plo_u, sizeof(float4) * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_phi_u, sizeof(float4) * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_pcz_u, sizeof(float) * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_order, sizeof(uint32_t) * (size_t)n));
+  BUILD_CUDA(cudaMalloc(&d_table, sizeof(uint32_t) * ((size_t)kSortDigits * ((n + kSortTile - 1) / kSortTile) + 1)));
   for (int i = 0; i < 2; i++) {
     BUILD_CUDA(cudaMalloc(&d_idx[i], sizeof(uint32_t) * (size_t)n));
     BUILD_CUDA(cudaMalloc(&d_nodeof[i], sizeof(uint32_t) * (size_t)n));
@@ -902,8 +870,41 @@ int build_on_device(Accel *a, cudaStream_t s) {
     const uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
     BUILD_CUDA(cudaMemcpyAsync(d_scene, init, sizeof(init), cudaMemcpyHostToDevice, s));
   }
+  // outputs are allocated up front (2n-1 is the node bound) so that no allocation stalls the build
+  BUILD_CUDA(cudaMalloc(&a->d_nodes, sizeof(Node40) * (2 * (size_t)n)));
+  BUILD_CUDA(cudaMalloc(&a->d_indices, sizeof(uint32_t) * (size_t)n));
   BUILD_CUDA(cudaEventRecord(ev0, s));
-  prim_setup_kernel<<<grid_n, 256, 0, s>>>(a->d_verts, a->d_faces, n, d_plo, d_phi, d_pcz, d_scene);
+  prim_setup_kernel<<<grid_n, 256, 0, s>>>(a->d_verts, a->d_faces, n, d_plo_u, d_phi_u, d_pcz_u, d_scene);
+  BUILD_CUDA(cudaGetLastError());
+  {
+    // Morton pre-order: sort the primitives along a 30-bit Z-curve over the scene box, then lay their
+    // records out in that order (slot s of the builder = primitive d_order[s])
+    uint32_t keys6[6];
+    BUILD_CUDA(cudaMemcpyAsync(keys6, d_scene, sizeof(keys6), cudaMemcpyDeviceToHost, s));
+    BUILD_CUDA(cudaStreamSynchronize(s));
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+      uint32_t kmin = keys6[k], kmax = keys6[3 + k];
+      uint32_t umin = (kmin & 0x80000000u) ? (kmin ^ 0x80000000u) : ~kmin;
+      uint32_t umax = (kmax & 0x80000000u) ? (kmax ^ 0x80000000u) : ~kmax;
+      memcpy(&lo[k], &umin, 4);
+      memcpy(&hi[k], &umax, 4);
+      a->root_bmin[k] = lo[k];
+      a->root_bmax[k] = hi[k];
+    }
+    float3 smin = make_float3(lo[0], lo[1], lo[2]);
+    float3 sinv = make_float3(hi[0] > lo[0] ? 1024.0f / (hi[0] - lo[0]) : 0.0f, hi[1] > lo[1] ? 1024.0f / (hi[1] - lo[1]) : 0.0f,
+                              hi[2] > lo[2] ? 1024.0f / (hi[2] - lo[2]) : 0.0f);
+    uint32_t *keys = d_flags, *keys_tmp = d_scan, *vals = d_order, *vals_tmp = d_nodeof[1];
+    morton_kernel<<<grid_n, 256, 0, s>>>(d_plo_u, d_phi_u, d_pcz_u, n, smin, sinv, keys, vals);
+    BUILD_CUDA(cudaGetLastError());
+    BUILD_CHECK(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 32, d_table, d_scratch, s));
+    if (vals != d_order) {  // odd number of passes: keep the result in d_order
+      BUILD_CUDA(cudaMemcpyAsync(d_order, vals, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    }
+    gather_prims_kernel<<<grid_n, 256, 0, s>>>(d_order, d_plo_u, d_phi_u, d_pcz_u, n, d_plo, d_phi, d_pcz);
+    BUILD_CUDA(cudaGetLastError());
+  }
   iota_kernel<<<grid_n, 256, 0, s>>>(d_idx[0], d_nodeof[0], n);
   init_build_kernel<<<1, 1, 0, s>>>(d_pool, d_ctr, d_scene, n, min_leaf, opt.max_tree_depth,
                                     d_active[0], d_subtrees);
@@ -942,7 +943,8 @@ int build_on_device(Accel *a, cudaStream_t s) {
   // ---- phase B
   if (hc.n_subtrees > 0) {
     BUILD_CUDA(cudaFuncSetAttribute(subtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem));
-    subtree_kernel<<<hc.n_subtrees, kSubBlock, sub_smem, s>>>(d_pool, d_ctr, d_subtrees, d_idx[which], d_plo, d_phi,
+    subtree_kernel<<<(hc.n_subtrees + kSubWarps - 1) / kSubWarps, kSubWarps * 32, sub_smem, s>>>(
+        d_pool, d_ctr, d_subtrees, hc.n_subtrees, d_idx[which], d_plo, d_phi,
                                                               d_pcz, B, min_leaf, opt.max_tree_depth);
     BUILD_CUDA(cudaGetLastError());
   }
@@ -955,26 +957,14 @@ int build_on_device(Accel *a, cudaStream_t s) {
   mark_leaves_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(d_pool, n_nodes, d_flags, d_ctr);
   BUILD_CUDA(cudaGetLastError());
   BUILD_CHECK(exclusive_scan_u32_async(d_flags, d_scan, n + 1, d_scratch, s));
-  BUILD_CUDA(cudaMalloc(&a->d_nodes, sizeof(Node40) * (size_t)n_nodes));
   emit_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(d_pool, n_nodes, d_scan, a->d_nodes);
   BUILD_CUDA(cudaGetLastError());
-  // indices_: without a pre-sort the primitive slot IS the primitive id
-  a->d_indices = d_idx[which];
-  d_idx[which] = nullptr;
+  // indices_ holds ORIGINAL primitive ids: slot -> primitive through the Morton order
+  map_indices_kernel<<<grid_n, 256, 0, s>>>(d_idx[which], d_order, n, a->d_indices);
+  BUILD_CUDA(cudaGetLastError());
   BUILD_CUDA(cudaEventRecord(ev1, s));
   BUILD_CUDA(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, s));
-  {
-    uint32_t keys[6];
-    BUILD_CUDA(cudaMemcpyAsync(keys, d_scene, sizeof(keys), cudaMemcpyDeviceToHost, s));
-    BUILD_CUDA(cudaStreamSynchronize(s));
-    for (int k = 0; k < 3; k++) {
-      uint32_t kmin = keys[k], kmax = keys[3 + k];
-      uint32_t umin = (kmin & 0x80000000u) ? (kmin ^ 0x80000000u) : ~kmin;
-      uint32_t umax = (kmax & 0x80000000u) ? (kmax ^ 0x80000000u) : ~kmax;
-      memcpy(&a->root_bmin[k], &umin, 4);
-      memcpy(&a->root_bmax[k], &umax, 4);
-    }
-  }
+  BUILD_CUDA(cudaStreamSynchronize(s));
   {
     float ms = 0.0f;
     BUILD_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -990,6 +980,11 @@ done:
   cudaFree(d_plo);
   cudaFree(d_phi);
   cudaFree(d_pcz);
+  cudaFree(d_plo_u);
+  cudaFree(d_phi_u);
+  cudaFree(d_pcz_u);
+  cudaFree(d_order);
+  cudaFree(d_table);
   for (int i = 0; i < 2; i++) {
     cudaFree(d_idx[i]);
     cudaFree(d_nodeof[i]);

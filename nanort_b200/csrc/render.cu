@@ -12,91 +12,49 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "wavefront.cuh"
 
 namespace nrt {
 
 namespace {
 
-struct Wave {
-  float4 *org_tmin;   // primary queue
-  float4 *dir_tmax;
-  Hit16 *hits;
-  uint32_t *pix;      // pixel of primary slot (0xFFFFFFFF = slot outside the image)
-  float4 *ao_org_tmin;  // compacted AO queue
-  float4 *ao_dir_tmax;
-  uint32_t *ao_pix;
-  Hit16 *ao_hits;
-};
-
-__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {  // lowbias32, same as scenes.py:hash_u32
-  x ^= x >> 16;
-  x *= 0x7FEB352Du;
-  x ^= x >> 15;
-  x *= 0x846CA68Bu;
-  x ^= x >> 16;
-  return x;
-}
-
-// scenes.py:rand_ps
-__device__ __forceinline__ float rand_ps(uint32_t pix, uint32_t smp, uint32_t dim, uint32_t seed) {
-  uint32_t h = hash_u32(pix + seed * 0x9E3779B1u);
-  h = hash_u32(h + smp * 0x85EBCA77u + dim * 0xC2B2AE3Du);
-  return (float)(h >> 8) * (1.0f / 16777216.0f);
-}
-
-// Slot -> (pixel, sample).  Slots enumerate this shard's tiles; inside a tile the order is
-// sample-major over 8x4 pixel blocks, so the 32 lanes of a warp start as one coherent 8x4 packet.
-__device__ __forceinline__ bool slot_to_pixel(const nrt_ao_params &p, unsigned long long slot, uint32_t &pix,
-                                              uint32_t &smp) {
-  const uint32_t tile_pix = p.tile_w * p.tile_h;
-  const unsigned long long per_tile = (unsigned long long)tile_pix * p.spp;
-  const uint32_t k = (uint32_t)(slot / per_tile);  // k-th tile of this shard
-  const uint32_t rem = (uint32_t)(slot % per_tile);
-  smp = rem / tile_pix;
-  const uint32_t q = rem % tile_pix;
-  const uint32_t bw = p.tile_w / 8;  // 8x4 blocks per tile row
-  const uint32_t blk = q / 32, in = q % 32;
-  const uint32_t bx = blk % bw, by = blk / bw;
-  const uint32_t lx = bx * 8 + (in & 7), ly = by * 4 + (in >> 3);
-  const uint32_t tiles_x = (p.width + p.tile_w - 1) / p.tile_w;
-  const uint32_t tile = k * p.n_shards + p.shard;
-  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-  const uint32_t x = tx * p.tile_w + lx, y = ty * p.tile_h + ly;
-  if (x >= p.width || y >= p.height) return false;
-  pix = y * p.width + x;
-  return true;
-}
-
 __global__ void __launch_bounds__(256)
-    gen_primary_kernel(nrt_ao_params p, unsigned long long slot0, uint32_t count, Wave w) {
+    gen_primary_kernel(nrt_ao_params p, unsigned long long slot0, uint32_t count, Wave w,
+                       unsigned long long *counters /* [1] valid primaries of this wave */) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  uint32_t pix, smp;
-  if (!slot_to_pixel(p, slot0 + i, pix, smp)) {
-    w.pix[i] = 0xFFFFFFFFu;
-    w.org_tmin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    w.dir_tmax[i] = make_float4(0.f, 0.f, -1.f, -1.f);  // max_t < min_t: retires at the root
-    return;
+  bool valid = false;
+  if (i < count) {
+    uint32_t pix, smp;
+    if (!slot_to_pixel(p, slot0 + i, pix, smp)) {
+      w.pix[i] = 0xFFFFFFFFu;
+      w.org_tmin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w.dir_tmax[i] = make_float4(0.f, 0.f, -1.f, -1.f);  // max_t < min_t: retires at the root
+    } else {
+      valid = true;
+      smp += p.sample0;
+      const float jx = rand_ps(pix, smp, 0, p.seed), jy = rand_ps(pix, smp, 1, p.seed);
+      const float px = (float)(pix % p.width), py = (float)(pix / p.width);
+      const float sx = (px + jx) / (float)p.width - 0.5f;
+      const float sy = 0.5f - (py + jy) / (float)p.height;
+      float dx = p.cam[3] * sx + p.cam[6] * sy + p.cam[9];
+      float dy = p.cam[4] * sx + p.cam[7] * sy + p.cam[10];
+      float dz = p.cam[5] * sx + p.cam[8] * sy + p.cam[11];
+      const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+      w.pix[i] = pix;
+      w.org_tmin[i] = make_float4(p.cam[0], p.cam[1], p.cam[2], p.ray_min_t);
+      w.dir_tmax[i] = make_float4(dx * inv, dy * inv, dz * inv, p.ray_max_t);
+    }
   }
-  smp += p.sample0;
-  const float jx = rand_ps(pix, smp, 0, p.seed), jy = rand_ps(pix, smp, 1, p.seed);
-  const float px = (float)(pix % p.width), py = (float)(pix / p.width);
-  const float sx = (px + jx) / (float)p.width - 0.5f;
-  const float sy = 0.5f - (py + jy) / (float)p.height;
-  float dx = p.cam[3] * sx + p.cam[6] * sy + p.cam[9];
-  float dy = p.cam[4] * sx + p.cam[7] * sy + p.cam[10];
-  float dz = p.cam[5] * sx + p.cam[8] * sy + p.cam[11];
-  const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-  w.pix[i] = pix;
-  w.org_tmin[i] = make_float4(p.cam[0], p.cam[1], p.cam[2], p.ray_min_t);
-  w.dir_tmax[i] = make_float4(dx * inv, dy * inv, dz * inv, p.ray_max_t);
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 1, (unsigned long long)__popc(m));
 }
 
-// One AO ray per primary hit, compacted with one atomic per warp; primary misses count as unoccluded.
+// Stand-alone AO stage (used when the queues are exported, and as the A/B partner of the fused epilogue):
+// one AO ray per primary hit, compacted with one atomic per warp; primary misses count as unoccluded.
 __global__ void __launch_bounds__(256)
     gen_ao_kernel(nrt_ao_params p, unsigned long long slot0, uint32_t count, Wave w,
                   const float *__restrict__ verts, const uint32_t *__restrict__ faces, float *__restrict__ accum,
-                  unsigned long long *counters /* [0] ao rays of this wave, [1] valid primaries */) {
+                  unsigned long long *counters /* [0] ao rays of this wave */) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool make = false;
@@ -109,53 +67,15 @@ __global__ void __launch_bounds__(256)
       if (h.prim_id == 0xFFFFFFFFu) {
         atomicAdd(accum + pix, 1.0f);
       } else {
-        const float4 o = w.org_tmin[i], d = w.dir_tmax[i];
-        const float Px = o.x + d.x * h.t, Py = o.y + d.y * h.t, Pz = o.z + d.z * h.t;
-        const uint32_t f0 = faces[3 * (size_t)h.prim_id], f1 = faces[3 * (size_t)h.prim_id + 1],
-                       f2 = faces[3 * (size_t)h.prim_id + 2];
-        const float *p0 = verts + 3 * (size_t)f0, *p1 = verts + 3 * (size_t)f1, *p2 = verts + 3 * (size_t)f2;
-        const float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
-        const float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
-        float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
-        float ln = sqrtf(nx * nx + ny * ny + nz * nz);
-        ln = ln > 0.0f ? 1.0f / ln : 0.0f;
-        nx *= ln;
-        ny *= ln;
-        nz *= ln;
-        if (nx * d.x + ny * d.y + nz * d.z > 0.0f) {
-          nx = -nx;
-          ny = -ny;
-          nz = -nz;
-        }
-        // branch-free orthonormal basis around n
-        const float sg = nz >= 0.0f ? 1.0f : -1.0f;
-        const float a = -1.0f / (sg + nz), b = nx * ny * a;
-        const float t1x = 1.0f + sg * nx * nx * a, t1y = sg * b, t1z = -sg * nx;
-        const float t2x = b, t2y = sg + ny * ny * a, t2z = -ny;
-        const uint32_t smp = p.sample0 + (uint32_t)(((slot0 + i) % ((unsigned long long)p.tile_w * p.tile_h * p.spp)) /
-                                                    (p.tile_w * p.tile_h));
-        const float u1 = rand_ps(pix, smp, 2, p.seed), u2 = rand_ps(pix, smp, 3, p.seed);
-        const float r = sqrtf(u1), ph = 6.28318530718f * u2;
-        float sn, cs;
-        sincosf(ph, &sn, &cs);
-        const float lx = r * cs, ly = r * sn, lz = sqrtf(fmaxf(0.0f, 1.0f - u1));
-        float wx = t1x * lx + t2x * ly + nx * lz, wy = t1y * lx + t2y * ly + ny * lz,
-              wz = t1z * lx + t2z * ly + nz * lz;
-        const float il = 1.0f / sqrtf(wx * wx + wy * wy + wz * wz);
-        o4 = make_float4(Px, Py, Pz, p.ao_min_t);
-        d4 = make_float4(wx * il, wy * il, wz * il, p.ao_max_t);
+        make_ao_ray(p, pix, slot_sample(p, slot0 + i), w.org_tmin[i], w.dir_tmax[i], h.t, h.prim_id, verts, faces, o4, d4);
         make = true;
       }
     }
   }
   const unsigned m = __ballot_sync(0xFFFFFFFFu, make);
-  const unsigned valid = __ballot_sync(0xFFFFFFFFu, pix != 0xFFFFFFFFu);
-  if (m == 0u && valid == 0u) return;
+  if (m == 0u) return;
   unsigned long long base = 0;
-  if (lane == 0) {
-    if (m) base = atomicAdd(counters + 0, (unsigned long long)__popc(m));
-    if (valid) atomicAdd(counters + 1, (unsigned long long)__popc(valid));
-  }
+  if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)__popc(m));
   base = __shfl_sync(0xFFFFFFFFu, base, 0);
   if (make) {
     const unsigned long long j = base + __popc(m & ((1u << lane) - 1u));
@@ -181,6 +101,11 @@ __global__ void __launch_bounds__(256)
     atomicAdd(totals + 0, n);
     atomicAdd(totals + 2, counters[1]);
   }
+}
+
+__global__ void fold_wave_counters_kernel(const unsigned long long *counters, unsigned long long *totals) {
+  totals[0] += counters[0];
+  totals[2] += counters[1];
 }
 
 // AoS copy of a SoA queue as 36-byte nanort::Ray records (workload export for the host-buffer arms)
@@ -211,6 +136,12 @@ __global__ void __launch_bounds__(256)
 int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const float4 *d_dir_tmax,
                                  const unsigned long long *d_count, size_t capacity, Hit16 *d_hits,
                                  const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
+int launch_traverse_primary_fused(const Accel *a, const Wave &w, const nrt_ao_params &p, unsigned long long slot0,
+                                  size_t count, float *d_accum, unsigned long long *d_wave_counters,
+                                  const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
+int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long long *d_count, size_t capacity,
+                             float *d_accum, unsigned long long *d_totals, const TraceOptions16 &opt, uint32_t flags,
+                             cudaStream_t s);
 
 }  // namespace nrt
 
@@ -286,12 +217,14 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
   }
   uint32_t launches = 0, trav_launches = 0;
   unsigned long long dumped_ao = 0;
+  const bool fused = !dump_primary && !dump_ao && !(p.flags & NRT_AO_UNFUSED);
+  const uint32_t trav_flags = p.flags & 0xFFFFu;
   int rc = NRT_OK;
   for (unsigned long long s0 = 0; s0 < total_slots && rc == NRT_OK; s0 += cap) {
     const uint32_t count = (uint32_t)std::min<unsigned long long>(cap, total_slots - s0);
     const uint32_t grid = (count + 255) / 256;
     cudaMemsetAsync(wave_ctr, 0, 2 * sizeof(unsigned long long), s);
-    gen_primary_kernel<<<grid, 256, 0, s>>>(p, s0, count, w);
+    gen_primary_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, wave_ctr);
     launches++;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
     if (res) {
@@ -303,35 +236,52 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
       ev.push_back(t1);
       ev.push_back(t2);
       ev.push_back(t3);
-      cudaEventRecord(t0, s);
     }
-    if (dump_primary) {
-      soa_to_aos_kernel<<<grid, 256, 0, s>>>(w.org_tmin, w.dir_tmax, nullptr, count, dump_primary + s0, 1u);
+    if (fused) {
+      // 3 launches per wave: the traversal kernels' retire steps spawn the AO rays and accumulate visibility
+      if (res) cudaEventRecord(t0, s);
+      rc = launch_traverse_primary_fused(a, w, p, s0, count, d_accum, wave_ctr, opt, trav_flags, s);
+      if (rc != NRT_OK) break;
+      if (res) {
+        cudaEventRecord(t1, s);
+        cudaEventRecord(t2, s);
+      }
+      rc = launch_traverse_ao_fused(a, w, wave_ctr, count, d_accum, totals, opt, trav_flags, s);
+      if (rc != NRT_OK) break;
+      if (res) cudaEventRecord(t3, s);
+      fold_wave_counters_kernel<<<1, 1, 0, s>>>(wave_ctr, totals);
+      launches += 3;
+      trav_launches += 2;
+    } else {
+      if (dump_primary) {
+        soa_to_aos_kernel<<<grid, 256, 0, s>>>(w.org_tmin, w.dir_tmax, nullptr, count, dump_primary + s0, 1u);
+        launches++;
+      }
+      if (res) cudaEventRecord(t0, s);
+      rc = launch_traverse_soa(a, w.org_tmin, w.dir_tmax, count, w.hits, opt, trav_flags, s);
+      if (rc != NRT_OK) break;
+      if (res) cudaEventRecord(t1, s);
+      launches++;
+      trav_launches++;
+      gen_ao_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, a->d_verts, a->d_faces, d_accum, wave_ctr);
+      launches++;
+      if (dump_ao) {
+        unsigned long long n_wave = 0;
+        soa_to_aos_kernel<<<grid, 256, 0, s>>>(w.ao_org_tmin, w.ao_dir_tmax, wave_ctr, 0, dump_ao + dumped_ao, 2u);
+        launches++;
+        cudaMemcpyAsync(&n_wave, wave_ctr, sizeof(n_wave), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        dumped_ao += n_wave;
+      }
+      if (res) cudaEventRecord(t2, s);
+      rc = launch_traverse_soa_devcount(a, w.ao_org_tmin, w.ao_dir_tmax, wave_ctr, count, w.ao_hits, opt, trav_flags, s);
+      if (rc != NRT_OK) break;
+      if (res) cudaEventRecord(t3, s);
+      launches++;
+      trav_launches++;
+      accumulate_ao_kernel<<<grid, 256, 0, s>>>(w, wave_ctr, d_accum, totals);
       launches++;
     }
-    rc = launch_traverse_soa(a, w.org_tmin, w.dir_tmax, count, w.hits, opt, p.flags, s);
-    if (rc != NRT_OK) break;
-    if (res) cudaEventRecord(t1, s);
-    launches++;
-    trav_launches++;
-    gen_ao_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, a->d_verts, a->d_faces, d_accum, wave_ctr);
-    launches++;
-    if (res) cudaEventRecord(t2, s);
-    if (dump_ao) {
-      unsigned long long n_wave = 0;
-      soa_to_aos_kernel<<<grid, 256, 0, s>>>(w.ao_org_tmin, w.ao_dir_tmax, wave_ctr, 0, dump_ao + dumped_ao, 2u);
-      launches++;
-      cudaMemcpyAsync(&n_wave, wave_ctr, sizeof(n_wave), cudaMemcpyDeviceToHost, s);
-      cudaStreamSynchronize(s);
-      dumped_ao += n_wave;
-    }
-    rc = launch_traverse_soa_devcount(a, w.ao_org_tmin, w.ao_dir_tmax, wave_ctr, count, w.ao_hits, opt, p.flags, s);
-    if (rc != NRT_OK) break;
-    if (res) cudaEventRecord(t3, s);
-    launches++;
-    trav_launches++;
-    accumulate_ao_kernel<<<grid, 256, 0, s>>>(w, wave_ctr, d_accum, totals);
-    launches++;
     if (cudaGetLastError() != cudaSuccess) rc = NRT_ERR_CUDA;
   }
   if (rc == NRT_OK && res) {

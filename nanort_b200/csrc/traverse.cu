@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "wavefront.cuh"
 
 namespace nrt {
 
@@ -514,11 +515,11 @@ __device__ __forceinline__ void tri_test2(const RayCtx &c, const TraceOptions16 
   }
 }
 
-template <class Rays, int LOCAL_DEPTH, bool COUNT, class P>
+template <class Rays, int LOCAL_DEPTH, bool COUNT, class P, class Epi>
 __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
     traverse_fast2_kernel(const WideNode *__restrict__ wide, const PackedTri *__restrict__ tris, Rays rays, size_t n,
-                          Hit16 *__restrict__ hits, uint8_t *__restrict__ mask, TraceOptions16 opt, uint32_t flags,
-                          unsigned long long *cursor, unsigned long long *counts, const unsigned long long *n_ptr) {
+                          Epi epi, TraceOptions16 opt, uint32_t flags, unsigned long long *cursor,
+                          unsigned long long *counts, const unsigned long long *n_ptr) {
   constexpr int BLOCK = P::kBlock;
   __shared__ uint2 stk[kStackSmem * BLOCK];
   if (n_ptr) n = (size_t)*n_ptr;
@@ -644,11 +645,10 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
       }
     }
 
-    // ---- retire
-    if (ray_idx >= 0 && cur == kNone && leaf == kNone) {
-      if (hits) write_result(hits, mask, (size_t)ray_idx, best, max_t);
-      ray_idx = -1;
-    }
+    // ---- retire: the epilogue (store the hit / spawn the AO ray / accumulate) runs warp-wide
+    const bool retiring = ray_idx >= 0 && cur == kNone && leaf == kNone;
+    if (__any_sync(FULL_MASK, retiring)) epi(retiring, (size_t)ray_idx, best.t, best.u, best.v, best.prim, max_t);
+    if (retiring) ray_idx = -1;
   }
 
   if (COUNT) {
@@ -675,23 +675,23 @@ int device_sm_count(int device) {
   return g_sm_count[device];
 }
 
-template <class Rays, int LOCAL_DEPTH, bool COUNT, class P>
-static cudaError_t launch_fast2(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
-                                const TraceOptions16 &opt, uint32_t flags, unsigned long long *cursor,
-                                unsigned long long *d_counts, const unsigned long long *n_ptr, cudaStream_t s) {
+template <class Rays, int LOCAL_DEPTH, bool COUNT, class P, class Epi>
+static cudaError_t launch_fast2(const Accel *a, Rays rays, size_t n, Epi epi, const TraceOptions16 &opt,
+                                uint32_t flags, unsigned long long *cursor, unsigned long long *d_counts,
+                                const unsigned long long *n_ptr, cudaStream_t s) {
   const int sms = device_sm_count(a->device);
   const size_t warps_per_block = P::kBlock / 32;
   size_t grid = (size_t)sms * P::kMinBlocks;
   const size_t need_blocks = ((n + 31) / 32 + warps_per_block - 1) / warps_per_block;
   if (grid > need_blocks) grid = need_blocks;
   if (grid == 0) grid = 1;
-  traverse_fast2_kernel<Rays, LOCAL_DEPTH, COUNT, P><<<(unsigned)grid, P::kBlock, 0, s>>>(
-      a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, n_ptr);
+  traverse_fast2_kernel<Rays, LOCAL_DEPTH, COUNT, P, Epi><<<(unsigned)grid, P::kBlock, 0, s>>>(
+      a->d_wide, a->d_tris, rays, n, epi, opt, flags, cursor, d_counts, n_ptr);
   return cudaGetLastError();
 }
 
 // Default policy (chosen from the sweep in profiles/r01_variant_sweep.md)
-typedef FastPolicy<128, 8, 8, 0> DefaultPolicy;
+typedef FastPolicy<128, 10, 16, 8> DefaultPolicy;
 
 template <class Rays, bool COUNT>
 static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
@@ -704,16 +704,16 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
   const bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
   const uint32_t variant = (flags >> 8) & 0xFFu;  // experiment selector (tools/trav_sweep.py); 0 = default
   cudaError_t e = cudaSuccess;
+  const StoreHitsEpilogue epi{d_hits, d_mask};
   if (deep) {
-    e = launch_fast2<Rays, 512 - kStackSmem, COUNT, DefaultPolicy>(a, rays, n, d_hits, d_mask, opt, flags, cursor,
-                                                                    d_counts, n_ptr, s);
+    e = launch_fast2<Rays, 512 - kStackSmem, COUNT, DefaultPolicy>(a, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, s);
   } else if (variant == 0 || COUNT) {
-    e = launch_fast2<Rays, 48, COUNT, DefaultPolicy>(a, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, n_ptr, s);
+    e = launch_fast2<Rays, 48, COUNT, DefaultPolicy>(a, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, s);
   } else {
 #define NRT_VARIANT(id, ...)                                                                                        \
   case id:                                                                                                          \
-    e = launch_fast2<Rays, 48, false, FastPolicy<__VA_ARGS__> >(a, rays, n, d_hits, d_mask, opt, flags, cursor,      \
-                                                                d_counts, n_ptr, s);                                \
+    e = launch_fast2<Rays, 48, false, FastPolicy<__VA_ARGS__> >(a, rays, n, epi, opt, flags, cursor, d_counts,      \
+                                                                n_ptr, s);                                          \
     break;
     switch (variant) {
       NRT_VARIANT(1, 128, 8, 8, 0)
@@ -729,6 +729,14 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
       NRT_VARIANT(11, 128, 10, 8, 0)
       NRT_VARIANT(12, 128, 8, 12, 12)
       NRT_VARIANT(13, 128, 8, 4, 24)
+      NRT_VARIANT(14, 128, 10, 8, 8)
+      NRT_VARIANT(15, 128, 10, 8, 4)
+      NRT_VARIANT(16, 128, 12, 8, 8)
+      NRT_VARIANT(17, 64, 20, 8, 8)
+      NRT_VARIANT(18, 128, 10, 16, 8)
+      NRT_VARIANT(19, 128, 10, 8, 12)
+      NRT_VARIANT(20, 256, 5, 8, 8)
+      NRT_VARIANT(21, 128, 9, 8, 8)
       case 255: {  // first-generation kernel, kept for A/B runs
         const int sms = device_sm_count(a->device);
         size_t grid = (size_t)sms * 8;
@@ -787,6 +795,52 @@ int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const
   if (flags & NRT_TRAVERSE_CONFORMANCE)
     return launch_conf<SoaRays, false>(a, r, capacity, d_hits, nullptr, opt, flags, nullptr, s, d_count);
   return launch_fast<SoaRays, false>(a, r, capacity, d_hits, nullptr, opt, flags, nullptr, s, d_count);
+}
+
+// Fused wavefront launches (render.cu): the retire step spawns the AO ray / accumulates visibility.
+template <class Epi, class P = DefaultPolicy>
+static int launch_fused(const Accel *a, SoaRays rays, size_t n, const unsigned long long *n_ptr, Epi epi,
+                        const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  if (n == 0) return NRT_OK;
+  unsigned long long *cursor =
+      reinterpret_cast<unsigned long long *>(a->d_counters) + 16 + (a->cursor_ring.fetch_add(1) & 31u);
+  NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+  const bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
+  cudaError_t e;
+  if (deep)
+    e = launch_fast2<SoaRays, 512 - kStackSmem, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
+  else
+    e = launch_fast2<SoaRays, 48, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
+  NRT_CUDA(e);
+  return NRT_OK;
+}
+
+int launch_traverse_primary_fused(const Accel *a, const Wave &w, const nrt_ao_params &p, unsigned long long slot0,
+                                  size_t count, float *d_accum, unsigned long long *d_wave_counters,
+                                  const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  PrimaryToAoEpilogue epi{p, slot0, w, a->d_verts, a->d_faces, d_accum, d_wave_counters};
+  return launch_fused(a, SoaRays{w.org_tmin, w.dir_tmax}, count, nullptr, epi, opt, flags, s);
+}
+
+int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long long *d_count, size_t capacity,
+                             float *d_accum, unsigned long long *d_totals, const TraceOptions16 &opt, uint32_t flags,
+                             cudaStream_t s) {
+  AoAccumulateEpilogue epi{w.ao_pix, d_accum, d_totals};
+  return launch_fused(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count, epi, opt, flags, s);
+}
+
+int launch_traverse_path_radiance(const Accel *a, const PathShadeEpilogue &epi, const unsigned long long *d_count,
+                                  size_t capacity, const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  // the shading block needs more registers than the plain traversal: 8 CTAs/SM (64 registers) instead of 10
+  return launch_fused<PathShadeEpilogue, FastPolicy<128, 8, 16, 8> >(
+      a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]}, capacity, d_count, epi, opt, flags, s);
+}
+
+int launch_traverse_path_shadow(const Accel *a, const PathQueues &q, const unsigned long long *d_count,
+                                size_t capacity, float *d_accum, const TraceOptions16 &opt, uint32_t flags,
+                                cudaStream_t s) {
+  ShadowAccumulateEpilogue epi{q.sh_contrib_pix, d_accum};
+  return launch_fused(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity, d_count, epi, opt, flags, s);
 }
 
 int launch_traverse_count(const Accel *a, const Ray36 *d_rays, size_t n, const TraceOptions16 &opt,

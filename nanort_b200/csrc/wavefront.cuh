@@ -35,9 +35,20 @@ __device__ __forceinline__ float rand_ps(uint32_t pix, uint32_t smp, uint32_t di
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
+// The part of nrt_ao_params / nrt_path_params that maps ray slots to pixels.
+struct TileMap {
+  uint32_t width, height, spp, sample0, tile_w, tile_h, shard, n_shards;
+};
+__host__ __device__ __forceinline__ TileMap tile_map(const nrt_ao_params &p) {
+  return TileMap{p.width, p.height, p.spp, p.sample0, p.tile_w, p.tile_h, p.shard, p.n_shards};
+}
+__host__ __device__ __forceinline__ TileMap tile_map(const nrt_path_params &p) {
+  return TileMap{p.width, p.height, p.spp, p.sample0, p.tile_w, p.tile_h, p.shard, p.n_shards};
+}
+
 // Slot -> (pixel, sample).  Slots enumerate this shard's tiles; inside a tile the order is sample-major over
 // 8x4 pixel blocks, so the 32 lanes of a warp start as one coherent 8x4 packet.
-__device__ __forceinline__ bool slot_to_pixel(const nrt_ao_params &p, unsigned long long slot, uint32_t &pix,
+__device__ __forceinline__ bool slot_to_pixel(const TileMap &p, unsigned long long slot, uint32_t &pix,
                                               uint32_t &smp) {
   const uint32_t tile_pix = p.tile_w * p.tile_h;
   const unsigned long long per_tile = (unsigned long long)tile_pix * p.spp;
@@ -56,6 +67,11 @@ __device__ __forceinline__ bool slot_to_pixel(const nrt_ao_params &p, unsigned l
   if (x >= p.width || y >= p.height) return false;
   pix = y * p.width + x;
   return true;
+}
+
+__device__ __forceinline__ bool slot_to_pixel(const nrt_ao_params &p, unsigned long long slot, uint32_t &pix,
+                                              uint32_t &smp) {
+  return slot_to_pixel(tile_map(p), slot, pix, smp);
 }
 
 __device__ __forceinline__ uint32_t slot_sample(const nrt_ao_params &p, unsigned long long slot) {
@@ -172,6 +188,194 @@ struct AoAccumulateEpilogue {
     if (retiring && !occluded) atomicAdd(accum + ao_pix[ray_idx], 1.0f);
     const unsigned m = __ballot_sync(0xFFFFFFFFu, occluded);
     if (m != 0u && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(totals + 1, (unsigned long long)__popc(m));
+  }
+};
+
+// ------------------------------------------------------------------ path tracing wavefront
+struct PathQueues {
+  // radiance queue in / out (ping-pong), SoA rays + the path (= primary slot of the wave) each ray belongs to
+  float4 *org_tmin[2];
+  float4 *dir_tmax[2];
+  uint32_t *path_id[2];
+  // shadow queue: ray + (contribution.rgb, pixel)
+  float4 *sh_org_tmin;
+  float4 *sh_dir_tmax;
+  float4 *sh_contrib_pix;
+  float4 *weight;  // per path: throughput rgb
+};
+
+__device__ __forceinline__ void geometric_normal(const float *__restrict__ verts, const uint32_t *__restrict__ faces,
+                                                 uint32_t prim, float &nx, float &ny, float &nz, float &area2) {
+  const uint32_t f0 = faces[3 * (size_t)prim], f1 = faces[3 * (size_t)prim + 1], f2 = faces[3 * (size_t)prim + 2];
+  const float *p0 = verts + 3 * (size_t)f0, *p1 = verts + 3 * (size_t)f1, *p2 = verts + 3 * (size_t)f2;
+  const float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
+  const float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
+  nx = e1y * e2z - e1z * e2y;
+  ny = e1z * e2x - e1x * e2z;
+  nz = e1x * e2y - e1y * e2x;
+  area2 = sqrtf(nx * nx + ny * ny + nz * nz);
+  const float il = area2 > 0.0f ? 1.0f / area2 : 0.0f;
+  nx *= il;
+  ny *= il;
+  nz *= il;
+}
+
+// Radiance rays of bounce `bounce`: the retire step is the reference's per-hit shading block.
+struct PathShadeEpilogue {
+  nrt_path_params p;
+  unsigned long long slot0;
+  int in;  // which radiance queue is being traversed; (in ^ 1) receives the continuation rays
+  uint32_t bounce;
+  PathQueues q;
+  const float *verts;
+  const uint32_t *faces;
+  float *accum;                  // rgb
+  unsigned long long *counters;  // [0] continuation rays, [1] shadow rays of this bounce
+  __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
+                                             float max_t) const {
+    (void)u;
+    (void)v;
+    bool cont = false, shadow = false;
+    float4 co = make_float4(0, 0, 0, 0), cd = co, so = co, sd = co, sc = co;
+    uint32_t pid = 0;
+    if (retiring && t < max_t) {
+      pid = q.path_id[in][ray_idx];
+      uint32_t pix, smp;
+      if (slot_to_pixel(tile_map(p), slot0 + pid, pix, smp)) {
+        smp += p.sample0;
+        const float4 o = q.org_tmin[in][ray_idx], d = q.dir_tmax[in][ray_idx];
+        float4 w = q.weight[pid];
+        float nx, ny, nz, a2;
+        geometric_normal(verts, faces, prim, nx, ny, nz, a2);
+        const float ndotd = nx * d.x + ny * d.y + nz * d.z;
+        if (prim - p.light_first_face < p.light_n_faces) {
+          // EMIT lobe: only when the previous event did no light sampling, i.e. for camera rays
+          if (bounce == 0) {
+            const float c = fmaxf(-ndotd, 0.0f);
+            atomicAdd(accum + 3 * (size_t)pix + 0, c * p.emission[0] * w.x);
+            atomicAdd(accum + 3 * (size_t)pix + 1, c * p.emission[1] * w.y);
+            atomicAdd(accum + 3 * (size_t)pix + 2, c * p.emission[2] * w.z);
+          }
+        } else {
+          const float Px = o.x + d.x * t, Py = o.y + d.y * t, Pz = o.z + d.z * t;
+          if (ndotd > 0.0f) {
+            nx = -nx;
+            ny = -ny;
+            nz = -nz;
+          }
+          const uint32_t dim = 8u + 8u * bounce;
+          // ---- next-event estimation (MeshLight::sampleDirect)
+          if (p.light_n_faces > 0) {
+            float xi1 = rand_ps(pix, smp, dim + 0, p.seed);
+            const float xi2 = rand_ps(pix, smp, dim + 1, p.seed);
+            const float nf = (float)p.light_n_faces;
+            uint32_t face = min((uint32_t)floorf(xi1 * nf), p.light_n_faces - 1u);
+            xi1 = xi1 * nf - (float)face;
+            const uint32_t fid = p.light_first_face + face;
+            const uint32_t f0 = faces[3 * (size_t)fid], f1 = faces[3 * (size_t)fid + 1], f2 = faces[3 * (size_t)fid + 2];
+            const float *v0 = verts + 3 * (size_t)f0, *v1 = verts + 3 * (size_t)f1, *v2 = verts + 3 * (size_t)f2;
+            const float s1 = sqrtf(xi1), c0 = 1.0f - s1, c1 = s1 * (1.0f - xi2), c2 = s1 * xi2;
+            float lnx, lny, lnz, la2;
+            geometric_normal(verts, faces, fid, lnx, lny, lnz, la2);
+            const float area = 0.5f * la2;
+            float lx = c0 * v0[0] + c1 * v1[0] + c2 * v2[0] - Px, ly = c0 * v0[1] + c1 * v1[1] + c2 * v2[1] - Py,
+                  lz = c0 * v0[2] + c1 * v1[2] + c2 * v2[2] - Pz;
+            const float dist = sqrtf(lx * lx + ly * ly + lz * lz);
+            if (dist > 0.000001f && area > 0.0f) {
+              const float id = 1.0f / dist;
+              lx *= id;
+              ly *= id;
+              lz *= id;
+              const float cos_l = fmaxf(-(lx * lnx + ly * lny + lz * lnz), 0.0f);
+              if (cos_l > 0.0f) {
+                const float pdf = (1.0f / nf) * (1.0f / area) * (dist * dist) / cos_l;  // PdfAtoW
+                const float cos_t = fabsf(lx * nx + ly * ny + lz * nz);
+                const float k = (1.0f / 3.14159265358979f) * cos_l * cos_t / pdf;  // brdf * cosine EDF * cos / pdf
+                so = make_float4(Px, Py, Pz, 0.00001f);
+                sd = make_float4(lx, ly, lz, dist - 0.00001f);
+                sc = make_float4(k * p.albedo[0] * p.emission[0] * w.x, k * p.albedo[1] * p.emission[1] * w.y,
+                                 k * p.albedo[2] * p.emission[2] * w.z, __uint_as_float(pix));
+                shadow = true;
+              }
+            }
+          }
+          // ---- cosine-weighted continuation + Russian roulette of the NEXT bounce
+          if (bounce + 1 < p.max_bounces) {
+            w.x *= p.albedo[0];
+            w.y *= p.albedo[1];
+            w.z *= p.albedo[2];
+            bool alive = true;
+            if (bounce + 1 > 3) {
+              alive = rand_ps(pix, smp, dim + 4, p.seed) >= 0.2f;
+              const float inv = 1.0f / 0.8f;
+              w.x *= inv;
+              w.y *= inv;
+              w.z *= inv;
+            }
+            if (alive) {
+              const float sg = nz >= 0.0f ? 1.0f : -1.0f;
+              const float a = -1.0f / (sg + nz), b = nx * ny * a;
+              const float t1x = 1.0f + sg * nx * nx * a, t1y = sg * b, t1z = -sg * nx;
+              const float t2x = b, t2y = sg + ny * ny * a, t2z = -ny;
+              const float u1 = rand_ps(pix, smp, dim + 2, p.seed), u2 = rand_ps(pix, smp, dim + 3, p.seed);
+              const float r = sqrtf(u1);
+              float sn, cs;
+              sincosf(6.28318530718f * u2, &sn, &cs);
+              const float hx = r * cs, hy = r * sn, hz = sqrtf(fmaxf(0.0f, 1.0f - u1));
+              const float wx = t1x * hx + t2x * hy + nx * hz, wy = t1y * hx + t2y * hy + ny * hz,
+                          wz = t1z * hx + t2z * hy + nz * hz;
+              const float il = 1.0f / sqrtf(wx * wx + wy * wy + wz * wz);
+              co = make_float4(Px, Py, Pz, p.ray_min_t);
+              cd = make_float4(wx * il, wy * il, wz * il, p.ray_max_t);
+              q.weight[pid] = w;
+              cont = true;
+            }
+          }
+        }
+      }
+    }
+    const int lane = threadIdx.x & 31;
+    const unsigned mc = __ballot_sync(0xFFFFFFFFu, cont), ms = __ballot_sync(0xFFFFFFFFu, shadow);
+    if ((mc | ms) == 0u) return;
+    unsigned long long bc = 0, bs = 0;
+    if (lane == 0) {
+      if (mc) bc = atomicAdd(counters + 0, (unsigned long long)__popc(mc));
+      if (ms) bs = atomicAdd(counters + 1, (unsigned long long)__popc(ms));
+    }
+    bc = __shfl_sync(0xFFFFFFFFu, bc, 0);
+    bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (cont) {
+      const unsigned long long j = bc + __popc(mc & lt);
+      q.org_tmin[in ^ 1][j] = co;
+      q.dir_tmax[in ^ 1][j] = cd;
+      q.path_id[in ^ 1][j] = pid;
+    }
+    if (shadow) {
+      const unsigned long long j = bs + __popc(ms & lt);
+      q.sh_org_tmin[j] = so;
+      q.sh_dir_tmax[j] = sd;
+      q.sh_contrib_pix[j] = sc;
+    }
+  }
+};
+
+// Shadow rays: an unoccluded light sample adds its contribution (CheckForOccluder returned false)
+struct ShadowAccumulateEpilogue {
+  const float4 *contrib_pix;
+  float *accum;
+  __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
+                                             float max_t) const {
+    (void)u;
+    (void)v;
+    (void)prim;
+    if (retiring && !(t < max_t)) {
+      const float4 c = contrib_pix[ray_idx];
+      const size_t pix = __float_as_uint(c.w);
+      atomicAdd(accum + 3 * pix + 0, c.x);
+      atomicAdd(accum + 3 * pix + 1, c.y);
+      atomicAdd(accum + 3 * pix + 2, c.z);
+    }
   }
 };
 

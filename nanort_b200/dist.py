@@ -60,3 +60,23 @@ class FramebufferGather:
         for r in range(self.world):
             out[self.all_idx[r]] = self.recv[r * self.pad: r * self.pad + len(self.all_idx[r])]
         return out
+
+
+def slot_pixels(width, height, tile_w, tile_h, shard, n_shards, spp):
+    """Host mirror of csrc/wavefront.cuh:slot_to_pixel: for every primary slot of `shard` (tile-major, inside
+    a tile sample-major over 8x4 pixel blocks) the pixel index, or -1 for slots outside the image, and the
+    sample index."""
+    tiles, tiles_x = shard_tiles(width, height, tile_w, tile_h, shard, n_shards)
+    tile_pix = tile_w * tile_h
+    q = np.arange(tile_pix, dtype=np.int64)
+    bw = tile_w // 8
+    blk, inb = q // 32, q % 32
+    lx = (blk % bw) * 8 + (inb & 7)
+    ly = (blk // bw) * 4 + (inb >> 3)
+    x = (tiles % tiles_x)[:, None, None] * tile_w + lx[None, None, :]
+    y = (tiles // tiles_x)[:, None, None] * tile_h + ly[None, None, :]
+    x = np.broadcast_to(x, (len(tiles), spp, tile_pix))
+    y = np.broadcast_to(y, (len(tiles), spp, tile_pix))
+    pix = np.where((x < width) & (y < height), y * width + x, -1)
+    smp = np.broadcast_to(np.arange(spp, dtype=np.int64)[None, :, None], pix.shape)
+    return pix.reshape(-1), smp.reshape(-1)

@@ -204,6 +204,19 @@ def instanced(copies_x=10, copies_z=10):
     return np.concatenate(vs).astype(np.float32), np.concatenate(fs).astype(np.uint32)
 
 
+def with_area_light(verts, faces, center, half_x, half_z):
+    """Appends a downward-facing emissive quad (2 triangles, the LAST two faces) -- the mesh light the
+    reference path tracer samples (examples/path_tracer/main.cc:323-392).  Returns (verts, faces,
+    light_first_face, light_n_faces)."""
+    cx, cy, cz = center
+    q = np.array([(cx - half_x, cy, cz - half_z), (cx + half_x, cy, cz - half_z), (cx + half_x, cy, cz + half_z),
+                  (cx - half_x, cy, cz + half_z)], np.float32)
+    base = len(verts)
+    lf = np.array([(base, base + 1, base + 2), (base, base + 2, base + 3)], np.uint32)  # normal (0,-1,0)
+    return (np.concatenate([verts, q]).astype(np.float32), np.concatenate([faces, lf]).astype(np.uint32),
+            len(faces), 2)
+
+
 # ----------------------------------------------------------------------------- cameras
 def _normalize(v):
     v = np.asarray(v, np.float64)
