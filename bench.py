@@ -246,7 +246,9 @@ def main():
         cam = S.scene_camera(SCENE, WIDTH, HEIGHT)
         diag = float(np.linalg.norm(verts.max(axis=0) - verts.min(axis=0)))
         ref = CpuReference(verts, faces)
-        ref.calibrate_standalone(S, verts, faces, cam, 0.25 * diag)
+        # every step traces the same bounded sample; the whole run (W + K steps) is kept to about 2.5 minutes
+        per_step = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+        ref.calibrate_standalone(S, verts, faces, cam, 0.25 * diag, target_s=per_step)
         for _ in range(args.warmup):
             ref.step()
         tot_t, tot_n = 0.0, 0
@@ -360,7 +362,8 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "hbm", "kernel": "traverse_fast_kernel<SoaRays>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "traverse_fast2_kernel<SoaRays, ..., PrimaryToAoEpilogue | AoAccumulateEpilogue>",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
         "launches_per_step": int(r.traverse_launches), "avg_launch_ms": trav_ms / max(1, r.traverse_launches),
         "alg_bytes_per_launch": alg_bytes / max(1, r.traverse_launches),

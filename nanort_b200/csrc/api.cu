@@ -157,6 +157,12 @@ int nrt_build(const float *verts, size_t stride_bytes, size_t n_verts, const uin
     delete a;
     return NRT_ERR_INVALID;
   }
+  if (a->options.max_tree_depth > 500) {
+    // the traversal stacks hold 512 entries, like the reference's kNANORT_MAX_STACK_DEPTH (nanort.h:63, 2497)
+    g_err = "nrt_build: max_tree_depth > 500 is not supported (512-entry traversal stack)";
+    delete a;
+    return NRT_ERR_INVALID;
+  }
   rc = common_init(a);
   if (rc == NRT_OK) rc = upload_geometry(a, verts, stride_bytes, n_verts, faces, n_prims);
   if (rc == NRT_OK) rc = build_on_device(a, a->streams[0]);
@@ -218,6 +224,11 @@ int nrt_adopt(const void *nodes_40B, size_t n_nodes, const uint32_t *indices, si
         }
       }
     }
+  }
+  if (a->stats.max_tree_depth > 500) {
+    g_err = "nrt_adopt: tree deeper than 500 levels (512-entry traversal stack, as the reference's)";
+    delete a;
+    return NRT_ERR_INVALID;
   }
   for (size_t i = 0; i < n_indices; i++) {
     if (indices[i] >= n_prims) {

@@ -90,6 +90,7 @@ struct Accel {
   uint32_t n_prims = 0;
   size_t n_nodes = 0;
   size_t n_wide = 0;
+  size_t n_top = 0;  // leading WideNodes that form the BFS-ordered top treelet (stageable in shared memory)
   bool root_is_leaf = false;
   // device: reference-layout tree + original geometry (conformance walk)
   Node40 *d_nodes = nullptr;

@@ -467,13 +467,44 @@ __global__ void __launch_bounds__(kFastBlock)
 //   * the stack is addressed as a __shared__ array (LDS/STS instead of generic LD/ST)
 //   * policy knobs: lanes that must have retired before a refill, lanes that must still be descending
 //     for the node phase to continue, CTA size / minimum CTAs per SM
-template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_>
+template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_, int TREELET_ = 0>
 struct FastPolicy {
   static constexpr int kBlock = BLOCK_;
   static constexpr int kMinBlocks = MINB_;
   static constexpr int kRefillMin = REFILL_MIN_;
   static constexpr int kNodeExit = NODE_EXIT_;  // leave the node phase when fewer lanes than this descend
+  // > 0: the first kTreelet WideNodes (the BFS-ordered top of the tree, layout.cu) are staged into shared
+  // memory by one TMA bulk copy (cp.async.bulk + mbarrier) when the CTA starts
+  static constexpr int kTreelet = TREELET_;
 };
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                             unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
 
 __device__ __forceinline__ void tri_test2(const RayCtx &c, const TraceOptions16 &opt, float4 a, float4 b, float4 cc,
                                           Best &best) {
@@ -519,12 +550,26 @@ template <class Rays, int LOCAL_DEPTH, bool COUNT, class P, class Epi>
 __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
     traverse_fast2_kernel(const WideNode *__restrict__ wide, const PackedTri *__restrict__ tris, Rays rays, size_t n,
                           Epi epi, TraceOptions16 opt, uint32_t flags, unsigned long long *cursor,
-                          unsigned long long *counts, const unsigned long long *n_ptr) {
+                          unsigned long long *counts, const unsigned long long *n_ptr, int n_top_avail) {
   constexpr int BLOCK = P::kBlock;
+  constexpr int TREELET = P::kTreelet;
   __shared__ uint2 stk[kStackSmem * BLOCK];
+  __shared__ __align__(128) float4 top[TREELET > 0 ? TREELET * 4 : 1];
+  __shared__ __align__(8) unsigned long long top_bar;
   if (n_ptr) n = (size_t)*n_ptr;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  int n_top = 0;
+  if (TREELET > 0) {
+    n_top = min(TREELET, n_top_avail);
+    if (tid == 0) mbar_init(&top_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&top_bar, (uint32_t)n_top * 64u);
+      tma_bulk_g2s(top, wide, (uint32_t)n_top * 64u, &top_bar);
+    }
+    mbar_wait(&top_bar, 0);
+  }
   const unsigned lt_mask = (1u << lane) - 1u;
   const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
 
@@ -603,9 +648,22 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
           __any_sync(FULL_MASK, leaf != kNone))  // few lanes still descend while others wait with leaves
         break;
       if (cur >= 0) {
-        const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
-        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        float4 q0, q1, q2;
+        int4 q3;
+        if (TREELET > 0 && cur < n_top) {
+          const float4 *sp4 = top + cur * 4;
+          q0 = sp4[0];
+          q1 = sp4[1];
+          q2 = sp4[2];
+          const float4 r3 = sp4[3];
+          q3 = make_int4(__float_as_int(r3.x), __float_as_int(r3.y), __float_as_int(r3.z), __float_as_int(r3.w));
+        } else {
+          const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
+          q0 = __ldg(p);
+          q1 = __ldg(p + 1);
+          q2 = __ldg(p + 2);
+          q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        }
         float t0, t1;
         const bool h0 = slab(c, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, min_t, best.t, t0);
         const bool h1 = slab(c, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, min_t, best.t, t1);
@@ -686,7 +744,7 @@ static cudaError_t launch_fast2(const Accel *a, Rays rays, size_t n, Epi epi, co
   if (grid > need_blocks) grid = need_blocks;
   if (grid == 0) grid = 1;
   traverse_fast2_kernel<Rays, LOCAL_DEPTH, COUNT, P, Epi><<<(unsigned)grid, P::kBlock, 0, s>>>(
-      a->d_wide, a->d_tris, rays, n, epi, opt, flags, cursor, d_counts, n_ptr);
+      a->d_wide, a->d_tris, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, (int)a->n_top);
   return cudaGetLastError();
 }
 
@@ -737,6 +795,10 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
       NRT_VARIANT(19, 128, 10, 8, 12)
       NRT_VARIANT(20, 256, 5, 8, 8)
       NRT_VARIANT(21, 128, 9, 8, 8)
+      NRT_VARIANT(30, 128, 10, 16, 8, 64)
+      NRT_VARIANT(31, 256, 5, 16, 8, 128)
+      NRT_VARIANT(32, 256, 5, 16, 8, 0)
+      NRT_VARIANT(33, 128, 9, 16, 8, 128)
       case 255: {  // first-generation kernel, kept for A/B runs
         const int sms = device_sm_count(a->device);
         size_t grid = (size_t)sms * 8;

@@ -54,5 +54,4 @@ def test_product_never_imports_the_oracle():
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
-                assert "oracle" not in txt.replace("oracle/", "").replace("oracle.", "") or True
                 assert "import oracle" not in txt and "from oracle" not in txt and "liborc" not in txt, fn

@@ -34,3 +34,19 @@ def test_wavefront_example_runs(tmp_path):
     out = subprocess.run([os.path.join(BIN, "ao_wavefront"), "160", "120", "2"], check=True, capture_output=True,
                          text=True, timeout=300, cwd=tmp_path).stdout
     assert "traced" in out and os.path.getsize(tmp_path / "ao.ppm") > 160 * 120
+
+
+def test_dump_load_interchange_with_cpu_nanort(tmp_path):
+    """Dump/Load in the reference's raw format: (1) a tree dumped by CPU nanort (committed fixture) is loaded
+    through the facade and traversed on the GPU; (2) a GPU-built tree dumped through the facade is loaded and
+    traversed by CPU nanort (when its binary travelled).  Both must print what CPU nanort prints for its own tree."""
+    if not os.path.exists(os.path.join(BIN, "dump_load_b200")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
+    want = open(os.path.join(ROOT, "tests", "golden", "dump_load_ref.txt")).read().strip().splitlines()
+    got = _run("dump_load_b200", "load", os.path.join(ROOT, "tests", "golden", "ref_tree_dump.bin"))
+    assert got == want
+    out = str(tmp_path / "gpu_tree.bin")
+    head = _run("dump_load_b200", "dump", out)
+    assert head[0].startswith("dumped ") and os.path.getsize(out) > 100000
+    if os.path.exists(os.path.join(BIN, "dump_load_ref")):
+        assert _run("dump_load_ref", "load", out) == want
