@@ -166,14 +166,14 @@ struct AosRays {
   __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy,
                                        float &dz, float &tmin, float &tmax) const {
     const float *p = reinterpret_cast<const float *>(rays + i);
-    ox = __ldg(p + 0);
-    oy = __ldg(p + 1);
-    oz = __ldg(p + 2);
-    dx = __ldg(p + 3);
-    dy = __ldg(p + 4);
-    dz = __ldg(p + 5);
-    tmin = __ldg(p + 6);
-    tmax = __ldg(p + 7);
+    ox = __ldcs(p + 0);
+    oy = __ldcs(p + 1);
+    oz = __ldcs(p + 2);
+    dx = __ldcs(p + 3);
+    dy = __ldcs(p + 4);
+    dz = __ldcs(p + 5);
+    tmin = __ldcs(p + 6);
+    tmax = __ldcs(p + 7);
   }
 };
 
@@ -182,8 +182,8 @@ struct SoaRays {
   const float4 *dir_tmax;
   __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy,
                                        float &dz, float &tmin, float &tmax) const {
-    float4 o = __ldg(org_tmin + i);
-    float4 d = __ldg(dir_tmax + i);
+    float4 o = __ldcs(org_tmin + i);  // read once: evict-first, keep L1/L2 for the tree
+    float4 d = __ldcs(dir_tmax + i);
     ox = o.x;
     oy = o.y;
     oz = o.z;
@@ -467,8 +467,9 @@ __global__ void __launch_bounds__(kFastBlock)
 //   * the stack is addressed as a __shared__ array (LDS/STS instead of generic LD/ST)
 //   * policy knobs: lanes that must have retired before a refill, lanes that must still be descending
 //     for the node phase to continue, CTA size / minimum CTAs per SM
-template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_, int TREELET_ = 0>
+template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_, int TREELET_ = 0, int STACK_SMEM_ = 16>
 struct FastPolicy {
+  static constexpr int kStackEntries = STACK_SMEM_;  // stack entries per lane kept in shared memory (<= 16)
   static constexpr int kBlock = BLOCK_;
   static constexpr int kMinBlocks = MINB_;
   static constexpr int kRefillMin = REFILL_MIN_;
@@ -553,7 +554,8 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
                           unsigned long long *counts, const unsigned long long *n_ptr, int n_top_avail) {
   constexpr int BLOCK = P::kBlock;
   constexpr int TREELET = P::kTreelet;
-  __shared__ uint2 stk[kStackSmem * BLOCK];
+  constexpr int SSM = P::kStackEntries;  // the local part grows by what shared memory gives up
+  __shared__ uint2 stk[(SSM > 0 ? SSM : 1) * BLOCK];
   __shared__ __align__(128) float4 top[TREELET > 0 ? TREELET * 4 : 1];
   __shared__ __align__(8) unsigned long long top_bar;
   if (n_ptr) n = (size_t)*n_ptr;
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
   const unsigned lt_mask = (1u << lane) - 1u;
   const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
 
-  uint2 lstk[LOCAL_DEPTH];
+  uint2 lstk[LOCAL_DEPTH + (kStackSmem - SSM)];
   int sp = 0;
   RayCtx c;
   Best best;
@@ -585,10 +587,10 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
 
   auto push = [&](int ref, float t) {
     const uint2 e = make_uint2((uint32_t)ref, __float_as_uint(t));
-    if (sp < kStackSmem)
+    if (sp < SSM)
       stk[sp * BLOCK + tid] = e;
-    else if (sp - kStackSmem < LOCAL_DEPTH)
-      lstk[sp - kStackSmem] = e;
+    else if (sp - SSM < LOCAL_DEPTH + (kStackSmem - SSM))
+      lstk[sp - SSM] = e;
     sp++;
   };
   // next stack entry that does not start behind the current best, or kNone
@@ -596,10 +598,10 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
     while (sp > 0) {
       --sp;
       uint2 e;
-      if (sp < kStackSmem)
+      if (sp < SSM)
         e = stk[sp * BLOCK + tid];
-      else if (sp - kStackSmem < LOCAL_DEPTH)
-        e = lstk[sp - kStackSmem];
+      else if (sp - SSM < LOCAL_DEPTH + (kStackSmem - SSM))
+        e = lstk[sp - SSM];
       else
         continue;
       if (__uint_as_float(e.y) <= best.t) return (int)e.x;
@@ -748,8 +750,11 @@ static cudaError_t launch_fast2(const Accel *a, Rays rays, size_t n, Epi epi, co
   return cudaGetLastError();
 }
 
-// Default policy (chosen from the sweep in profiles/r01_variant_sweep.md)
-typedef FastPolicy<128, 10, 16, 8> DefaultPolicy;
+// Default policy (chosen from the sweeps in profiles/r01_variant_sweep.md): 128-thread CTAs, 10 per SM (48
+// registers), refill when 16 lanes retired, node phase ends below 8 descending lanes, no TMA treelet, and the
+// whole per-lane stack in thread-local memory (L1-backed) -- the shared-memory short stack measured 2-3 % slower
+// because its carve-out takes L1 capacity away from the tree.
+typedef FastPolicy<128, 10, 16, 8, 0, 0> DefaultPolicy;
 
 template <class Rays, bool COUNT>
 static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
@@ -799,6 +804,10 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
       NRT_VARIANT(31, 256, 5, 16, 8, 128)
       NRT_VARIANT(32, 256, 5, 16, 8, 0)
       NRT_VARIANT(33, 128, 9, 16, 8, 128)
+      NRT_VARIANT(40, 128, 10, 16, 8, 0, 8)
+      NRT_VARIANT(41, 128, 10, 16, 8, 0, 0)
+      NRT_VARIANT(42, 128, 10, 16, 8, 0, 4)
+      NRT_VARIANT(43, 128, 12, 16, 8, 0, 8)
       case 255: {  // first-generation kernel, kept for A/B runs
         const int sms = device_sm_count(a->device);
         size_t grid = (size_t)sms * 8;

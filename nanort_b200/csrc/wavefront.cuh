@@ -125,7 +125,7 @@ struct StoreHitsEpilogue {
     if (retiring && hits) {
       const bool hit = t < max_t;  // a hit exactly at max_t is a miss (nanort.h:2552)
       float4 r = hit ? make_float4(u, v, t, __uint_as_float(prim)) : make_float4(0.0f, 0.0f, max_t, __uint_as_float(0xFFFFFFFFu));
-      reinterpret_cast<float4 *>(hits)[ray_idx] = r;
+      __stcs(reinterpret_cast<float4 *>(hits) + ray_idx, r);  // written once, never re-read by this kernel
       if (mask) mask[ray_idx] = hit ? 1 : 0;
     }
   }
