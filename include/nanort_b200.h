@@ -164,14 +164,16 @@ int nrt_ao_workload_device(const nrt_accel *a, const nrt_ao_params *p, float *d_
 
 /*
  * Device-resident wavefront form of the reference path tracer's pixel -> sample -> bounce loop
- * (examples/path_tracer/main.cc:804-991), diffuse + emissive materials only:
+ * (examples/path_tracer/main.cc:804-991) with its material model (tinyobj materials: diffuse, specular,
+ * transmittance, emission, ior, dissolve; main.cc:884-973):
  *   camera ray :809-817, Russian roulette after bounce 3 with p = 0.2 :828-837, radiance Traverse :839-854,
- *   geometric normal flipped to the viewer :878-881, EMIT lobe (only when the previous event did no light
- *   sampling) :958-966, diffuse lobe with next-event estimation: MeshLight::sampleDirect :337-392 + the
- *   CheckForOccluder shadow Traverse :675-701, cosine-weighted continuation :216-250, at most max_bounces.
+ *   interpolated face-varying normal :862-875 (geometric normal when none is given) flipped to the viewer
+ *   :878-881, Schlick Fresnel :894-900, lobe probabilities rhoS/rhoD/rhoR/rhoE :902-929, glossy reflection
+ *   :931-935, diffuse lobe with next-event estimation (MeshLight::sampleDirect :337-392 + the CheckForOccluder
+ *   shadow Traverse :675-701) and cosine-weighted continuation :937-957 / :216-250, refraction :958-962,
+ *   emission (only when the previous event did no light sampling) :963-971, at most max_bounces.
  * Every bounce is two traversal launches (radiance rays, shadow rays) whose retire steps do the shading.
- * Faces [light_first_face, light_first_face + light_n_faces) of the mesh are the emitters (radiance
- * `emission`, cosine EDF); every other face is Lambertian with reflectance `albedo`.
+ * All pointers are DEVICE pointers.
  */
 typedef struct nrt_path_params {
   float cam[12];
@@ -180,10 +182,14 @@ typedef struct nrt_path_params {
   uint32_t tile_w, tile_h, shard, n_shards;
   uint32_t max_bounces;   /* uMaxBounces, main.cc:33 (10) */
   float ray_min_t, ray_max_t; /* 1e-3, 1e30 (main.cc:840-842) */
-  float albedo[3];
-  float emission[3];
-  uint32_t light_first_face, light_n_faces;
+  uint32_t n_materials, n_emissive;
+  const void *d_materials;            /* n_materials x 16 floats: diffuse[3] specular[3] transmittance[3] emission[3]
+                                         ior dissolve pad pad */
+  const void *d_material_ids;         /* uint32 per face, or NULL = material 0 everywhere (Mesh::material_ids) */
+  const void *d_emissive_faces;       /* uint32[n_emissive]: faces whose material emits (MeshLight, main.cc:323-335) */
+  const void *d_facevarying_normals;  /* float[9 * n_faces] or NULL (Mesh::facevarying_normals) */
   uint32_t flags;         /* NRT_TRAVERSE_* */
+  uint32_t pad;
 } nrt_path_params;
 
 typedef struct nrt_path_result {

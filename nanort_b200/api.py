@@ -84,9 +84,10 @@ class PathParams(C.Structure):
         ("tile_w", C.c_uint32), ("tile_h", C.c_uint32), ("shard", C.c_uint32), ("n_shards", C.c_uint32),
         ("max_bounces", C.c_uint32),
         ("ray_min_t", C.c_float), ("ray_max_t", C.c_float),
-        ("albedo", C.c_float * 3), ("emission", C.c_float * 3),
-        ("light_first_face", C.c_uint32), ("light_n_faces", C.c_uint32),
-        ("flags", C.c_uint32),
+        ("n_materials", C.c_uint32), ("n_emissive", C.c_uint32),
+        ("d_materials", C.c_void_p), ("d_material_ids", C.c_void_p), ("d_emissive_faces", C.c_void_p),
+        ("d_facevarying_normals", C.c_void_p),
+        ("flags", C.c_uint32), ("pad", C.c_uint32),
     ]
 
 

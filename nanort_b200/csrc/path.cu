@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256)
   if (i < count) {
     uint32_t pix, smp;
     q.path_id[0][i] = i;
-    q.weight[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    q.weight[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);  // weight 1, do_emission = true (main.cc:820-824)
     if (!slot_to_pixel(tile_map(p), slot0 + i, pix, smp)) {
       q.org_tmin[0][i] = make_float4(0.f, 0.f, 0.f, 0.f);
       q.dir_tmax[0][i] = make_float4(0.f, 0.f, -1.f, -1.f);  // retires at the root as a miss
@@ -84,8 +84,8 @@ extern "C" int nrt_render_path_device(const nrt_accel *h, const nrt_path_params 
   Accel *a = const_cast<Accel *>(reinterpret_cast<const Accel *>(h));
   const nrt_path_params p = *pp;
   if (p.width == 0 || p.height == 0 || p.spp == 0 || p.n_shards == 0 || p.shard >= p.n_shards || p.tile_w == 0 ||
-      p.tile_h == 0 || (p.tile_w % 8) != 0 || (p.tile_h % 4) != 0 || p.max_bounces == 0 ||
-      (uint64_t)p.light_first_face + p.light_n_faces > a->n_prims) {
+      p.tile_h == 0 || (p.tile_w % 8) != 0 || (p.tile_h % 4) != 0 || p.max_bounces == 0 || p.n_materials == 0 ||
+      !p.d_materials || (p.n_emissive > 0 && !p.d_emissive_faces)) {
     set_error("nrt_render_path_device: bad parameters");
     return NRT_ERR_INVALID;
   }

@@ -32,17 +32,11 @@ __global__ void __launch_bounds__(256)
     } else {
       valid = true;
       smp += p.sample0;
-      const float jx = rand_ps(pix, smp, 0, p.seed), jy = rand_ps(pix, smp, 1, p.seed);
-      const float px = (float)(pix % p.width), py = (float)(pix / p.width);
-      const float sx = (px + jx) / (float)p.width - 0.5f;
-      const float sy = 0.5f - (py + jy) / (float)p.height;
-      float dx = p.cam[3] * sx + p.cam[6] * sy + p.cam[9];
-      float dy = p.cam[4] * sx + p.cam[7] * sy + p.cam[10];
-      float dz = p.cam[5] * sx + p.cam[8] * sy + p.cam[11];
-      const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+      float dx, dy, dz;
+      camera_ray(p.cam, p.width, p.height, p.seed, pix, smp, dx, dy, dz);
       w.pix[i] = pix;
       w.org_tmin[i] = make_float4(p.cam[0], p.cam[1], p.cam[2], p.ray_min_t);
-      w.dir_tmax[i] = make_float4(dx * inv, dy * inv, dz * inv, p.ray_max_t);
+      w.dir_tmax[i] = make_float4(dx, dy, dz, p.ray_max_t);
     }
   }
   const unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
@@ -139,6 +133,9 @@ int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const
 int launch_traverse_primary_fused(const Accel *a, const Wave &w, const nrt_ao_params &p, unsigned long long slot0,
                                   size_t count, float *d_accum, unsigned long long *d_wave_counters,
                                   const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
+int launch_traverse_camera_fused(const Accel *a, const Wave &w, const nrt_ao_params &p, unsigned long long slot0,
+                                 size_t count, float *d_accum, unsigned long long *d_wave_counters,
+                                 const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
 int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long long *d_count, size_t capacity,
                              float *d_accum, unsigned long long *d_totals, const TraceOptions16 &opt, uint32_t flags,
                              cudaStream_t s);
@@ -146,6 +143,23 @@ int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long 
 }  // namespace nrt
 
 using namespace nrt;
+
+// number of slots in [s0, s0 + count) that map to pixels inside the image (whole tiles per wave)
+static unsigned long long valid_slots(const nrt_ao_params &p, unsigned long long s0, uint32_t count) {
+  const unsigned long long per_tile = (unsigned long long)p.tile_w * p.tile_h * p.spp;
+  const uint32_t tiles_x = (p.width + p.tile_w - 1) / p.tile_w;
+  unsigned long long total = 0;
+  for (unsigned long long k = s0 / per_tile; k < (s0 + count) / per_tile; k++) {
+    const unsigned long long tile = k * p.n_shards + p.shard;
+    const uint32_t tx = (uint32_t)(tile % tiles_x), ty = (uint32_t)(tile / tiles_x);
+    const uint32_t x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+    if (x0 >= p.width || y0 >= p.height) continue;
+    const uint32_t wv = p.width - x0 < p.tile_w ? p.width - x0 : p.tile_w;
+    const uint32_t hv = p.height - y0 < p.tile_h ? p.height - y0 : p.tile_h;
+    total += (unsigned long long)wv * hv * p.spp;
+  }
+  return total;
+}
 
 // dump_primary / dump_ao (optional, device): AoS copies of the two ray queues, primary rays at their slot
 // index, AO rays appended in queue order; *n_ao_out receives the AO count (forces a sync per wave).
@@ -216,7 +230,7 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
     NRT_CUDA(cudaEventRecord(e_begin, s));
   }
   uint32_t launches = 0, trav_launches = 0;
-  unsigned long long dumped_ao = 0;
+  unsigned long long dumped_ao = 0, valid_primaries_host = 0;
   const bool fused = !dump_primary && !dump_ao && !(p.flags & NRT_AO_UNFUSED);
   const uint32_t trav_flags = p.flags & 0xFFFFu;
   int rc = NRT_OK;
@@ -224,8 +238,10 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
     const uint32_t count = (uint32_t)std::min<unsigned long long>(cap, total_slots - s0);
     const uint32_t grid = (count + 255) / 256;
     cudaMemsetAsync(wave_ctr, 0, 2 * sizeof(unsigned long long), s);
-    gen_primary_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, wave_ctr);
-    launches++;
+    if (!fused) {
+      gen_primary_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, wave_ctr);
+      launches++;
+    }
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
     if (res) {
       cudaEventCreate(&t0);
@@ -238,9 +254,10 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
       ev.push_back(t3);
     }
     if (fused) {
-      // 3 launches per wave: the traversal kernels' retire steps spawn the AO rays and accumulate visibility
+      // two traversal launches per wave and nothing else: camera rays are generated at ray fetch, the retire
+      // steps spawn the AO rays and accumulate visibility
       if (res) cudaEventRecord(t0, s);
-      rc = launch_traverse_primary_fused(a, w, p, s0, count, d_accum, wave_ctr, opt, trav_flags, s);
+      rc = launch_traverse_camera_fused(a, w, p, s0, count, d_accum, wave_ctr, opt, trav_flags, s);
       if (rc != NRT_OK) break;
       if (res) {
         cudaEventRecord(t1, s);
@@ -252,6 +269,7 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
       fold_wave_counters_kernel<<<1, 1, 0, s>>>(wave_ctr, totals);
       launches += 3;
       trav_launches += 2;
+      valid_primaries_host += valid_slots(p, s0, count);
     } else {
       if (dump_primary) {
         soa_to_aos_kernel<<<grid, 256, 0, s>>>(w.org_tmin, w.dir_tmax, nullptr, count, dump_primary + s0, 1u);
@@ -294,7 +312,7 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
     } else {
       res->ao_rays = ht[0];
       res->ao_hits = ht[1];
-      res->primary_rays = ht[2];
+      res->primary_rays = ht[2] + valid_primaries_host;
       float tms = 0.0f, total = 0.0f;
       for (size_t i = 0; i + 3 < ev.size(); i += 4) {
         float m1 = 0, m2 = 0;

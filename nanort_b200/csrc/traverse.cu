@@ -869,8 +869,8 @@ int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const
 }
 
 // Fused wavefront launches (render.cu): the retire step spawns the AO ray / accumulates visibility.
-template <class Epi, class P = DefaultPolicy>
-static int launch_fused(const Accel *a, SoaRays rays, size_t n, const unsigned long long *n_ptr, Epi epi,
+template <class Epi, class P = DefaultPolicy, class Rays = SoaRays>
+static int launch_fused(const Accel *a, Rays rays, size_t n, const unsigned long long *n_ptr, Epi epi,
                         const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   if (n == 0) return NRT_OK;
   unsigned long long *cursor =
@@ -879,9 +879,9 @@ static int launch_fused(const Accel *a, SoaRays rays, size_t n, const unsigned l
   const bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
   cudaError_t e;
   if (deep)
-    e = launch_fast2<SoaRays, 512 - kStackSmem, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
+    e = launch_fast2<Rays, 512 - kStackSmem, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
   else
-    e = launch_fast2<SoaRays, 48, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
+    e = launch_fast2<Rays, 48, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
   NRT_CUDA(e);
   return NRT_OK;
 }
@@ -889,8 +889,17 @@ static int launch_fused(const Accel *a, SoaRays rays, size_t n, const unsigned l
 int launch_traverse_primary_fused(const Accel *a, const Wave &w, const nrt_ao_params &p, unsigned long long slot0,
                                   size_t count, float *d_accum, unsigned long long *d_wave_counters,
                                   const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
-  PrimaryToAoEpilogue epi{p, slot0, w, a->d_verts, a->d_faces, d_accum, d_wave_counters};
+  PrimaryToAoEpilogue<false> epi{p, slot0, w, a->d_verts, a->d_faces, d_accum, d_wave_counters};
   return launch_fused(a, SoaRays{w.org_tmin, w.dir_tmax}, count, nullptr, epi, opt, flags, s);
+}
+
+// Same, with the camera rays generated inside the kernel (no generator kernel, no primary queue)
+int launch_traverse_camera_fused(const Accel *a, const Wave &w, const nrt_ao_params &p, unsigned long long slot0,
+                                 size_t count, float *d_accum, unsigned long long *d_wave_counters,
+                                 const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  PrimaryToAoEpilogue<true> epi{p, slot0, w, a->d_verts, a->d_faces, d_accum, d_wave_counters};
+  return launch_fused<PrimaryToAoEpilogue<true>, DefaultPolicy, CameraRays>(a, CameraRays{p, slot0}, count, nullptr, epi,
+                                                                            opt, flags, s);
 }
 
 int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long long *d_count, size_t capacity,
@@ -903,7 +912,7 @@ int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long 
 int launch_traverse_path_radiance(const Accel *a, const PathShadeEpilogue &epi, const unsigned long long *d_count,
                                   size_t capacity, const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   // the shading block needs more registers than the plain traversal: 8 CTAs/SM (64 registers) instead of 10
-  return launch_fused<PathShadeEpilogue, FastPolicy<128, 8, 16, 8> >(
+  return launch_fused<PathShadeEpilogue, FastPolicy<128, 8, 16, 8, 0, 0> >(
       a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]}, capacity, d_count, epi, opt, flags, s);
 }
 

@@ -79,6 +79,49 @@ __device__ __forceinline__ uint32_t slot_sample(const nrt_ao_params &p, unsigned
   return p.sample0 + (uint32_t)((slot % ((unsigned long long)tile_pix * p.spp)) / tile_pix);
 }
 
+// Jittered pinhole camera ray of (pixel, sample) -- examples/path_tracer/main.cc:809-817.  One definition for the
+// stand-alone generator kernel, the in-kernel generator (CameraRays) and the AO epilogue, so that all of them
+// produce bit-identical rays.
+__device__ __forceinline__ void camera_ray(const float *cam, uint32_t width, uint32_t height, uint32_t seed,
+                                           uint32_t pix, uint32_t smp, float &dx, float &dy, float &dz) {
+  const float jx = rand_ps(pix, smp, 0, seed), jy = rand_ps(pix, smp, 1, seed);
+  const float px = (float)(pix % width), py = (float)(pix / width);
+  const float sx = (px + jx) / (float)width - 0.5f;
+  const float sy = 0.5f - (py + jy) / (float)height;
+  dx = cam[3] * sx + cam[6] * sy + cam[9];
+  dy = cam[4] * sx + cam[7] * sy + cam[10];
+  dz = cam[5] * sx + cam[8] * sy + cam[11];
+  const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+  dx *= inv;
+  dy *= inv;
+  dz *= inv;
+}
+
+// Ray "loader" that generates the camera ray of slot (slot0 + i) instead of reading a queue: the primary
+// traversal then needs no generator kernel and no primary ray queue at all.
+struct CameraRays {
+  nrt_ao_params p;
+  unsigned long long slot0;
+  __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy, float &dz,
+                                       float &tmin, float &tmax) const {
+    uint32_t pix, smp;
+    ox = p.cam[0];
+    oy = p.cam[1];
+    oz = p.cam[2];
+    if (slot_to_pixel(p, slot0 + i, pix, smp)) {
+      camera_ray(p.cam, p.width, p.height, p.seed, pix, smp + p.sample0, dx, dy, dz);
+      tmin = p.ray_min_t;
+      tmax = p.ray_max_t;
+    } else {  // slot outside the image: retires at the root as a miss
+      dx = 0.0f;
+      dy = 0.0f;
+      dz = -1.0f;
+      tmin = 0.0f;
+      tmax = -1.0f;
+    }
+  }
+};
+
 // One cosine-hemisphere AO ray from a primary hit.
 __device__ __forceinline__ void make_ao_ray(const nrt_ao_params &p, uint32_t pix, uint32_t smp, float4 o, float4 d,
                                             float t, uint32_t prim, const float *__restrict__ verts,
@@ -131,7 +174,9 @@ struct StoreHitsEpilogue {
   }
 };
 
-// primary rays: a hit spawns its AO ray straight into the compacted AO queue, a miss adds 1 to its pixel
+// primary rays: a hit spawns its AO ray straight into the compacted AO queue, a miss adds 1 to its pixel.
+// GEN: the primary rays were generated in the kernel (CameraRays) -- pixel and ray are recomputed from the slot.
+template <bool GEN>
 struct PrimaryToAoEpilogue {
   nrt_ao_params p;
   unsigned long long slot0;
@@ -148,11 +193,29 @@ struct PrimaryToAoEpilogue {
     float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4;
     uint32_t pix = 0xFFFFFFFFu;
     if (retiring) {
-      pix = w.pix[ray_idx];
+      uint32_t smp = 0;
+      float4 ro, rd;
+      if (GEN) {
+        if (slot_to_pixel(p, slot0 + ray_idx, pix, smp)) {
+          smp += p.sample0;
+          float dx, dy, dz;
+          camera_ray(p.cam, p.width, p.height, p.seed, pix, smp, dx, dy, dz);
+          ro = make_float4(p.cam[0], p.cam[1], p.cam[2], p.ray_min_t);
+          rd = make_float4(dx, dy, dz, p.ray_max_t);
+        } else {
+          pix = 0xFFFFFFFFu;
+        }
+      } else {
+        pix = w.pix[ray_idx];
+        if (pix != 0xFFFFFFFFu) {
+          smp = slot_sample(p, slot0 + ray_idx);
+          ro = w.org_tmin[ray_idx];
+          rd = w.dir_tmax[ray_idx];
+        }
+      }
       if (pix != 0xFFFFFFFFu) {
         if (t < max_t) {
-          make_ao_ray(p, pix, slot_sample(p, slot0 + ray_idx), w.org_tmin[ray_idx], w.dir_tmax[ray_idx], t, prim,
-                      verts, faces, o4, d4);
+          make_ao_ray(p, pix, smp, ro, rd, t, prim, verts, faces, o4, d4);
           make = true;
         } else {
           atomicAdd(accum + pix, 1.0f);
@@ -220,7 +283,19 @@ __device__ __forceinline__ void geometric_normal(const float *__restrict__ verts
   nz *= il;
 }
 
-// Radiance rays of bounce `bounce`: the retire step is the reference's per-hit shading block.
+// 16 floats per material, the tinyobj fields the reference reads (main.cc:884-892)
+struct PathMaterial {
+  float diffuse[3];
+  float specular[3];
+  float transmittance[3];
+  float emission[3];
+  float ior;
+  float dissolve;
+  float pad[2];
+};
+
+// Radiance rays of bounce `bounce`: the retire step is the reference's per-hit shading block
+// (examples/path_tracer/main.cc:856-976): normal, material, Fresnel, lobe probabilities, lobe choice.
 struct PathShadeEpilogue {
   nrt_path_params p;
   unsigned long long slot0;
@@ -233,8 +308,6 @@ struct PathShadeEpilogue {
   unsigned long long *counters;  // [0] continuation rays, [1] shadow rays of this bounce
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
                                              float max_t) const {
-    (void)u;
-    (void)v;
     bool cont = false, shadow = false;
     float4 co = make_float4(0, 0, 0, 0), cd = co, so = co, sd = co, sc = co;
     uint32_t pid = 0;
@@ -244,66 +317,151 @@ struct PathShadeEpilogue {
       if (slot_to_pixel(tile_map(p), slot0 + pid, pix, smp)) {
         smp += p.sample0;
         const float4 o = q.org_tmin[in][ray_idx], d = q.dir_tmax[in][ray_idx];
-        float4 w = q.weight[pid];
+        float4 w = q.weight[pid];  // throughput rgb, w.w = do_emission (no light sampling at the previous event)
+        const PathMaterial *mats = reinterpret_cast<const PathMaterial *>(p.d_materials);
+        const uint32_t *mat_ids = reinterpret_cast<const uint32_t *>(p.d_material_ids);
+        const uint32_t *emissive = reinterpret_cast<const uint32_t *>(p.d_emissive_faces);
+        const float *fv_normals = reinterpret_cast<const float *>(p.d_facevarying_normals);
+        // ---- normal: interpolated face-varying normals when given (main.cc:862-875), else geometric
         float nx, ny, nz, a2;
-        geometric_normal(verts, faces, prim, nx, ny, nz, a2);
-        const float ndotd = nx * d.x + ny * d.y + nz * d.z;
-        if (prim - p.light_first_face < p.light_n_faces) {
-          // EMIT lobe: only when the previous event did no light sampling, i.e. for camera rays
-          if (bounce == 0) {
-            const float c = fmaxf(-ndotd, 0.0f);
-            atomicAdd(accum + 3 * (size_t)pix + 0, c * p.emission[0] * w.x);
-            atomicAdd(accum + 3 * (size_t)pix + 1, c * p.emission[1] * w.y);
-            atomicAdd(accum + 3 * (size_t)pix + 2, c * p.emission[2] * w.z);
+        if (fv_normals) {
+          const float *n0 = fv_normals + 9 * (size_t)prim;
+          const float b0 = 1.0f - u - v;
+          nx = b0 * n0[0] + u * n0[3] + v * n0[6];
+          ny = b0 * n0[1] + u * n0[4] + v * n0[7];
+          nz = b0 * n0[2] + u * n0[5] + v * n0[8];
+          const float l = sqrtf(nx * nx + ny * ny + nz * nz);
+          if (fabsf(l) > 1.0e-6f) {
+            const float il = 1.0f / l;
+            nx *= il;
+            ny *= il;
+            nz *= il;
           }
         } else {
-          const float Px = o.x + d.x * t, Py = o.y + d.y * t, Pz = o.z + d.z * t;
-          if (ndotd > 0.0f) {
-            nx = -nx;
-            ny = -ny;
-            nz = -nz;
-          }
+          geometric_normal(verts, faces, prim, nx, ny, nz, a2);
+        }
+        const float onx = nx, ony = ny, onz = nz;  // originalNorm
+        const float ndotd = nx * d.x + ny * d.y + nz * d.z;
+        if (ndotd > 0.0f) {  // flip towards the incoming ray (main.cc:878-881)
+          nx = -nx;
+          ny = -ny;
+          nz = -nz;
+        }
+        const PathMaterial m = mats[mat_ids ? mat_ids[prim] : 0u];
+        // ---- Fresnel and lobe probabilities (main.cc:894-929)
+        const float inside = ndotd < 0.0f ? -1.0f : 1.0f;  // sign(dot(rayDir, originalNorm))
+        const float n1 = inside < 0.0f ? 1.0f / m.ior : m.ior;
+        const float n2 = 1.0f / n1;
+        const float r0s = (n1 - n2) / (n1 + n2);
+        const float r0 = r0s * r0s;
+        const float hdn = 1.0f - (-(d.x * nx + d.y * ny + d.z * nz));
+        const float fresnel = r0 + (1.0f - r0) * (hdn * hdn * hdn * hdn * hdn);
+        const float third = 1.0f / 3.0f;
+        float rhoS = (third * m.specular[0] + third * m.specular[1] + third * m.specular[2]) * fresnel;
+        float rhoD = (third * m.diffuse[0] + third * m.diffuse[1] + third * m.diffuse[2]) * (1.0f - fresnel) *
+                     (1.0f - m.dissolve);
+        float rhoR = (third * m.transmittance[0] + third * m.transmittance[1] + third * m.transmittance[2]) *
+                     (1.0f - fresnel) * m.dissolve;
+        float rhoE = third * m.emission[0] + third * m.emission[1] + third * m.emission[2];
+        const float total = rhoS + rhoD + rhoR + rhoE;
+        if (!(total < 0.0001f)) {
+          rhoS /= total;
+          rhoD /= total;
+          rhoR /= total;
           const uint32_t dim = 8u + 8u * bounce;
-          // ---- next-event estimation (MeshLight::sampleDirect)
-          if (p.light_n_faces > 0) {
-            float xi1 = rand_ps(pix, smp, dim + 0, p.seed);
-            const float xi2 = rand_ps(pix, smp, dim + 1, p.seed);
-            const float nf = (float)p.light_n_faces;
-            uint32_t face = min((uint32_t)floorf(xi1 * nf), p.light_n_faces - 1u);
-            xi1 = xi1 * nf - (float)face;
-            const uint32_t fid = p.light_first_face + face;
-            const uint32_t f0 = faces[3 * (size_t)fid], f1 = faces[3 * (size_t)fid + 1], f2 = faces[3 * (size_t)fid + 2];
-            const float *v0 = verts + 3 * (size_t)f0, *v1 = verts + 3 * (size_t)f1, *v2 = verts + 3 * (size_t)f2;
-            const float s1 = sqrtf(xi1), c0 = 1.0f - s1, c1 = s1 * (1.0f - xi2), c2 = s1 * xi2;
-            float lnx, lny, lnz, la2;
-            geometric_normal(verts, faces, fid, lnx, lny, lnz, la2);
-            const float area = 0.5f * la2;
-            float lx = c0 * v0[0] + c1 * v1[0] + c2 * v2[0] - Px, ly = c0 * v0[1] + c1 * v1[1] + c2 * v2[1] - Py,
-                  lz = c0 * v0[2] + c1 * v1[2] + c2 * v2[2] - Pz;
-            const float dist = sqrtf(lx * lx + ly * ly + lz * lz);
-            if (dist > 0.000001f && area > 0.0f) {
-              const float id = 1.0f / dist;
-              lx *= id;
-              ly *= id;
-              lz *= id;
-              const float cos_l = fmaxf(-(lx * lnx + ly * lny + lz * lnz), 0.0f);
-              if (cos_l > 0.0f) {
-                const float pdf = (1.0f / nf) * (1.0f / area) * (dist * dist) / cos_l;  // PdfAtoW
-                const float cos_t = fabsf(lx * nx + ly * ny + lz * nz);
-                const float k = (1.0f / 3.14159265358979f) * cos_l * cos_t / pdf;  // brdf * cosine EDF * cos / pdf
-                so = make_float4(Px, Py, Pz, 0.00001f);
-                sd = make_float4(lx, ly, lz, dist - 0.00001f);
-                sc = make_float4(k * p.albedo[0] * p.emission[0] * w.x, k * p.albedo[1] * p.emission[1] * w.y,
-                                 k * p.albedo[2] * p.emission[2] * w.z, __uint_as_float(pix));
-                shadow = true;
+          const float pick = rand_ps(pix, smp, dim + 5, p.seed);
+          const float Px = o.x + d.x * t, Py = o.y + d.y * t, Pz = o.z + d.z * t;
+          float ox = 0.f, oy = 0.f, oz = 0.f;  // outDir
+          bool scatter = true;
+          if (pick < rhoS) {  // glossy reflection
+            const float k = 2.0f * (d.x * nx + d.y * ny + d.z * nz);
+            ox = d.x - k * nx;
+            oy = d.y - k * ny;
+            oz = d.z - k * nz;
+            w.x *= m.specular[0];
+            w.y *= m.specular[1];
+            w.z *= m.specular[2];
+            w.w = 1.0f;
+          } else if (pick < rhoS + rhoD) {  // diffuse + next-event estimation
+            if (p.n_emissive > 0) {  // MeshLight::sampleDirect (main.cc:337-392)
+              float xi1 = rand_ps(pix, smp, dim + 0, p.seed);
+              const float xi2 = rand_ps(pix, smp, dim + 1, p.seed);
+              const float nf = (float)p.n_emissive;
+              const uint32_t face = min((uint32_t)floorf(xi1 * nf), p.n_emissive - 1u);
+              xi1 = xi1 * nf - (float)face;
+              const uint32_t fid = emissive[face];
+              const PathMaterial lm = mats[mat_ids ? mat_ids[fid] : 0u];
+              const uint32_t f0 = faces[3 * (size_t)fid], f1 = faces[3 * (size_t)fid + 1], f2 = faces[3 * (size_t)fid + 2];
+              const float *v0 = verts + 3 * (size_t)f0, *v1 = verts + 3 * (size_t)f1, *v2 = verts + 3 * (size_t)f2;
+              const float s1 = sqrtf(xi1), c0 = 1.0f - s1, c1 = s1 * (1.0f - xi2), c2 = s1 * xi2;
+              float lnx, lny, lnz, la2;
+              geometric_normal(verts, faces, fid, lnx, lny, lnz, la2);
+              const float area = 0.5f * la2;
+              float lx = c0 * v0[0] + c1 * v1[0] + c2 * v2[0] - Px, ly = c0 * v0[1] + c1 * v1[1] + c2 * v2[1] - Py,
+                    lz = c0 * v0[2] + c1 * v1[2] + c2 * v2[2] - Pz;
+              const float dist = sqrtf(lx * lx + ly * ly + lz * lz);
+              if (dist > 0.000001f && area > 0.0f) {
+                const float id = 1.0f / dist;
+                lx *= id;
+                ly *= id;
+                lz *= id;
+                const float cos_l = fmaxf(-(lx * lnx + ly * lny + lz * lnz), 0.0f);
+                if (cos_l > 0.0f) {
+                  const float pdf = (1.0f / nf) * (1.0f / area) * (dist * dist) / cos_l;  // PdfAtoW
+                  const float cos_t = fabsf(lx * nx + ly * ny + lz * nz);
+                  const float k = (1.0f / 3.14159265358979f) * cos_l * cos_t / pdf;  // brdf * cosine EDF * cos / pdf
+                  so = make_float4(Px, Py, Pz, 0.00001f);
+                  sd = make_float4(lx, ly, lz, dist - 0.00001f);
+                  sc = make_float4(k * m.diffuse[0] * lm.emission[0] * w.x, k * m.diffuse[1] * lm.emission[1] * w.y,
+                                   k * m.diffuse[2] * lm.emission[2] * w.z, __uint_as_float(pix));
+                  shadow = true;
+                }
               }
             }
+            // cosine-weighted direction about the flipped normal (main.cc:216-250)
+            const float sg = nz >= 0.0f ? 1.0f : -1.0f;
+            const float a = -1.0f / (sg + nz), b = nx * ny * a;
+            const float t1x = 1.0f + sg * nx * nx * a, t1y = sg * b, t1z = -sg * nx;
+            const float t2x = b, t2y = sg + ny * ny * a, t2z = -ny;
+            const float u1 = rand_ps(pix, smp, dim + 2, p.seed), u2 = rand_ps(pix, smp, dim + 3, p.seed);
+            const float r = sqrtf(u1);
+            float sn, cs;
+            sincosf(6.28318530718f * u2, &sn, &cs);
+            const float hx = r * cs, hy = r * sn, hz = sqrtf(fmaxf(0.0f, 1.0f - u1));
+            ox = t1x * hx + t2x * hy + nx * hz;
+            oy = t1y * hx + t2y * hy + ny * hz;
+            oz = t1z * hx + t2z * hy + nz * hz;
+            w.x *= m.diffuse[0];
+            w.y *= m.diffuse[1];
+            w.z *= m.diffuse[2];
+            w.w = 0.0f;
+          } else if (pick < rhoD + rhoS + rhoR) {  // refraction: refract(rayDir, -inside * originalNorm, n1)
+            const float rnx = -inside * onx, rny = -inside * ony, rnz = -inside * onz;
+            const float ndi = rnx * d.x + rny * d.y + rnz * d.z;
+            const float k = 1.0f - n1 * n1 * (1.0f - ndi * ndi);
+            if (k < 0.0f) {
+              ox = oy = oz = 0.0f;  // the reference continues with a zero direction (a ray that hits nothing)
+            } else {
+              const float c = n1 * ndi + sqrtf(k);
+              ox = n1 * d.x - c * rnx;
+              oy = n1 * d.y - c * rny;
+              oz = n1 * d.z - c * rnz;
+            }
+            w.x *= m.transmittance[0];
+            w.y *= m.transmittance[1];
+            w.z *= m.transmittance[2];
+            w.w = 1.0f;
+          } else {  // emission (cosine EDF), only if the previous event did not sample the lights
+            if (w.w != 0.0f) {
+              const float c = fmaxf(-(onx * d.x + ony * d.y + onz * d.z), 0.0f);
+              atomicAdd(accum + 3 * (size_t)pix + 0, c * m.emission[0] * w.x);
+              atomicAdd(accum + 3 * (size_t)pix + 1, c * m.emission[1] * w.y);
+              atomicAdd(accum + 3 * (size_t)pix + 2, c * m.emission[2] * w.z);
+            }
+            scatter = false;
           }
-          // ---- cosine-weighted continuation + Russian roulette of the NEXT bounce
-          if (bounce + 1 < p.max_bounces) {
-            w.x *= p.albedo[0];
-            w.y *= p.albedo[1];
-            w.z *= p.albedo[2];
+          // ---- continuation + Russian roulette of the NEXT bounce (main.cc:828-837)
+          if (scatter && bounce + 1 < p.max_bounces) {
             bool alive = true;
             if (bounce + 1 > 3) {
               alive = rand_ps(pix, smp, dim + 4, p.seed) >= 0.2f;
@@ -313,20 +471,8 @@ struct PathShadeEpilogue {
               w.z *= inv;
             }
             if (alive) {
-              const float sg = nz >= 0.0f ? 1.0f : -1.0f;
-              const float a = -1.0f / (sg + nz), b = nx * ny * a;
-              const float t1x = 1.0f + sg * nx * nx * a, t1y = sg * b, t1z = -sg * nx;
-              const float t2x = b, t2y = sg + ny * ny * a, t2z = -ny;
-              const float u1 = rand_ps(pix, smp, dim + 2, p.seed), u2 = rand_ps(pix, smp, dim + 3, p.seed);
-              const float r = sqrtf(u1);
-              float sn, cs;
-              sincosf(6.28318530718f * u2, &sn, &cs);
-              const float hx = r * cs, hy = r * sn, hz = sqrtf(fmaxf(0.0f, 1.0f - u1));
-              const float wx = t1x * hx + t2x * hy + nx * hz, wy = t1y * hx + t2y * hy + ny * hz,
-                          wz = t1z * hx + t2z * hy + nz * hz;
-              const float il = 1.0f / sqrtf(wx * wx + wy * wy + wz * wz);
               co = make_float4(Px, Py, Pz, p.ray_min_t);
-              cd = make_float4(wx * il, wy * il, wz * il, p.ray_max_t);
+              cd = make_float4(ox, oy, oz, p.ray_max_t);
               q.weight[pid] = w;
               cont = true;
             }

@@ -217,6 +217,48 @@ def with_area_light(verts, faces, center, half_x, half_z):
             len(faces), 2)
 
 
+MATERIAL_DTYPE = np.dtype([("diffuse", "<f4", (3,)), ("specular", "<f4", (3,)), ("transmittance", "<f4", (3,)),
+                           ("emission", "<f4", (3,)), ("ior", "<f4"), ("dissolve", "<f4"), ("pad", "<f4", (2,))])
+assert MATERIAL_DTYPE.itemsize == 64
+
+
+def material(diffuse=(0, 0, 0), specular=(0, 0, 0), transmittance=(0, 0, 0), emission=(0, 0, 0), ior=1.0, dissolve=0.0):
+    """One tinyobj-style material record as the reference path tracer reads it (main.cc:884-892).  NOTE the
+    reference's convention: dissolve weighs the REFRACTION lobe, (1 - dissolve) the diffuse one (main.cc:908-913),
+    exactly like examples/common/cornellbox_suzanne_lucy.mtl uses it (d 0 = diffuse, d 1 = glass)."""
+    m = np.zeros(1, MATERIAL_DTYPE)
+    m["diffuse"], m["specular"], m["transmittance"], m["emission"] = diffuse, specular, transmittance, emission
+    m["ior"], m["dissolve"] = ior, dissolve
+    return m
+
+
+def cornell_with_materials():
+    """The 34-triangle Cornell box + a ceiling light, with the material set of the reference's
+    cornellbox_suzanne_lucy.mtl: grey floor/ceiling/back, red and green walls, a mirror-like tall box, a glass
+    short box, an emitter.  Returns (verts, faces, materials, material_ids, emissive_faces)."""
+    v, f = cornell()
+    v, f, l0, ln = with_area_light(v, f, (0.0, 9.99, 0.0), 1.5, 1.5)
+    mats = np.concatenate([
+        material(diffuse=(0.8, 0.8, 0.8)),                                    # 0 grey
+        material(diffuse=(0.8, 0.05, 0.05)),                                  # 1 red
+        material(diffuse=(0.023, 0.41, 0.048)),                               # 2 green
+        material(specular=(1.0, 1.0, 1.0)),                                   # 3 "Monkey": pure specular
+        material(specular=(0.9, 0.9, 1.0), transmittance=(0.9, 0.9, 1.0), ior=1.5, dissolve=1.0),  # 4 "Reflective" glass
+        material(emission=(15.0, 15.0, 15.0)),                                # 5 light
+        material(diffuse=(1.0, 0.8, 0.8), specular=(0.2, 0.2, 0.2)),          # 6 "Lucy"
+    ])
+    ids = np.zeros(len(f), np.uint32)
+    ids[0:2] = 6      # floor: diffuse + a little specular
+    ids[2:6] = 0      # ceiling, back
+    ids[6:8] = 1      # left wall
+    ids[8:10] = 2     # right wall
+    ids[10:22] = 3    # tall box
+    ids[22:34] = 4    # short box
+    ids[l0:l0 + ln] = 5
+    emissive = np.nonzero(mats["emission"][ids].sum(axis=1) > 0)[0].astype(np.uint32)
+    return v, f, mats, ids, emissive
+
+
 # ----------------------------------------------------------------------------- cameras
 def _normalize(v):
     v = np.asarray(v, np.float64)

@@ -11,16 +11,23 @@ from nanort_b200 import api, scenes as S
 def path_config(spp=8):
     v, f = S.make_scene("terrain")
     v, f, l0, ln = S.with_area_light(v, f, (0.0, 6.0, 0.0), 2.0, 2.0)
+    mats = np.concatenate([S.material(diffuse=(0.7, 0.7, 0.7)), S.material(emission=(20, 20, 20))])
+    ids = np.zeros(len(f), np.uint32); ids[l0:] = 1
+    emissive = np.arange(l0, l0 + ln, dtype=np.uint32)
     acc = api.BVHAccel(); acc.Build(len(f), v, f)
     W, H = 1920, 1080
     cam = S.scene_camera("terrain", W, H)
+    d_m = torch.as_tensor(mats.view(np.float32).reshape(-1), device="cuda")
+    d_i = torch.as_tensor(ids.astype(np.int32), device="cuda")
+    d_e = torch.as_tensor(emissive.astype(np.int32), device="cuda")
     p = api.PathParams()
     for i in range(12): p.cam[i] = float(cam[i])
     p.width, p.height, p.spp, p.sample0, p.seed = W, H, spp, 0, 3
     p.tile_w, p.tile_h, p.shard, p.n_shards = 64, 8, 0, 1
     p.max_bounces, p.ray_min_t, p.ray_max_t = 10, 1e-3, 1e30
-    for k in range(3): p.albedo[k], p.emission[k] = 0.7, 20.0
-    p.light_first_face, p.light_n_faces, p.flags = l0, ln, 0
+    p.n_materials, p.n_emissive = len(mats), len(emissive)
+    p.d_materials, p.d_material_ids, p.d_emissive_faces = d_m.data_ptr(), d_i.data_ptr(), d_e.data_ptr()
+    p.d_facevarying_normals, p.flags = None, 0
     accum = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
     for it in range(3):
         accum.zero_()
