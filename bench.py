@@ -125,9 +125,10 @@ def config_dict(n_gpus):
         "workload": f"sphere_grid 100,002 triangles (BASELINE.json configs[1]), {WIDTH}x{HEIGHT}, {SPP}*N spp "
                     f"(N={n_gpus}: {SPP * n_gpus} spp), primary + 1 cosine AO ray per hit, closest-hit; "
                     f"tiles {TILE_W}x{TILE_H} round-robin over ranks; BVH replicated; framebuffer all_gather",
-        "rays_per_gpu_per_step": "33,177,600 primary + ~18.2 M AO",
-        "l2_policy": "inputs larger than L2: each wave's ray/hit queues are 8 Mi rays x 104 B = 832 MiB (L2 = 126 MB); "
-                     "scene+BVH (7 MB) stay L2-resident by design",
+        "rays_per_gpu_per_step": "33,177,600 primary + ~18.2 M AO, in 2 waves of 16 Mi camera rays",
+        "l2_policy": "inputs larger than L2: camera rays are generated inside the traversal kernel (no input stream); the "
+                     "only stream between the two launches of a wave is the compacted AO queue, ~9 M rays x 36 B = 330 MB per "
+                     "16 Mi-ray wave = 2.6 x the 126 MB L2; scene + BVH (7 MB) stay cache-resident by design",
         "parallelism": f"ray-tile sharding x{n_gpus}",
     }
 

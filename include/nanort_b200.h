@@ -66,6 +66,22 @@ int nrt_build(const float *verts, size_t stride_bytes, size_t n_verts, const uin
               uint32_t n_prims, const void *build_opts_28B, nrt_accel **out);
 
 /*
+ * nrt_build with a choice of builder.  flags:
+ *   NRT_BUILD_FAST (0)              the production binned-SAH builder (what nrt_build runs)
+ *   NRT_BUILD_REFERENCE_TREE        conformance build: reproduce, on the device, exactly the node array and
+ *                                   indices_ CPU nanort writes at the pinned commit (x-only binning of
+ *                                   nanort.h:1357, axis retry / median fallback :1827-1857, TriangleSAHPred +
+ *                                   libstdc++ std::partition element order, BuildTree / parallel-join node order)
+ *   NRT_BUILD_REFERENCE_CPP03_ORDER with the flag above: the serial (C++03 / small scene) node order even above
+ *                                   min_primitives_for_parallel_build (default: the C++11 build's joined order)
+ */
+#define NRT_BUILD_FAST 0u
+#define NRT_BUILD_REFERENCE_TREE 1u
+#define NRT_BUILD_REFERENCE_CPP03_ORDER 2u
+int nrt_build_ex(const float *verts, size_t stride_bytes, size_t n_verts, const uint32_t *faces, uint32_t n_prims,
+                 const void *build_opts_28B, uint32_t flags, nrt_accel **out);
+
+/*
  * Conformance entry: adopt an existing nanort-layout tree (e.g. one built by
  * the CPU reference; BVHAccel::GetNodes()/GetIndices(), nanort.h:786-787, or
  * the Dump format nanort.h:2164-2220) so the GPU traverses exactly that tree.

@@ -20,6 +20,9 @@ from .scenes import HIT_DTYPE, NODE_DTYPE, RAY_DTYPE
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnanort_b200.so")
 
+BUILD_FAST = 0
+BUILD_REFERENCE_TREE = 1          # bit-identical to CPU nanort's arrays (conformance build)
+BUILD_REFERENCE_CPP03_ORDER = 2   # ... in the serial build's node order
 TRAVERSE_FAST = 0
 TRAVERSE_CONFORMANCE = 1
 TRAVERSE_CPP03_INVERSE = 2
@@ -45,7 +48,7 @@ STATS_DTYPE = np.dtype(
 
 # every symbol include/nanort_b200.h declares
 EXPORTS = [
-    "nrt_last_error", "nrt_device_count", "nrt_set_device", "nrt_build", "nrt_adopt", "nrt_free", "nrt_stats",
+    "nrt_last_error", "nrt_device_count", "nrt_set_device", "nrt_build", "nrt_build_ex", "nrt_adopt", "nrt_free", "nrt_stats",
     "nrt_bounding_box", "nrt_nodes", "nrt_traverse", "nrt_traverse_device", "nrt_traverse_count_device",
     "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device", "nrt_render_path_device",
 ]
@@ -118,6 +121,7 @@ def lib():
     L.nrt_device_count.restype = C.c_int
     L.nrt_set_device.argtypes = [C.c_int]
     L.nrt_build.argtypes = [vp, sz, sz, vp, u32, vp, C.POINTER(vp)]
+    L.nrt_build_ex.argtypes = [vp, sz, sz, vp, u32, vp, u32, C.POINTER(vp)]
     L.nrt_adopt.argtypes = [vp, sz, vp, sz, vp, sz, sz, vp, u32, C.POINTER(vp)]
     L.nrt_free.argtypes = [vp]
     L.nrt_free.restype = None
@@ -223,7 +227,7 @@ class BVHAccel:
         return self._h is not None
 
     # -- build
-    def Build(self, num_primitives, vertices, faces, options=None, vertex_stride_bytes=12):
+    def Build(self, num_primitives, vertices, faces, options=None, vertex_stride_bytes=12, flags=BUILD_FAST):
         """BVHAccel::Build(num_primitives, TriangleMesh(vertices, faces, stride), pred, options)
         (nanort.h:716-718).  Returns False for num_primitives == 0 like the reference."""
         self.free()
@@ -234,8 +238,8 @@ class BVHAccel:
         self._set_device()
         h = C.c_void_p()
         n_verts = vertices.size * 4 // vertex_stride_bytes
-        _check(lib().nrt_build(_p(vertices), vertex_stride_bytes, n_verts, _p(faces), int(num_primitives),
-                               _p(options), C.byref(h)))
+        _check(lib().nrt_build_ex(_p(vertices), vertex_stride_bytes, n_verts, _p(faces), int(num_primitives),
+                                  _p(options), int(flags), C.byref(h)))
         self._h = h
         return True
 

@@ -133,6 +133,11 @@ int nrt_set_device(int device) {
 
 int nrt_build(const float *verts, size_t stride_bytes, size_t n_verts, const uint32_t *faces, uint32_t n_prims,
               const void *build_opts_28B, nrt_accel **out) {
+  return nrt_build_ex(verts, stride_bytes, n_verts, faces, n_prims, build_opts_28B, NRT_BUILD_FAST, out);
+}
+
+int nrt_build_ex(const float *verts, size_t stride_bytes, size_t n_verts, const uint32_t *faces, uint32_t n_prims,
+                 const void *build_opts_28B, uint32_t flags, nrt_accel **out) {
   if (!out) {
     g_err = "nrt_build: out is NULL";
     return NRT_ERR_INVALID;
@@ -165,7 +170,11 @@ int nrt_build(const float *verts, size_t stride_bytes, size_t n_verts, const uin
   }
   rc = common_init(a);
   if (rc == NRT_OK) rc = upload_geometry(a, verts, stride_bytes, n_verts, faces, n_prims);
-  if (rc == NRT_OK) rc = build_on_device(a, a->streams[0]);
+  if (rc == NRT_OK) {
+    rc = (flags & NRT_BUILD_REFERENCE_TREE)
+             ? build_reference_tree_on_device(a, !(flags & NRT_BUILD_REFERENCE_CPP03_ORDER), a->streams[0])
+             : build_on_device(a, a->streams[0]);
+  }
   if (rc == NRT_OK) rc = derive_private_layout(a, a->streams[0]);
   if (rc != NRT_OK) {
     destroy(a);

@@ -168,6 +168,8 @@ int launch_traverse_soa(const Accel *a, const float4 *d_org_tmin, const float4 *
 int derive_private_layout(Accel *a, cudaStream_t s);
 // build.cu
 int build_on_device(Accel *a, cudaStream_t s);
+// build_ref.cu
+int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s);
 
 int device_sm_count(int device);
 

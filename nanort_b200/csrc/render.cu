@@ -184,8 +184,9 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
   const unsigned long long per_tile = (unsigned long long)p.tile_w * p.tile_h * p.spp;
   const unsigned long long total_slots = (unsigned long long)my_tiles * per_tile;
 
-  // wave capacity: whole tiles, at most ~8 Mi rays (832 MiB of queues, far beyond the 126 MB L2)
-  const unsigned long long kMaxWave = 8ull << 20;
+  // wave capacity: whole tiles, at most 16 Mi camera rays; the compacted AO queue of such a wave (~9 M rays x
+  // 36 B = 330 MB) is written by the primary launch and read back by the AO launch -- 2.6 x the 126 MB L2
+  const unsigned long long kMaxWave = 16ull << 20;
   unsigned long long tiles_per_wave = kMaxWave / per_tile;
   if (tiles_per_wave == 0) tiles_per_wave = 1;
   const unsigned long long cap = std::min<unsigned long long>(total_slots, tiles_per_wave * per_tile);
