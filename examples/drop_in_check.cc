@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "nanort.h"
@@ -54,6 +55,28 @@ int main(int argc, char **argv) {
          int(stats.num_leaf_nodes) - int(stats.num_branch_nodes), accel.IsValid() ? 1 : 0, bmin[0], bmin[1], bmin[2],
          bmax[0], bmax[1], bmax[2]);
 
+#ifdef PRINT_TREE
+  // conformance builds must agree on the whole tree, not only on the hits
+  {
+    const std::vector<nanort::BVHNode<float> > &nodes = accel.GetNodes();
+    const std::vector<unsigned int> &indices = accel.GetIndices();
+    unsigned long long h = 1469598103934665603ull;
+    for (size_t i = 0; i < nodes.size(); i++) {
+      const nanort::BVHNode<float> &nd = nodes[i];
+      unsigned int w[10];
+      memcpy(w, nd.bmin, 12);
+      memcpy(w + 3, nd.bmax, 12);
+      w[6] = (unsigned int)nd.flag;
+      w[7] = nd.flag ? 0u : (unsigned int)nd.axis;  // leaf.axis is uninitialised in the reference
+      w[8] = nd.data[0];
+      w[9] = nd.data[1];
+      for (int k = 0; k < 10; k++) h = (h ^ w[k]) * 1099511628211ull;
+    }
+    for (size_t i = 0; i < indices.size(); i++) h = (h ^ indices[i]) * 1099511628211ull;
+    printf("tree nodes %zu leaves %u branches %u depth %u hash %016llx\n", nodes.size(), stats.num_leaf_nodes,
+           stats.num_branch_nodes, stats.max_tree_depth, h);
+  }
+#endif
   int hits = 0;
   for (int i = 0; i < n_rays; i++) {
     nanort::Ray<float> ray;

@@ -40,6 +40,26 @@
 
 #include "nanort_b200.h"
 
+// The reference's own switch keeps its meaning (nanort.h:51-82, 418-462): with NANORT_USE_CPP11_FEATURE
+// vsafe_inverse treats -0.0f as negative (copysign) and, in conformance mode, large scenes get the parallel build's
+// node order; without it the C++03 conventions apply.
+#ifdef NANORT_USE_CPP11_FEATURE
+#define NANORT_B200_INVERSE_FLAG 0u
+#define NANORT_B200_ORDER_FLAG 0u
+#else
+#define NANORT_B200_INVERSE_FLAG NRT_TRAVERSE_CPP03_INVERSE
+#define NANORT_B200_ORDER_FLAG NRT_BUILD_REFERENCE_CPP03_ORDER
+#endif
+// -DNANORT_B200_CONFORMANCE: Build writes exactly the arrays CPU nanort would (conformance builder) and Traverse
+// walks them in the reference's visiting order -- bit-identical results, ties included.  Default: the fast path.
+#ifdef NANORT_B200_CONFORMANCE
+#define NANORT_B200_BUILD_FLAGS (NRT_BUILD_REFERENCE_TREE | NANORT_B200_ORDER_FLAG)
+#define NANORT_B200_TRAVERSE_FLAGS (NRT_TRAVERSE_CONFORMANCE | NANORT_B200_INVERSE_FLAG)
+#else
+#define NANORT_B200_BUILD_FLAGS NRT_BUILD_FAST
+#define NANORT_B200_TRAVERSE_FLAGS (NRT_TRAVERSE_FAST | NANORT_B200_INVERSE_FLAG)
+#endif
+
 namespace nanort {
 
 // ---- ray type flags (carried in Ray::type, never read by the kernel) -- :86-94
@@ -318,7 +338,8 @@ class BVHAccel<float> {
     n_prims_ = 0;
     if (num_primitives == 0) return false;
     nrt_accel *h = NULL;
-    int rc = nrt_build(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), num_primitives, &options, &h);
+    int rc = nrt_build_ex(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), num_primitives, &options,
+                          NANORT_B200_BUILD_FLAGS, &h);
     if (rc != NRT_OK) {
       fprintf(stderr, "nanort_b200: Build failed: %s\n", nrt_last_error());
       return false;
@@ -339,7 +360,7 @@ class BVHAccel<float> {
     if (!Ready(intersector)) return false;
     TriangleIntersection<float> rec;
     unsigned char hit = 0;
-    if (nrt_traverse(handle_.get(), &ray, 1, &rec, &hit, &options, NRT_TRAVERSE_FAST) != NRT_OK) {
+    if (nrt_traverse(handle_.get(), &ray, 1, &rec, &hit, &options, NANORT_B200_TRAVERSE_FLAGS) != NRT_OK) {
       fprintf(stderr, "nanort_b200: Traverse failed: %s\n", nrt_last_error());
       return false;
     }
@@ -358,7 +379,7 @@ class BVHAccel<float> {
   template <class I>
   size_t TraverseBatch(const Ray<float> *rays, size_t n, const I &intersector, TriangleIntersection<float> *hits,
                        unsigned char *hit_mask, const BVHTraceOptions &options = BVHTraceOptions(),
-                       unsigned int flags = NRT_TRAVERSE_FAST) const {
+                       unsigned int flags = NANORT_B200_TRAVERSE_FLAGS) const {
     if (!Ready(intersector)) return static_cast<size_t>(-1);
     std::vector<unsigned char> tmp;
     if (!hit_mask) {

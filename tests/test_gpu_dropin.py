@@ -50,3 +50,14 @@ def test_dump_load_interchange_with_cpu_nanort(tmp_path):
     assert head[0].startswith("dumped ") and os.path.getsize(out) > 50000
     if os.path.exists(os.path.join(BIN, "dump_load_ref")):
         assert _run("dump_load_ref", "load", out) == want
+
+
+def test_drop_in_conformance_mode_reproduces_tree_and_hits():
+    """-DNANORT_B200_CONFORMANCE: the facade's Build must produce CPU nanort's exact arrays (hash of every node
+    and of indices_) and its per-ray Traverse the exact hit records -- the golden output of the same source
+    compiled against the reference header with -DPRINT_TREE."""
+    if not os.path.exists(os.path.join(BIN, "drop_in_check_b200_conf")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
+    got = _run("drop_in_check_b200_conf", "24", "400")
+    want = open(os.path.join(ROOT, "tests", "golden", "drop_in_check_ref_tree.txt")).read().strip().splitlines()
+    assert got[1].startswith("tree nodes ") and got == want
