@@ -365,6 +365,7 @@ int nrt_traverse(const nrt_accel *h, const void *rays_36B, size_t n_rays, void *
   Accel *a = const_cast<Accel *>(reinterpret_cast<const Accel *>(h));
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
+  std::lock_guard<std::mutex> lock(a->host_mu);
   NRT_CUDA(cudaSetDevice(a->device));
   const size_t kChunk = (size_t)1 << 20;  // 1 Mi rays = 36 MiB up, 17 MiB down per chunk
   size_t chunk = std::min(n_rays, kChunk);

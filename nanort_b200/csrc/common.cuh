@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -114,6 +115,9 @@ struct Accel {
   void *d_stage_hits[3] = {nullptr, nullptr, nullptr};
   void *d_stage_mask[3] = {nullptr, nullptr, nullptr};
   size_t stage_rays = 0;  // capacity in rays of every staging buffer
+  // the reference's Traverse may be called from many host threads at once (examples/path_tracer/main.cc:787-799);
+  // the staging slots of the host-pointer path are shared, so those calls are serialised per accel
+  std::mutex host_mu;
   // wavefront pass scratch (render.cu)
   void *d_wave = nullptr;
   size_t wave_bytes = 0;

@@ -61,3 +61,11 @@ def test_drop_in_conformance_mode_reproduces_tree_and_hits():
     got = _run("drop_in_check_b200_conf", "24", "400")
     want = open(os.path.join(ROOT, "tests", "golden", "drop_in_check_ref_tree.txt")).read().strip().splitlines()
     assert got[1].startswith("tree nodes ") and got == want
+
+
+def test_concurrent_per_ray_traverse_from_worker_threads():
+    """8 host threads calling accel.Traverse per ray, as the reference path tracer's row workers do."""
+    if not os.path.exists(os.path.join(BIN, "threads_check")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
+    out = _run("threads_check")
+    assert out[-1].endswith("mismatches 0"), out

@@ -12,3 +12,11 @@ for r in range(reps):
     st = acc.GetStatistics()
     print(f"  build {r}: wall {1e3*(t1-t0):.1f} ms, device {st['build_secs']*1e3:.2f} ms, nodes {st['num_leaf_nodes']+st['num_branch_nodes']}, depth {st['max_tree_depth']}", flush=True)
     acc.free()
+if len(sys.argv) > 3 and sys.argv[3] == "ref":
+    for r in range(2):
+        acc = api.BVHAccel()
+        t0 = time.time(); acc.Build(len(f), v, f, flags=api.BUILD_REFERENCE_TREE); t1 = time.time()
+        st = acc.GetStatistics()
+        print(f"  conformance build {r}: wall {1e3*(t1-t0):.1f} ms, device {st['build_secs']*1e3:.2f} ms, nodes "
+              f"{st['num_leaf_nodes']+st['num_branch_nodes']}, depth {st['max_tree_depth']}", flush=True)
+        acc.free()
