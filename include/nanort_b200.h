@@ -220,6 +220,52 @@ typedef struct nrt_path_result {
 int nrt_render_path_device(const nrt_accel *a, const nrt_path_params *p, float *d_accum_rgb, nrt_path_result *res,
                            void *stream);
 
+
+/* ------------------------------------------------------------------ two-level scene (instancing)
+ * Replaces the reference's scene-graph example, which is how nanort traverses transformed instances:
+ *   nanosg::Scene<float,M>::AddNode / Commit   examples/nanosg/nanosg.h:673-755   -> nrt_scene_commit
+ *   nanosg::Scene<float,M>::Traverse           examples/nanosg/nanosg.h:779-875   -> nrt_scene_traverse[_device]
+ *   BVHAccel<float>::ListNodeIntersections     nanort.h:2607-2692                 (inside the kernels)
+ * An instance is a bottom-level accel (borrowed: it must outlive the scene and live on the same device) plus the
+ * node's local transform, float[4][4] in the reference's row-vector convention (p' = p . M, translation in row 3,
+ * nanosg.h:214-222).  Many instances may share one accel.  The hit record carries what Scene::Traverse returns
+ * short of the mesh-dependent normals: {u, v, t (world distance), prim_id, node_id, P (world hit point)}.
+ * Reference behaviours kept as they are: the world ray's min_t / max_t gate only the top-level walk; the local ray
+ * is {0, FLT_MAX}; at most the 64 nearest instance boxes are examined per ray; cull_back_face is inert. */
+typedef struct nrt_scene nrt_scene;
+
+typedef struct nrt_instance {
+  const nrt_accel *accel;
+  float xform[16];
+} nrt_instance;
+
+typedef struct nrt_scene_hit {
+  float u, v, t;
+  uint32_t prim_id, node_id;
+  float P[3];
+} nrt_scene_hit; /* 32 bytes */
+
+/* flags: NRT_BUILD_FAST (good top-level tree) or NRT_BUILD_REFERENCE_TREE [| NRT_BUILD_REFERENCE_CPP03_ORDER]
+ * (top-level node array bit-identical to the reference's Commit).  n_instances == 0 fails like Commit does. */
+int nrt_scene_commit(const nrt_instance *instances, uint32_t n_instances, uint32_t flags, nrt_scene **out);
+void nrt_scene_free(nrt_scene *s);
+/* Scene::GetBoundingBox (nanosg.h:761-769) */
+int nrt_scene_bounding_box(const nrt_scene *s, float bmin[3], float bmax[3]);
+/* host mirror of the top-level tree in nanort's layout (indices = instance ids) */
+int nrt_scene_nodes(nrt_scene *s, const void **nodes_40B, size_t *n_nodes, const uint32_t **indices,
+                    size_t *n_indices);
+/* per-instance derived state as Node::Update computes it (nanosg.h:400-445), 76 floats:
+ * xform[16] inverse[16] inverse33[16] inverse_transpose33[16] local_bmin[3] local_bmax[3] world_bmin[3] world_bmax[3] */
+int nrt_scene_instance_state(const nrt_scene *s, uint32_t instance, float out76[76]);
+/* n x Scene::Traverse with HOST pointers; hits[i] = {0,0,max_t,~0,~0,0,0,0} and hit_mask[i] = 0 on a miss.
+ * flags: NRT_TRAVERSE_FAST / NRT_TRAVERSE_CONFORMANCE (the reference's exact list-then-visit order) /
+ * NRT_TRAVERSE_CPP03_INVERSE */
+int nrt_scene_traverse(const nrt_scene *s, const void *rays_36B, size_t n_rays, void *hits_32B, uint8_t *hit_mask,
+                       uint32_t flags);
+/* the same with DEVICE pointers, asynchronous on `stream` */
+int nrt_scene_traverse_device(const nrt_scene *s, const void *d_rays_36B, size_t n_rays, void *d_hits_32B,
+                              uint8_t *d_hit_mask, uint32_t flags, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

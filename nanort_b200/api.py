@@ -51,6 +51,8 @@ EXPORTS = [
     "nrt_last_error", "nrt_device_count", "nrt_set_device", "nrt_build", "nrt_build_ex", "nrt_adopt", "nrt_free", "nrt_stats",
     "nrt_bounding_box", "nrt_nodes", "nrt_traverse", "nrt_traverse_device", "nrt_traverse_count_device",
     "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device", "nrt_render_path_device",
+    "nrt_scene_commit", "nrt_scene_free", "nrt_scene_bounding_box", "nrt_scene_nodes", "nrt_scene_instance_state",
+    "nrt_scene_traverse", "nrt_scene_traverse_device",
 ]
 
 
@@ -138,6 +140,14 @@ def lib():
     L.nrt_render_ao_device.argtypes = [vp, C.POINTER(AoParams), vp, C.POINTER(AoResult), vp]
     L.nrt_ao_workload_device.argtypes = [vp, C.POINTER(AoParams), vp, vp, vp, u64p, u64p, vp]
     L.nrt_render_path_device.argtypes = [vp, C.POINTER(PathParams), vp, C.POINTER(PathResult), vp]
+    L.nrt_scene_commit.argtypes = [vp, u32, u32, C.POINTER(vp)]
+    L.nrt_scene_free.argtypes = [vp]
+    L.nrt_scene_free.restype = None
+    L.nrt_scene_bounding_box.argtypes = [vp, vp, vp]
+    L.nrt_scene_nodes.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
+    L.nrt_scene_instance_state.argtypes = [vp, u32, vp]
+    L.nrt_scene_traverse.argtypes = [vp, vp, sz, vp, vp, u32]
+    L.nrt_scene_traverse_device.argtypes = [vp, vp, sz, vp, vp, u32, vp]
     _lib = L
     return L
 
@@ -337,3 +347,86 @@ class BVHAccel:
                                           C.byref(res) if want_result else None,
                                           C.c_void_p(stream) if stream else None))
         return res
+
+
+# ------------------------------------------------------------------ two-level scene (examples/nanosg)
+SCENE_HIT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("t", "<f4"), ("prim_id", "<u4"), ("node_id", "<u4"),
+                            ("P", "<f4", (3,))])
+INSTANCE_STATE_DTYPE = np.dtype([("xform", "<f4", (4, 4)), ("inv", "<f4", (4, 4)), ("inv33", "<f4", (4, 4)),
+                                 ("invT33", "<f4", (4, 4)), ("lbmin", "<f4", (3,)), ("lbmax", "<f4", (3,)),
+                                 ("xbmin", "<f4", (3,)), ("xbmax", "<f4", (3,))])
+
+
+class Instance(C.Structure):
+    _fields_ = [("accel", C.c_void_p), ("xform", C.c_float * 16)]
+
+
+class Scene:
+    """Mirror of nanosg::Scene (examples/nanosg/nanosg.h:664-905): AddNode(accel, xform) ..., Commit(), Traverse.
+    The accels are borrowed and kept alive by this object."""
+
+    def __init__(self):
+        self._h = None
+        self._nodes = []
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().nrt_scene_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def AddNode(self, accel: "BVHAccel", xform) -> bool:
+        x = np.ascontiguousarray(xform, np.float32).reshape(16)
+        self._nodes.append((accel, x))
+        return True
+
+    def Commit(self, flags=BUILD_FAST) -> bool:
+        if self._h:
+            lib().nrt_scene_free(self._h)
+            self._h = None
+        n = len(self._nodes)
+        arr = (Instance * max(n, 1))()
+        for i, (a, x) in enumerate(self._nodes):
+            arr[i].accel = a._h
+            arr[i].xform[:] = x.tolist()
+        h = C.c_void_p()
+        rc = lib().nrt_scene_commit(C.cast(arr, C.c_void_p), n, int(flags), C.byref(h))
+        if rc == -1 and n == 0:  # Commit() returns false for an empty scene (nanosg.h:708-711)
+            return False
+        _check(rc)
+        self._h = h
+        return True
+
+    def GetBoundingBox(self):
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        _check(lib().nrt_scene_bounding_box(self._h, _p(a), _p(b)))
+        return a, b
+
+    def GetTopLevel(self):
+        pn, nn, pi, ni = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        _check(lib().nrt_scene_nodes(self._h, C.byref(pn), C.byref(nn), C.byref(pi), C.byref(ni)))
+        nodes = np.frombuffer((C.c_char * (nn.value * 40)).from_address(pn.value), NODE_DTYPE).copy()
+        idx = np.frombuffer((C.c_char * (ni.value * 4)).from_address(pi.value), np.uint32).copy()
+        return nodes, idx
+
+    def InstanceStates(self):
+        out = np.zeros(len(self._nodes), INSTANCE_STATE_DTYPE)
+        for i in range(len(self._nodes)):
+            _check(lib().nrt_scene_instance_state(self._h, i, out[i:i + 1].ctypes.data))
+        return out
+
+    def Traverse(self, rays, flags=TRAVERSE_FAST):
+        """Batch of Scene::Traverse calls on HOST arrays: (hits, mask)."""
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype.itemsize == 36
+        n = len(rays)
+        hits, mask = np.zeros(n, SCENE_HIT_DTYPE), np.zeros(n, np.uint8)
+        _check(lib().nrt_scene_traverse(self._h, _p(rays), n, _p(hits), _p(mask), int(flags)))
+        return hits, mask
+
+    def TraverseDevice(self, d_rays_ptr, n, d_hits_ptr, d_mask_ptr=None, flags=TRAVERSE_FAST, stream=None):
+        _check(lib().nrt_scene_traverse_device(self._h, C.c_void_p(d_rays_ptr), int(n), C.c_void_p(d_hits_ptr),
+                                               C.c_void_p(d_mask_ptr) if d_mask_ptr else None, int(flags),
+                                               C.c_void_p(stream) if stream else None))

@@ -77,6 +77,39 @@ __global__ void prim_setup_kernel(const float *__restrict__ verts, const uint32_
   }
 }
 
+// Same records for axis-aligned boxes as primitives (the two-level scene's top-level build,
+// NodeBBoxGeometry::BoundingBoxAndCenter, examples/nanosg/nanosg.h:560-573): centre = (bmax + bmin) / 2.
+__global__ void box_setup_kernel(const float *__restrict__ boxes6, uint32_t n, float4 *__restrict__ plo,
+                                 float4 *__restrict__ phi, float *__restrict__ pcz,
+                                 uint32_t *__restrict__ scene_keys /*6*/) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (i < n) {
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      lo[k] = boxes6[6 * (size_t)i + k];
+      hi[k] = boxes6[6 * (size_t)i + 3 + k];
+      c[k] = (hi[k] + lo[k]) / 2.0f;
+    }
+    plo[i] = make_float4(lo[0], lo[1], lo[2], c[0]);
+    phi[i] = make_float4(hi[0], hi[1], hi[2], c[1]);
+    pcz[i] = c[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float a = lo[k], b = hi[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fminf(a, __shfl_xor_sync(0xFFFFFFFFu, a, o));
+      b = fmaxf(b, __shfl_xor_sync(0xFFFFFFFFu, b, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(scene_keys + k, fkey(a));
+      atomicMax(scene_keys + 3 + k, fkey(b));
+    }
+  }
+}
+
 __global__ void init_build_kernel(BNode *pool, BuildCounters *ctr, const uint32_t *scene_keys, uint32_t n,
                                   uint32_t min_leaf, uint32_t max_depth, uint32_t *active0, uint32_t *subtrees) {
   BNode r;
@@ -680,7 +713,10 @@ int build_on_device(Accel *a, cudaStream_t s) {
   BUILD_CUDA(cudaMalloc(&a->d_nodes, sizeof(Node40) * (2 * (size_t)n)));
   BUILD_CUDA(cudaMalloc(&a->d_indices, sizeof(uint32_t) * (size_t)n));
   BUILD_CUDA(cudaEventRecord(ev0, s));
-  prim_setup_kernel<<<grid_n, 256, 0, s>>>(a->d_verts, a->d_faces, n, d_plo_u, d_phi_u, d_pcz_u, d_scene);
+  if (a->d_prim_boxes)
+    box_setup_kernel<<<grid_n, 256, 0, s>>>(a->d_prim_boxes, n, d_plo_u, d_phi_u, d_pcz_u, d_scene);
+  else
+    prim_setup_kernel<<<grid_n, 256, 0, s>>>(a->d_verts, a->d_faces, n, d_plo_u, d_phi_u, d_pcz_u, d_scene);
   BUILD_CUDA(cudaGetLastError());
   {
     // Morton pre-order: sort the primitives along a 30-bit Z-curve over the scene box, then lay their

@@ -43,6 +43,22 @@ __global__ void ref_prim_kernel(const float *__restrict__ verts, const uint32_t 
   C[i] = make_float2(s[1], s[2]);
 }
 
+// box primitives (two-level scene, top level): centre = (bmax + bmin) / 2 in every slot the predicate reads
+__global__ void ref_box_prim_kernel(const float *__restrict__ boxes6, uint32_t n, float4 *__restrict__ A,
+                                    float4 *__restrict__ B, float2 *__restrict__ C) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float lo[3], hi[3], c[3];
+  for (int k = 0; k < 3; k++) {
+    lo[k] = boxes6[6 * (size_t)i + k];
+    hi[k] = boxes6[6 * (size_t)i + 3 + k];
+    c[k] = (hi[k] + lo[k]) / 2.0f;
+  }
+  A[i] = make_float4(lo[0], lo[1], lo[2], c[0]);
+  B[i] = make_float4(hi[0], hi[1], hi[2], c[0]);
+  C[i] = make_float2(c[1], c[2]);
+}
+
 struct RefCounters {
   uint32_t pool;
   uint32_t n_fresh[2];   // nodes created by the previous / this level (ping-pong)
@@ -202,9 +218,11 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-__device__ __forceinline__ bool ref_pred(const float4 &b, const float2 &c, int axis, float pos) {
+// triangles: (p0+p1)+p2 < pos*3 (TriangleSAHPred, nanort.h:897-911), mul = 3; boxes: (bmin+bmax)/2 < pos
+// (NodeBBoxPred, examples/nanosg/nanosg.h:520-532), mul = 1 (pos * 1.0f is exact)
+__device__ __forceinline__ bool ref_pred(const float4 &b, const float2 &c, int axis, float pos, float mul) {
   const float s = axis == 0 ? b.w : (axis == 1 ? c.x : c.y);
-  return s < pos * 3.0f;
+  return s < pos * mul;
 }
 
 // round k: how many primitives of every undecided node satisfy the predicate on axis k
@@ -212,7 +230,7 @@ __global__ void __launch_bounds__(256)
     ref_count_kernel(const BNode *__restrict__ pool, const uint32_t *__restrict__ node_of,
                      const uint32_t *__restrict__ idx, const float4 *__restrict__ B, const float2 *__restrict__ C,
                      uint32_t n, uint32_t level, int axis, const float *__restrict__ cut3,
-                     const uint32_t *__restrict__ state, uint32_t *__restrict__ cnt) {
+                     const uint32_t *__restrict__ state, uint32_t *__restrict__ cnt, float pred_mul) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t slot = kInactive;
   bool t = false;
@@ -221,7 +239,7 @@ __global__ void __launch_bounds__(256)
     if (nd.split_bin == level && nd.pad != kInactive && !(state[nd.pad] >> 31)) {
       slot = nd.pad;
       const uint32_t s = idx[p];
-      t = ref_pred(B[s], C[s], axis, cut3[(size_t)slot * 3 + axis]);
+      t = ref_pred(B[s], C[s], axis, cut3[(size_t)slot * 3 + axis], pred_mul);
     }
   }
   const unsigned same = __match_any_sync(0xFFFFFFFFu, slot);
@@ -257,7 +275,7 @@ __global__ void __launch_bounds__(256)
     ref_flags_kernel(const BNode *__restrict__ pool, const uint32_t *__restrict__ node_of,
                      const uint32_t *__restrict__ idx, const float4 *__restrict__ B, const float2 *__restrict__ C,
                      uint32_t n, uint32_t level, const float *__restrict__ cut3, const uint32_t *__restrict__ state,
-                     uint32_t *__restrict__ mf, uint32_t *__restrict__ mt) {
+                     uint32_t *__restrict__ mf, uint32_t *__restrict__ mt, float pred_mul) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > n) return;
   uint32_t f = 0, t = 0;
@@ -266,7 +284,7 @@ __global__ void __launch_bounds__(256)
     if (nd.split_bin == level && nd.pad != kInactive && (state[nd.pad] & 0x40000000u)) {
       const int axis = (int)(state[nd.pad] & 3u);
       const uint32_t s = idx[p];
-      const bool pr = ref_pred(B[s], C[s], axis, cut3[(size_t)nd.pad * 3 + axis]);
+      const bool pr = ref_pred(B[s], C[s], axis, cut3[(size_t)nd.pad * 3 + axis], pred_mul);
       const bool left_part = p < nd.l + nd.nleft;
       f = (left_part && !pr) ? 1u : 0u;
       t = (!left_part && pr) ? 1u : 0u;
@@ -462,6 +480,7 @@ int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s) {
   const uint32_t n = a->n_prims;
   const BuildOptions28 &opt = a->options;
   const int nbins = (int)opt.bin_size;
+  const float pred_mul = a->d_prim_boxes ? 1.0f : 3.0f;
   const uint32_t min_leaf = opt.min_leaf_primitives < 1 ? 1u : opt.min_leaf_primitives;
   if (nbins > 256) {
     set_error("nrt_build: bin_size > 256 is not supported by the device builders");
@@ -524,7 +543,10 @@ int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s) {
   RB_CUDA(cudaMalloc(&a->d_indices, sizeof(uint32_t) * (size_t)n));
 
   RB_CUDA(cudaEventRecord(ev0, s));
-  ref_prim_kernel<<<grid_n, 256, 0, s>>>(a->d_verts, a->d_faces, n, dA, dB, dC);
+  if (a->d_prim_boxes)
+    ref_box_prim_kernel<<<grid_n, 256, 0, s>>>(a->d_prim_boxes, n, dA, dB, dC);
+  else
+    ref_prim_kernel<<<grid_n, 256, 0, s>>>(a->d_verts, a->d_faces, n, dA, dB, dC);
   ref_iota_kernel<<<grid_n, 256, 0, s>>>(d_idx[0], d_nodeof, n);
   ref_init_kernel<<<1, 1, 0, s>>>(d_pool, d_ctr, n, min_leaf, opt.max_tree_depth, d_fresh[0], d_active[0]);
   RB_CUDA(cudaGetLastError());
@@ -550,13 +572,13 @@ int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s) {
       // ---- up to three partition attempts (nanort.h:1827-1857)
       for (int axis = 0; axis < 3; axis++) {
         ref_count_kernel<<<grid_n, 256, 0, s>>>(d_pool, d_nodeof, d_idx[which], dB, dC, n, level, axis, d_cut,
-                                                d_state, d_cnt);
+                                                d_state, d_cnt, pred_mul);
         ref_decide_kernel<<<(n_active + 255) / 256, 256, 0, s>>>(d_pool, d_active[cur], n_active, axis, d_cnt, d_state);
       }
       RB_CUDA(cudaGetLastError());
       // ---- std::partition's element order
       ref_flags_kernel<<<grid_n1, 256, 0, s>>>(d_pool, d_nodeof, d_idx[which], dB, dC, n, level, d_cut, d_state, d_mf,
-                                               d_mt);
+                                               d_mt, pred_mul);
       RB_CHECK(exclusive_scan_u32_async(d_mf, d_smf, n + 1, d_scratch, s));
       RB_CHECK(exclusive_scan_u32_async(d_mt, d_smt, n + 1, d_scratch, s));
       ref_compact_kernel<<<grid_n, 256, 0, s>>>(d_mf, d_mt, d_smf, d_smt, n, d_mfl, d_mtl);

@@ -99,6 +99,9 @@ struct Accel {
   float *d_verts = nullptr;  // tightly packed float3 (stride 12)
   size_t n_verts = 0;
   uint32_t *d_faces = nullptr;
+  // when set, the primitives of this accel are n_prims axis-aligned boxes (6 floats each: bmin, bmax) instead of
+  // triangles -- the top-level tree of a two-level scene; such an accel has no private traversal layout
+  float *d_prim_boxes = nullptr;
   // device: private traversal layout
   WideNode *d_wide = nullptr;
   PackedTri *d_tris = nullptr;

@@ -1,0 +1,986 @@
+// Two-level scene: instances of bottom-level accels under a top-level tree (sm_100a, --fmad=false).
+//
+// Replaces (file:line under /root/reference):
+//   nanosg::Node::Update                      examples/nanosg/nanosg.h:400-445   instance_setup_kernel
+//   Matrix::Inverse / Mult / MultV            examples/nanosg/nanosg.h:92-222    mat_inverse / multv
+//   XformBoundingBox                          examples/nanosg/nanosg.h:241-299   instance_setup_kernel
+//   nanosg::Scene::Commit (top-level Build)   examples/nanosg/nanosg.h:706-755   nrt_scene_commit (build.cu / build_ref.cu
+//                                                                                 over box primitives)
+//   BVHAccel::ListNodeIntersections +
+//   TestLeafNodeIntersections                 nanort.h:2558-2692                 scene_list_kernel
+//   NodeBBoxIntersector::Intersect            examples/nanosg/nanosg.h:597-637   raw_box()
+//   nanosg::Scene::Traverse                   examples/nanosg/nanosg.h:779-875   scene_list_kernel / scene_fast_kernel
+//
+// Two kernels.  scene_list_kernel is the reference's algorithm verbatim, one thread per ray: collect the (at most 64)
+// nearest instance boxes in a max-heap that follows libstdc++'s push_heap / pop_heap sift rules, visit them nearest
+// first, walk each instance's nanort-layout tree in the reference's order.  scene_fast_kernel is the production path:
+// persistent warps, one pass over the top-level tree (sub-trees that start behind the current nearest hit are
+// skipped), each candidate instance traversed with the 64-byte child-pair nodes exactly like traverse_fast2_kernel.
+// Both compute the local ray, the world hit point and the world distance with the reference's operation order, so a
+// hit record is bit-identical to the reference's whenever both pick the same (instance, triangle); the pick itself
+// can differ only between candidates at exactly the same world distance.  A ray that pierces more than 64 instance
+// boxes (the reference then drops the farthest boxes) or whose direction is not unit length (the reference's answer
+// then depends on its visiting order) is re-run by the list kernel.
+#include <float.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "trav_common.cuh"
+
+namespace nrt {
+
+namespace {
+
+constexpr int kMaxNodeHits = 64;  // kMaxIntersections, nanosg.h:787
+constexpr int kNoLeaf = kEmptyLeaf;
+
+// m[r][k] for r = 0..3, k = 0..2 (the only entries MultV reads), flat index 3 r + k, as three float4
+struct Mat43 {
+  float4 a, b, c;
+};
+
+struct InstanceDev {
+  Mat43 inv;    // world -> local, points
+  Mat43 inv33;  // world -> local, directions
+  Mat43 xf;     // local -> world
+  float bmin[3], bmax[3];  // world box
+  uint32_t pad[2];
+  const WideNode *wide;
+  const PackedTri *tris;
+  const Node40 *nodes;
+  uint64_t pad2;
+};
+static_assert(sizeof(InstanceDev) == 208, "InstanceDev");
+
+struct SceneDev {
+  const Node40 *top_nodes;
+  const uint32_t *top_idx;
+  const InstanceDev *inst;
+};
+
+struct SceneHit32 {
+  float u, v, t;
+  uint32_t prim_id, node_id;
+  float P[3];
+};
+static_assert(sizeof(SceneHit32) == 32, "nrt_scene_hit");
+
+// t[k] = ((m[0][k] v0 + m[1][k] v1) + m[2][k] v2) + m[3][k]   (Matrix::MultV, nanosg.h:214-222)
+__device__ __forceinline__ void multv(const Mat43 &m, float x, float y, float z, float &ox, float &oy, float &oz) {
+  ox = ((m.a.x * x + m.a.w * y) + m.b.z * z) + m.c.y;
+  oy = ((m.a.y * x + m.b.x * y) + m.b.w * z) + m.c.z;
+  oz = ((m.a.z * x + m.b.y * y) + m.c.x * z) + m.c.w;
+}
+
+__device__ __forceinline__ Mat43 load_mat(const Mat43 *p) {
+  Mat43 m;
+  const float4 *q = reinterpret_cast<const float4 *>(p);
+  m.a = __ldg(q);
+  m.b = __ldg(q + 1);
+  m.c = __ldg(q + 2);
+  return m;
+}
+
+// ---- instance setup ------------------------------------------------------------------------------------------
+// Cramer's-rule inverse in the reference's operation order.  Pair products, then for every element
+// (p0 s0 + p1 s1 + p2 s2) - (q0 s0' + q1 s1' + q2 s2'); the tables hold {pair index, source index}.  The very last
+// term of element 15 reads source 0 where the rule has source 10 -- the reference does (nanosg.h:173); only m[3][3]
+// depends on it and MultV never reads that entry.
+__constant__ uint8_t kPairs[2][12][2] = {
+    {{10, 15}, {11, 14}, {9, 15}, {11, 13}, {9, 14}, {10, 13}, {8, 15}, {11, 12}, {8, 14}, {10, 12}, {8, 13}, {9, 12}},
+    {{2, 7}, {3, 6}, {1, 7}, {3, 5}, {1, 6}, {2, 5}, {0, 7}, {3, 4}, {0, 6}, {2, 4}, {0, 5}, {1, 4}}};
+__constant__ uint8_t kCof[16][2][3][2] = {
+    {{{0, 5}, {3, 6}, {4, 7}}, {{1, 5}, {2, 6}, {5, 7}}},
+    {{{1, 4}, {6, 6}, {9, 7}}, {{0, 4}, {7, 6}, {8, 7}}},
+    {{{2, 4}, {7, 5}, {10, 7}}, {{3, 4}, {6, 5}, {11, 7}}},
+    {{{5, 4}, {8, 5}, {11, 6}}, {{4, 4}, {9, 5}, {10, 6}}},
+    {{{1, 1}, {2, 2}, {5, 3}}, {{0, 1}, {3, 2}, {4, 3}}},
+    {{{0, 0}, {7, 2}, {8, 3}}, {{1, 0}, {6, 2}, {9, 3}}},
+    {{{3, 0}, {6, 1}, {11, 3}}, {{2, 0}, {7, 1}, {10, 3}}},
+    {{{4, 0}, {9, 1}, {10, 2}}, {{5, 0}, {8, 1}, {11, 2}}},
+    {{{0, 13}, {3, 14}, {4, 15}}, {{1, 13}, {2, 14}, {5, 15}}},
+    {{{1, 12}, {6, 14}, {9, 15}}, {{0, 12}, {7, 14}, {8, 15}}},
+    {{{2, 12}, {7, 13}, {10, 15}}, {{3, 12}, {6, 13}, {11, 15}}},
+    {{{5, 12}, {8, 13}, {11, 14}}, {{4, 12}, {9, 13}, {10, 14}}},
+    {{{2, 10}, {5, 11}, {1, 9}}, {{4, 11}, {0, 9}, {3, 10}}},
+    {{{8, 11}, {0, 8}, {7, 10}}, {{6, 10}, {9, 11}, {1, 8}}},
+    {{{6, 9}, {11, 11}, {3, 8}}, {{10, 11}, {2, 8}, {7, 9}}},
+    {{{10, 10}, {4, 8}, {9, 9}}, {{8, 9}, {11, 0}, {5, 8}}}};
+
+__device__ void mat_inverse(float m[16]) {  // m[4 r + c], in place
+  float src[16], pr[12], out[16];
+  for (int i = 0; i < 4; i++)
+    for (int c = 0; c < 4; c++) src[i + 4 * c] = m[4 * i + c];
+  for (int half = 0; half < 2; half++) {
+    for (int k = 0; k < 12; k++) pr[k] = src[kPairs[half][k][0]] * src[kPairs[half][k][1]];
+    for (int e = 8 * half; e < 8 * half + 8; e++) {
+      float acc[2];
+      for (int sgn = 0; sgn < 2; sgn++) {
+        const uint8_t(*t)[2] = kCof[e][sgn];
+        acc[sgn] = (pr[t[0][0]] * src[t[0][1]] + pr[t[1][0]] * src[t[1][1]]) + pr[t[2][0]] * src[t[2][1]];
+      }
+      out[e] = acc[0] - acc[1];
+    }
+  }
+  float det = ((src[0] * out[0] + src[1] * out[1]) + src[2] * out[2]) + src[3] * out[3];
+  det = 1.0f / det;
+  for (int e = 0; e < 16; e++) m[e] = out[e] * det;
+}
+
+__device__ __forceinline__ Mat43 to_mat43(const float m[16]) {
+  Mat43 r;
+  r.a = make_float4(m[0], m[1], m[2], m[4]);
+  r.b = make_float4(m[5], m[6], m[8], m[9]);
+  r.c = make_float4(m[10], m[12], m[13], m[14]);
+  return r;
+}
+
+// (b < a) ? b : a  and  (a < b) ? b : a : std::min / std::max as XformBoundingBox calls them
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+
+struct InstanceIn {  // host -> device
+  float xform[16];
+  float lbmin[3], lbmax[3];
+  uint32_t pad[2];
+  const WideNode *wide;
+  const PackedTri *tris;
+  const Node40 *nodes;
+  uint64_t pad2;
+};
+
+// Node::Update for scene roots: xform = identity x local; world box; inverse; inverse of the 3x3 part.
+// state76 (optional): the reference's member layout, see nrt_scene_instance_state.
+__global__ void instance_setup_kernel(const InstanceIn *__restrict__ in, uint32_t n, InstanceDev *__restrict__ out,
+                                      float *__restrict__ boxes6, float *__restrict__ state76) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const InstanceIn I = in[i];
+  float xf[16];
+  // Matrix::Mult(xform, identity, local): dst[i][j] = sum_k parent[k][j] * local[i][k], accumulated from 0
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      float acc = 0.0f;
+      for (int k = 0; k < 4; k++) acc += (k == c ? 1.0f : 0.0f) * I.xform[4 * r + k];
+      xf[4 * r + c] = acc;
+    }
+  const Mat43 X = to_mat43(xf);
+  float bmin[3], bmax[3];
+  for (int c = 0; c < 8; c++) {
+    float x, y, z;
+    multv(X, (c & 1) ? I.lbmax[0] : I.lbmin[0], (c & 2) ? I.lbmax[1] : I.lbmin[1], (c & 4) ? I.lbmax[2] : I.lbmin[2],
+          x, y, z);
+    if (c == 0) {
+      bmin[0] = bmax[0] = x;
+      bmin[1] = bmax[1] = y;
+      bmin[2] = bmax[2] = z;
+    } else {
+      bmin[0] = std_min(x, bmin[0]);
+      bmin[1] = std_min(y, bmin[1]);
+      bmin[2] = std_min(z, bmin[2]);
+      bmax[0] = std_max(x, bmax[0]);
+      bmax[1] = std_max(y, bmax[1]);
+      bmax[2] = std_max(z, bmax[2]);
+    }
+  }
+  float inv[16], inv33[16];
+  for (int e = 0; e < 16; e++) inv[e] = inv33[e] = xf[e];
+  mat_inverse(inv);
+  inv33[12] = inv33[13] = inv33[14] = 0.0f;
+  mat_inverse(inv33);
+  InstanceDev o;
+  o.inv = to_mat43(inv);
+  o.inv33 = to_mat43(inv33);
+  o.xf = X;
+  for (int k = 0; k < 3; k++) {
+    o.bmin[k] = bmin[k];
+    o.bmax[k] = bmax[k];
+    boxes6[6 * (size_t)i + k] = bmin[k];
+    boxes6[6 * (size_t)i + 3 + k] = bmax[k];
+  }
+  o.pad[0] = o.pad[1] = 0;
+  o.wide = I.wide;
+  o.tris = I.tris;
+  o.nodes = I.nodes;
+  o.pad2 = 0;
+  out[i] = o;
+  if (state76) {
+    float *s = state76 + 76 * (size_t)i;
+    for (int e = 0; e < 16; e++) {
+      s[e] = xf[e];
+      s[16 + e] = inv[e];
+      s[32 + e] = inv33[e];
+      s[48 + 4 * (e % 4) + e / 4] = inv33[e];  // transpose
+    }
+    for (int k = 0; k < 3; k++) {
+      s[64 + k] = I.lbmin[k];
+      s[67 + k] = I.lbmax[k];
+      s[70 + k] = bmin[k];
+      s[73 + k] = bmax[k];
+    }
+  }
+}
+
+// ---- shared per-ray pieces ------------------------------------------------------------------------------------
+struct WorldRay {
+  float ox, oy, oz, dx, dy, dz, min_t, max_t;
+};
+
+__device__ __forceinline__ WorldRay load_world(const Ray36 *rays, size_t i) {
+  const float *p = reinterpret_cast<const float *>(rays + i);
+  WorldRay w;
+  w.ox = __ldg(p + 0);
+  w.oy = __ldg(p + 1);
+  w.oz = __ldg(p + 2);
+  w.dx = __ldg(p + 3);
+  w.dy = __ldg(p + 4);
+  w.dz = __ldg(p + 5);
+  w.min_t = __ldg(p + 6);
+  w.max_t = __ldg(p + 7);
+  return w;
+}
+
+// safemax / safemin of the reference: (a > b) ? a : b, (a < b) ? a : b
+__device__ __forceinline__ float smax(float a, float b) { return (a > b) ? a : b; }
+__device__ __forceinline__ float smin(float a, float b) { return (a < b) ? a : b; }
+
+// NodeBBoxIntersector::Intersect: plain reciprocal direction, no range clamp, no widening
+__device__ __forceinline__ bool raw_box(const WorldRay &w, float rix, float riy, float riz, const float *bmin,
+                                        const float *bmax, float &tmin) {
+  const bool sx = w.dx < 0.0f, sy = w.dy < 0.0f, sz = w.dz < 0.0f;
+  const float lox = __ldg(bmin + 0), loy = __ldg(bmin + 1), loz = __ldg(bmin + 2);
+  const float hix = __ldg(bmax + 0), hiy = __ldg(bmax + 1), hiz = __ldg(bmax + 2);
+  const float tnx = ((sx ? hix : lox) - w.ox) * rix, tfx = ((sx ? lox : hix) - w.ox) * rix;
+  const float tny = ((sy ? hiy : loy) - w.oy) * riy, tfy = ((sy ? loy : hiy) - w.oy) * riy;
+  const float tnz = ((sz ? hiz : loz) - w.oz) * riz, tfz = ((sz ? loz : hiz) - w.oz) * riz;
+  tmin = smax(tnz, smax(tny, tnx));
+  const float tmax = smin(tfz, smin(tfy, tfx));
+  return tmin <= tmax;
+}
+
+// world distance of a local hit: P_local = o + t d; P = P_local . xform; t_world = |P - org|  (nanosg.h:832-848)
+__device__ __forceinline__ float world_hit(const Mat43 &xf, const WorldRay &w, float lox, float loy, float loz,
+                                           float ldx, float ldy, float ldz, float t, float &px, float &py, float &pz) {
+  const float lx = lox + t * ldx, ly = loy + t * ldy, lz = loz + t * ldz;
+  multv(xf, lx, ly, lz, px, py, pz);
+  const float ax = px - w.ox, ay = py - w.oy, az = pz - w.oz;
+  return sqrtf((ax * ax + ay * ay) + az * az);
+}
+
+__device__ __forceinline__ TraceOptions16 local_trace_options() {
+  TraceOptions16 o;
+  o.prim_ids_range[0] = 0;
+  o.prim_ids_range[1] = 0x7FFFFFFFu;
+  o.skip_prim_id = 0xFFFFFFFFu;
+  o.cull_back_face = 0;  // Scene::Traverse never forwards its flag (nanosg.h:800-829)
+  o.pad[0] = o.pad[1] = o.pad[2] = 0;
+  return o;
+}
+
+struct SceneBest {
+  float t, u, v, px, py, pz;
+  uint32_t prim, node;
+};
+
+__device__ __forceinline__ void store_scene_hit(SceneHit32 *hits, uint8_t *mask, size_t i, const SceneBest &b,
+                                                bool hit, float max_t) {
+  float4 r0, r1;
+  if (hit) {
+    r0 = make_float4(b.u, b.v, b.t, __uint_as_float(b.prim));
+    r1 = make_float4(__uint_as_float(b.node), b.px, b.py, b.pz);
+  } else {
+    r0 = make_float4(0.0f, 0.0f, max_t, __uint_as_float(0xFFFFFFFFu));
+    r1 = make_float4(__uint_as_float(0xFFFFFFFFu), 0.0f, 0.0f, 0.0f);
+  }
+  float4 *o = reinterpret_cast<float4 *>(hits + i);
+  o[0] = r0;
+  o[1] = r1;
+  if (mask) mask[i] = hit ? 1 : 0;
+}
+
+// ---- the reference's algorithm, one thread per ray ---------------------------------------------------------------
+// std::priority_queue<NodeHit, vector, NodeHitComparator>: comp(a, b) = a.t_min < b.t_min, top = farthest.
+// Sift rules of libstdc++'s __push_heap / __adjust_heap, so that entries with equal t_min leave in the same order.
+struct NodeHitHeap {
+  float t[kMaxNodeHits + 1];
+  uint32_t id[kMaxNodeHits + 1];
+  int n;
+  __device__ __forceinline__ void sift_up(int hole, float vt, uint32_t vid) {
+    int parent = (hole - 1) / 2;
+    while (hole > 0 && t[parent] < vt) {
+      t[hole] = t[parent];
+      id[hole] = id[parent];
+      hole = parent;
+      parent = (hole - 1) / 2;
+    }
+    t[hole] = vt;
+    id[hole] = vid;
+  }
+  __device__ __forceinline__ void push(float vt, uint32_t vid) {
+    n++;
+    sift_up(n - 1, vt, vid);
+  }
+  // the top moves to slot n - 1, the heap shrinks by one
+  __device__ __forceinline__ void pop() {
+    const int len = n - 1;
+    const float vt = t[len];
+    const uint32_t vid = id[len];
+    t[len] = t[0];
+    id[len] = id[0];
+    int hole = 0, child = 0;
+    while (child < (len - 1) / 2) {
+      child = 2 * (child + 1);
+      if (t[child] < t[child - 1]) child--;
+      t[hole] = t[child];
+      id[hole] = id[child];
+      hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+      child = 2 * (child + 1);
+      t[hole] = t[child - 1];
+      id[hole] = id[child - 1];
+      hole = child - 1;
+    }
+    n = len;
+    sift_up(hole, vt, vid);
+  }
+};
+
+constexpr int kListStack = 512;  // kMaxStackDepth (nanort.h:2613) == kNANORT_MAX_STACK_DEPTH
+
+__global__ void __launch_bounds__(128)
+    scene_list_kernel(SceneDev sc, const Ray36 *__restrict__ rays, size_t n, const uint32_t *__restrict__ subset,
+                      const unsigned long long *__restrict__ n_subset, SceneHit32 *__restrict__ hits,
+                      uint8_t *__restrict__ mask, uint32_t flags) {
+  if (n_subset) n = (size_t)*n_subset;
+  const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
+  const TraceOptions16 opt = local_trace_options();
+  for (size_t job = (size_t)blockIdx.x * blockDim.x + threadIdx.x; job < n; job += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = subset ? (size_t)subset[job] : job;
+    const WorldRay w = load_world(rays, i);
+    RayCtx c;
+    setup_ray(c, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, w.min_t, cpp03);
+    const float rix = 1.0f / w.dx, riy = 1.0f / w.dy, riz = 1.0f / w.dz;
+    NodeHitHeap heap;
+    heap.n = 0;
+    uint32_t stack[kListStack];
+    int sp = 0;
+    stack[0] = 0;
+    while (sp >= 0) {  // ListNodeIntersections: hit_t stays at ray.max_t
+      const Node40 *nd = sc.top_nodes + stack[sp];
+      sp--;
+      const float *f = reinterpret_cast<const float *>(nd);
+      float tn;
+      if (!slab(c, __ldg(f + 0), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3), __ldg(f + 4), __ldg(f + 5), w.min_t, w.max_t,
+                tn))
+        continue;
+      const uint32_t d0 = __ldg(&nd->data[0]), d1 = __ldg(&nd->data[1]);
+      if (__ldg(&nd->flag) == 0) {
+        const int axis = __ldg(&nd->axis);
+        const int sgn = axis == 0 ? c.sx : (axis == 1 ? c.sy : c.sz);
+        if (sp + 2 < kListStack) {
+          stack[++sp] = sgn ? d0 : d1;
+          stack[++sp] = sgn ? d1 : d0;
+        }
+        continue;
+      }
+      for (uint32_t k = 0; k < d0; k++) {
+        const uint32_t id = __ldg(sc.top_idx + d1 + k);
+        float tmin;
+        if (!raw_box(w, rix, riy, riz, sc.inst[id].bmin, sc.inst[id].bmax, tmin)) continue;
+        if (heap.n < kMaxNodeHits) {
+          heap.push(tmin, id);
+        } else if (tmin < heap.t[0]) {
+          heap.pop();
+          heap.push(tmin, id);
+        }
+      }
+    }
+    const int n_hits = heap.n;
+    for (int k = 0; k < n_hits; k++) heap.pop();  // in-place heap sort: slots 0..n_hits-1 now run nearest first
+
+    SceneBest best;
+    best.t = FLT_MAX;
+    best.node = 0xFFFFFFFFu;
+    bool has_hit = false;
+    for (int k = 0; k < n_hits; k++) {
+      if (best.t < heap.t[k]) continue;  // early cull (nanosg.h:803-807)
+      const uint32_t id = heap.id[k];
+      const InstanceDev *I = sc.inst + id;
+      const Mat43 minv = load_mat(&I->inv), minv33 = load_mat(&I->inv33);
+      float lox, loy, loz, ldx, ldy, ldz;
+      multv(minv, w.ox, w.oy, w.oz, lox, loy, loz);
+      multv(minv33, w.dx, w.dy, w.dz, ldx, ldy, ldz);
+      RayCtx lc;
+      setup_ray(lc, lox, loy, loz, ldx, ldy, ldz, 0.0f, cpp03);
+      Best lb;
+      lb.t = FLT_MAX;
+      lb.u = 0.0f;
+      lb.v = 0.0f;
+      lb.prim = 0xFFFFFFFFu;
+      float hit_t = FLT_MAX;
+      const Node40 *nodes = I->nodes;
+      const PackedTri *tris = I->tris;
+      sp = 0;
+      stack[0] = 0;
+      while (sp >= 0) {  // BVHAccel::Traverse in the reference's order (nanort.h:2526-2547)
+        const Node40 *nd = nodes + stack[sp];
+        sp--;
+        const float *f = reinterpret_cast<const float *>(nd);
+        float tn;
+        if (!slab(lc, __ldg(f + 0), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3), __ldg(f + 4), __ldg(f + 5), 0.0f, hit_t,
+                  tn))
+          continue;
+        const uint32_t d0 = __ldg(&nd->data[0]), d1 = __ldg(&nd->data[1]);
+        if (__ldg(&nd->flag) == 0) {
+          const int axis = __ldg(&nd->axis);
+          const int sgn = axis == 0 ? lc.sx : (axis == 1 ? lc.sy : lc.sz);
+          if (sp + 2 < kListStack) {
+            stack[++sp] = sgn ? d0 : d1;
+            stack[++sp] = sgn ? d1 : d0;
+          }
+        } else {
+          bool any = false;
+          for (uint32_t q = 0; q < d0; q++) {
+            const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)d1 + q);
+            if (tri_test(lc, opt, __ldg(t), __ldg(t + 1), __ldg(t + 2), lb)) any = true;
+          }
+          if (any) hit_t = lb.t;
+        }
+      }
+      if (!(lb.t < FLT_MAX)) continue;
+      const Mat43 mxf = load_mat(&I->xf);
+      float px, py, pz;
+      const float tw = world_hit(mxf, w, lox, loy, loz, ldx, ldy, ldz, lb.t, px, py, pz);
+      if (tw < best.t) {
+        best.t = tw;
+        best.u = lb.u;
+        best.v = lb.v;
+        best.prim = lb.prim;
+        best.node = id;
+        best.px = px;
+        best.py = py;
+        best.pz = pz;
+        has_hit = true;
+      }
+    }
+    store_scene_hit(hits, mask, i, best, has_hit, w.max_t);
+  }
+}
+
+// ---- production kernel ---------------------------------------------------------------------------------------------
+// Lane states: dead (ray < 0) | top-level walk (inst < 0) | inside an instance (inst >= 0, while-while over the
+// instance's WideNodes).  One outer iteration = refill, top-level steps until every walking lane has entered an
+// instance or finished, inner nodes, leaves, instance exits, retirement.
+constexpr int kTopStack = 64;   // the host falls back to the list kernel for deeper top-level trees
+constexpr int kSceneBlock = 128;
+
+template <int LOCAL_DEPTH>
+__global__ void __launch_bounds__(kSceneBlock, 5)
+    scene_fast_kernel(SceneDev sc, const Ray36 *__restrict__ rays, size_t n, SceneHit32 *__restrict__ hits,
+                      uint8_t *__restrict__ mask, uint32_t flags, unsigned long long *cursor,
+                      uint32_t *__restrict__ overflow, unsigned long long *overflow_count) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
+  const TraceOptions16 opt = local_trace_options();
+
+  long long ray_idx = -1;
+  bool exhausted = false;
+  WorldRay w;
+  RayCtx wc;             // top-level walk constants (safe inverse, signs)
+  float rix = 0.0f, riy = 0.0f, riz = 0.0f;
+  SceneBest nearest;
+  uint32_t tstk[kTopStack];
+  int tsp = 0;
+  uint32_t leaf_pos = 0, leaf_end = 0, n_boxes = 0;
+  // instance state
+  int inst = -1;
+  RayCtx c;
+  Best best;
+  const WideNode *wide = nullptr;
+  const PackedTri *tris = nullptr;
+  uint2 lstk[LOCAL_DEPTH];
+  int sp = 0, cur = kNoLeaf, leaf = kNoLeaf;
+
+  auto push = [&](int ref, float t) {
+    if (sp < LOCAL_DEPTH) lstk[sp] = make_uint2((uint32_t)ref, __float_as_uint(t));
+    sp++;
+  };
+  auto pop = [&]() -> int {
+    while (sp > 0) {
+      --sp;
+      if (sp >= LOCAL_DEPTH) continue;
+      const uint2 e = lstk[sp];
+      if (__uint_as_float(e.y) <= best.t) return (int)e.x;
+    }
+    return kNoLeaf;
+  };
+
+  for (;;) {
+    // ---- replace retired rays
+    const unsigned dead = __ballot_sync(FULL_MASK, ray_idx < 0);
+    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= 8)) {
+      const int cnt = __popc(dead);
+      const int leader = __ffs(dead) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(cursor, (unsigned long long)cnt);
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
+      if (ray_idx < 0) {
+        const unsigned long long mine = base + (unsigned long long)__popc(dead & lt_mask);
+        if (mine < (unsigned long long)n) {
+          w = load_world(rays, (size_t)mine);
+          setup_ray(wc, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, w.min_t, cpp03);
+          rix = 1.0f / w.dx;
+          riy = 1.0f / w.dy;
+          riz = 1.0f / w.dz;
+          nearest.t = FLT_MAX;
+          nearest.node = 0xFFFFFFFFu;
+          ray_idx = (long long)mine;
+          tstk[0] = 0;
+          tsp = 1;
+          leaf_pos = leaf_end = 0;
+          n_boxes = 0;
+          // Scene::Traverse compares world DISTANCES of hits with ray PARAMETERS of box entries (nanosg.h:803, 848):
+          // for a direction that is not unit length its answer depends on the visiting order, which only the list
+          // kernel reproduces.  Such a ray skips the walk and is handed over like a > 64-box ray.
+          const float len2 = (w.dx * w.dx + w.dy * w.dy) + w.dz * w.dz;
+          if (!(fabsf(len2 - 1.0f) <= 1e-5f)) {
+            tsp = 0;
+            n_boxes = (uint32_t)kMaxNodeHits + 1u;
+          }
+          inst = -1;
+          cur = leaf = kNoLeaf;
+        }
+      }
+    }
+    if (__all_sync(FULL_MASK, ray_idx < 0)) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- top-level walk
+    for (;;) {
+      const bool walking = ray_idx >= 0 && inst < 0 && (leaf_pos < leaf_end || tsp > 0);
+      if (!__any_sync(FULL_MASK, walking)) break;
+      if (!walking) continue;
+      if (leaf_pos < leaf_end) {
+        const uint32_t id = __ldg(sc.top_idx + leaf_pos);
+        leaf_pos++;
+        const InstanceDev *I = sc.inst + id;
+        float tmin;
+        if (!raw_box(w, rix, riy, riz, I->bmin, I->bmax, tmin)) continue;
+        n_boxes++;
+        if (nearest.t < tmin) continue;  // early cull (nanosg.h:803-807)
+        const Mat43 minv = load_mat(&I->inv), minv33 = load_mat(&I->inv33);
+        float lox, loy, loz, ldx, ldy, ldz;
+        multv(minv, w.ox, w.oy, w.oz, lox, loy, loz);
+        multv(minv33, w.dx, w.dy, w.dz, ldx, ldy, ldz);
+        setup_ray(c, lox, loy, loz, ldx, ldy, ldz, 0.0f, cpp03);
+        best.t = FLT_MAX;
+        best.u = 0.0f;
+        best.v = 0.0f;
+        best.prim = 0xFFFFFFFFu;
+        wide = I->wide;
+        tris = I->tris;
+        inst = (int)id;
+        sp = 0;
+        cur = 0;
+        leaf = kNoLeaf;
+      } else {
+        const Node40 *nd = sc.top_nodes + tstk[--tsp];
+        const float *f = reinterpret_cast<const float *>(nd);
+        const float lox = __ldg(f + 0), loy = __ldg(f + 1), loz = __ldg(f + 2);
+        const float hix = __ldg(f + 3), hiy = __ldg(f + 4), hiz = __ldg(f + 5);
+        float tn;
+        if (!slab(wc, lox, loy, loz, hix, hiy, hiz, w.min_t, w.max_t, tn)) continue;
+        // entry distance without the min_t clamp: every instance box below starts at or after it, and an instance
+        // whose box starts behind the nearest hit is never visited (same rule as the early cull above)
+        const float enx = ((wc.sx ? hix : lox) - wc.ox) * wc.ix;
+        const float eny = ((wc.sy ? hiy : loy) - wc.oy) * wc.iy;
+        const float enz = ((wc.sz ? hiz : loz) - wc.oz) * wc.iz;
+        if (fmaxf(enx, fmaxf(eny, enz)) > nearest.t) continue;
+        const uint32_t d0 = __ldg(&nd->data[0]), d1 = __ldg(&nd->data[1]);
+        if (__ldg(&nd->flag) == 0) {
+          const int axis = __ldg(&nd->axis);
+          const int sgn = axis == 0 ? wc.sx : (axis == 1 ? wc.sy : wc.sz);
+          if (tsp + 2 <= kTopStack) {
+            tstk[tsp++] = sgn ? d0 : d1;
+            tstk[tsp++] = sgn ? d1 : d0;
+          }
+        } else {
+          leaf_pos = d1;
+          leaf_end = d1 + d0;
+        }
+      }
+    }
+
+    // ---- instance: inner nodes
+    for (;;) {
+      const unsigned desc = __ballot_sync(FULL_MASK, cur >= 0);
+      if (desc == 0u) break;
+      if (__popc(desc) < 8 && __any_sync(FULL_MASK, leaf != kNoLeaf)) break;
+      if (cur >= 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
+        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        float t0, t1;
+        const bool h0 = slab(c, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, 0.0f, best.t, t0);
+        const bool h1 = slab(c, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, 0.0f, best.t, t1);
+        const bool both = h0 & h1;
+        const bool swap = t1 < t0;
+        const int nearr = swap ? q3.y : q3.x;
+        const int farr = swap ? q3.x : q3.y;
+        if (both) push(farr, swap ? t0 : t1);
+        int next = both ? nearr : (h0 ? q3.x : q3.y);
+        if (!(h0 | h1)) next = pop();
+        if (next < 0 && next != kNoLeaf && leaf == kNoLeaf) {
+          leaf = next;
+          next = pop();
+        }
+        cur = next;
+      }
+    }
+
+    // ---- instance: leaves
+    for (;;) {
+      if (!__any_sync(FULL_MASK, leaf != kNoLeaf)) break;
+      if (leaf != kNoLeaf) {
+        const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)(~leaf));
+        for (;;) {
+          const float4 a = __ldg(t), b = __ldg(t + 1), cc = __ldg(t + 2);
+          tri_test2(c, opt, a, b, cc, best);
+          if (__float_as_uint(b.w) != 0u) break;
+          t += 3;
+        }
+        leaf = kNoLeaf;
+        if (cur < 0 && cur != kNoLeaf) {
+          leaf = cur;
+          cur = pop();
+        }
+      }
+    }
+
+    // ---- instance exit: world distance of the local hit, keep the nearest
+    if (ray_idx >= 0 && inst >= 0 && cur == kNoLeaf && leaf == kNoLeaf) {
+      if (best.t < FLT_MAX) {
+        const InstanceDev *I = sc.inst + inst;
+        const Mat43 minv33 = load_mat(&I->inv33), mxf = load_mat(&I->xf);
+        float ldx, ldy, ldz, px, py, pz;
+        multv(minv33, w.dx, w.dy, w.dz, ldx, ldy, ldz);
+        const float tw = world_hit(mxf, w, c.ox, c.oy, c.oz, ldx, ldy, ldz, best.t, px, py, pz);
+        if (tw < nearest.t) {
+          nearest.t = tw;
+          nearest.u = best.u;
+          nearest.v = best.v;
+          nearest.prim = best.prim;
+          nearest.node = (uint32_t)inst;
+          nearest.px = px;
+          nearest.py = py;
+          nearest.pz = pz;
+        }
+      }
+      inst = -1;
+    }
+
+    // ---- retire
+    if (ray_idx >= 0 && inst < 0 && tsp == 0 && leaf_pos >= leaf_end) {
+      store_scene_hit(hits, mask, (size_t)ray_idx, nearest, nearest.node != 0xFFFFFFFFu, w.max_t);
+      if (n_boxes > (uint32_t)kMaxNodeHits) {  // the reference keeps only the 64 nearest boxes: redo exactly
+        const unsigned long long slot = atomicAdd(overflow_count, 1ull);
+        overflow[slot] = (uint32_t)ray_idx;
+      }
+      ray_idx = -1;
+    }
+  }
+}
+
+}  // namespace
+
+// ---- scene object -------------------------------------------------------------------------------------------------
+struct Scene {
+  int device = 0;
+  uint32_t n = 0;
+  Accel *top = nullptr;  // box-primitive accel: d_nodes / d_indices / d_prim_boxes
+  InstanceDev *d_inst = nullptr;
+  float *d_state = nullptr;  // 76 floats per instance
+  uint32_t max_blas_depth = 0;
+  uint32_t *d_overflow = nullptr;
+  size_t overflow_cap = 0;
+  unsigned long long *d_counters = nullptr;  // [0..15] cursor ring, [16] overflow count
+  std::atomic<uint32_t> ring{0};
+  cudaStream_t stream = nullptr;
+  void *d_rays = nullptr, *d_hits = nullptr, *d_mask = nullptr;
+  size_t stage = 0;
+  std::mutex mu;
+};
+
+static void scene_destroy(Scene *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->top) {
+    cudaFree(s->top->d_nodes);
+    cudaFree(s->top->d_indices);
+    cudaFree(s->top->d_prim_boxes);
+    delete s->top;
+  }
+  cudaFree(s->d_inst);
+  cudaFree(s->d_state);
+  cudaFree(s->d_overflow);
+  cudaFree(s->d_counters);
+  cudaFree(s->d_rays);
+  cudaFree(s->d_hits);
+  cudaFree(s->d_mask);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_hits, uint8_t *d_mask, uint32_t flags,
+                        cudaStream_t s) {
+  if (n == 0) return NRT_OK;
+  if (n > 0xFFFFFFFFull) {
+    set_error("nrt_scene_traverse: more than 2^32-1 rays in one call");
+    return NRT_ERR_INVALID;
+  }
+  const SceneDev dev{sc->top->d_nodes, sc->top->d_indices, sc->d_inst};
+  const bool list_only = (flags & NRT_TRAVERSE_CONFORMANCE) != 0 ||
+                         sc->top->stats.max_tree_depth + 2 > (uint32_t)kTopStack;
+  const int sms = device_sm_count(sc->device);
+  if (list_only) {
+    const size_t blocks = std::min<size_t>((n + 127) / 128, (size_t)sms * 32);
+    scene_list_kernel<<<(unsigned)blocks, 128, 0, s>>>(dev, d_rays, n, nullptr, nullptr, d_hits, d_mask, flags);
+    NRT_CUDA(cudaGetLastError());
+    return NRT_OK;
+  }
+  {
+    std::lock_guard<std::mutex> lock(sc->mu);
+    if (sc->overflow_cap < n) {  // grows rarely; the free synchronises with launches still using the old list
+      cudaFree(sc->d_overflow);
+      sc->d_overflow = nullptr;
+      sc->overflow_cap = 0;
+      NRT_CUDA(cudaMalloc(&sc->d_overflow, sizeof(uint32_t) * n));
+      sc->overflow_cap = n;
+    }
+  }
+  unsigned long long *cursor = sc->d_counters + (sc->ring.fetch_add(1) & 15u);
+  unsigned long long *ovf = sc->d_counters + 16;
+  NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+  NRT_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned long long), s));
+  size_t grid = (size_t)sms * 5;
+  const size_t need = ((n + 31) / 32 + 3) / 4;
+  if (grid > need) grid = need;
+  if (sc->max_blas_depth + 2 > 48)
+    scene_fast_kernel<512><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
+                                                                  sc->d_overflow, ovf);
+  else
+    scene_fast_kernel<48><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
+                                                                 sc->d_overflow, ovf);
+  NRT_CUDA(cudaGetLastError());
+  // rays that pierced more than 64 instance boxes (device-side count, usually zero)
+  scene_list_kernel<<<(unsigned)std::min<size_t>((n + 127) / 128, (size_t)sms * 4), 128, 0, s>>>(
+      dev, d_rays, n, sc->d_overflow, ovf, d_hits, d_mask, flags);
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+}  // namespace nrt
+
+using namespace nrt;
+
+extern "C" {
+
+int nrt_scene_commit(const nrt_instance *instances, uint32_t n_instances, uint32_t flags, nrt_scene **out) {
+  if (!out) {
+    set_error("nrt_scene_commit: out is NULL");
+    return NRT_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (!instances || n_instances == 0) {  // Scene::Commit refuses an empty scene (nanosg.h:708-711)
+    set_error("nrt_scene_commit: empty scene");
+    return NRT_ERR_INVALID;
+  }
+  for (uint32_t i = 0; i < n_instances; i++) {
+    const Accel *a = reinterpret_cast<const Accel *>(instances[i].accel);
+    if (!a || !a->d_wide || !a->d_nodes) {
+      set_error("nrt_scene_commit: instance without a built accel");
+      return NRT_ERR_INVALID;
+    }
+    if (a->device != reinterpret_cast<const Accel *>(instances[0].accel)->device) {
+      set_error("nrt_scene_commit: instances live on different devices");
+      return NRT_ERR_INVALID;
+    }
+  }
+  Scene *sc = new (std::nothrow) Scene();
+  if (!sc) return NRT_ERR_NOMEM;
+  sc->device = reinterpret_cast<const Accel *>(instances[0].accel)->device;
+  sc->n = n_instances;
+  int rc = NRT_OK;
+  InstanceIn *d_in = nullptr;
+  auto fail = [&](int code) {
+    cudaFree(d_in);
+    scene_destroy(sc);
+    return code;
+  };
+  cudaError_t e = cudaSetDevice(sc->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 32 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(sc->d_counters, 0, 32 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&sc->d_inst, sizeof(InstanceDev) * (size_t)n_instances);
+  if (e == cudaSuccess) e = cudaMalloc(&sc->d_state, sizeof(float) * 76 * (size_t)n_instances);
+  if (e == cudaSuccess) e = cudaMalloc(&d_in, sizeof(InstanceIn) * (size_t)n_instances);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "nrt_scene_commit allocations", __FILE__, __LINE__));
+  sc->top = new (std::nothrow) Accel();
+  if (!sc->top) return fail(NRT_ERR_NOMEM);
+  sc->top->device = sc->device;
+  sc->top->n_prims = n_instances;
+  sc->top->options = default_build_options();
+  sc->top->options.min_leaf_primitives = 1;  // nanosg.h:731-732
+  e = cudaMalloc(&sc->top->d_prim_boxes, sizeof(float) * 6 * (size_t)n_instances);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "nrt_scene_commit boxes", __FILE__, __LINE__));
+  {
+    std::vector<InstanceIn> h(n_instances);
+    for (uint32_t i = 0; i < n_instances; i++) {
+      const Accel *a = reinterpret_cast<const Accel *>(instances[i].accel);
+      memset(&h[i], 0, sizeof(InstanceIn));
+      memcpy(h[i].xform, instances[i].xform, sizeof(float) * 16);
+      for (int k = 0; k < 3; k++) {  // BVHAccel::BoundingBox = the root node's box (nanort.h:792-804)
+        h[i].lbmin[k] = a->root_bmin[k];
+        h[i].lbmax[k] = a->root_bmax[k];
+      }
+      h[i].wide = a->d_wide;
+      h[i].tris = a->d_tris;
+      h[i].nodes = a->d_nodes;
+      sc->max_blas_depth = std::max(sc->max_blas_depth, a->stats.max_tree_depth);
+    }
+    e = cudaMemcpyAsync(d_in, h.data(), sizeof(InstanceIn) * (size_t)n_instances, cudaMemcpyHostToDevice, sc->stream);
+    if (e == cudaSuccess) {
+      instance_setup_kernel<<<(n_instances + 127) / 128, 128, 0, sc->stream>>>(d_in, n_instances, sc->d_inst,
+                                                                              sc->top->d_prim_boxes, sc->d_state);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc->stream);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "nrt_scene_commit instance setup", __FILE__, __LINE__));
+  }
+  rc = (flags & NRT_BUILD_REFERENCE_TREE)
+           ? build_reference_tree_on_device(sc->top, !(flags & NRT_BUILD_REFERENCE_CPP03_ORDER), sc->stream)
+           : build_on_device(sc->top, sc->stream);
+  if (rc == NRT_OK) {
+    e = cudaStreamSynchronize(sc->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "nrt_scene_commit build", __FILE__, __LINE__);
+  }
+  if (rc != NRT_OK) return fail(rc);
+  cudaFree(d_in);
+  *out = reinterpret_cast<nrt_scene *>(sc);
+  return NRT_OK;
+}
+
+void nrt_scene_free(nrt_scene *s) { scene_destroy(reinterpret_cast<Scene *>(s)); }
+
+int nrt_scene_bounding_box(const nrt_scene *s, float bmin[3], float bmax[3]) {
+  if (!s || !bmin || !bmax) {
+    set_error("nrt_scene_bounding_box: NULL argument");
+    return NRT_ERR_INVALID;
+  }
+  const Scene *sc = reinterpret_cast<const Scene *>(s);
+  for (int k = 0; k < 3; k++) {
+    bmin[k] = sc->top->root_bmin[k];
+    bmax[k] = sc->top->root_bmax[k];
+  }
+  return NRT_OK;
+}
+
+int nrt_scene_nodes(nrt_scene *s, const void **nodes_40B, size_t *n_nodes, const uint32_t **indices,
+                    size_t *n_indices) {
+  if (!s) {
+    set_error("nrt_scene_nodes: NULL scene");
+    return NRT_ERR_INVALID;
+  }
+  Scene *sc = reinterpret_cast<Scene *>(s);
+  Accel *a = sc->top;
+  std::lock_guard<std::mutex> lock(sc->mu);
+  if (!a->mirrors_valid) {
+    NRT_CUDA(cudaSetDevice(sc->device));
+    a->h_nodes.resize(a->n_nodes);
+    a->h_indices.resize(a->n_prims);
+    NRT_CUDA(cudaMemcpy(a->h_nodes.data(), a->d_nodes, sizeof(Node40) * a->n_nodes, cudaMemcpyDeviceToHost));
+    NRT_CUDA(cudaMemcpy(a->h_indices.data(), a->d_indices, sizeof(uint32_t) * a->n_prims, cudaMemcpyDeviceToHost));
+    a->mirrors_valid = true;
+  }
+  if (nodes_40B) *nodes_40B = a->h_nodes.data();
+  if (n_nodes) *n_nodes = a->h_nodes.size();
+  if (indices) *indices = a->h_indices.data();
+  if (n_indices) *n_indices = a->h_indices.size();
+  return NRT_OK;
+}
+
+int nrt_scene_instance_state(const nrt_scene *s, uint32_t instance, float out76[76]) {
+  const Scene *sc = reinterpret_cast<const Scene *>(s);
+  if (!sc || !out76 || instance >= sc->n) {
+    set_error("nrt_scene_instance_state: bad argument");
+    return NRT_ERR_INVALID;
+  }
+  NRT_CUDA(cudaSetDevice(sc->device));
+  NRT_CUDA(cudaMemcpy(out76, sc->d_state + 76 * (size_t)instance, sizeof(float) * 76, cudaMemcpyDeviceToHost));
+  return NRT_OK;
+}
+
+int nrt_scene_traverse_device(const nrt_scene *s, const void *d_rays_36B, size_t n_rays, void *d_hits_32B,
+                              uint8_t *d_hit_mask, uint32_t flags, void *stream) {
+  if (!s || (n_rays && (!d_rays_36B || !d_hits_32B))) {
+    set_error("nrt_scene_traverse_device: NULL argument");
+    return NRT_ERR_INVALID;
+  }
+  Scene *sc = const_cast<Scene *>(reinterpret_cast<const Scene *>(s));
+  NRT_CUDA(cudaSetDevice(sc->device));
+  return scene_launch(sc, static_cast<const Ray36 *>(d_rays_36B), n_rays, static_cast<SceneHit32 *>(d_hits_32B),
+                      d_hit_mask, flags, static_cast<cudaStream_t>(stream));
+}
+
+int nrt_scene_traverse(const nrt_scene *s, const void *rays_36B, size_t n_rays, void *hits_32B, uint8_t *hit_mask,
+                       uint32_t flags) {
+  if (!s || (n_rays && (!rays_36B || !hits_32B))) {
+    set_error("nrt_scene_traverse: NULL argument");
+    return NRT_ERR_INVALID;
+  }
+  if (n_rays == 0) return NRT_OK;
+  Scene *sc = const_cast<Scene *>(reinterpret_cast<const Scene *>(s));
+  NRT_CUDA(cudaSetDevice(sc->device));
+  const size_t kChunk = (size_t)1 << 20;
+  const size_t chunk = std::min(n_rays, kChunk);
+  // one caller at a time on the staging buffers (Scene::Traverse is const and thread-safe in the reference)
+  static std::mutex host_mu;
+  std::lock_guard<std::mutex> lock(host_mu);
+  if (sc->stage < chunk) {
+    cudaFree(sc->d_rays);
+    cudaFree(sc->d_hits);
+    cudaFree(sc->d_mask);
+    sc->d_rays = sc->d_hits = sc->d_mask = nullptr;
+    sc->stage = 0;
+    NRT_CUDA(cudaMalloc(&sc->d_rays, chunk * sizeof(Ray36)));
+    NRT_CUDA(cudaMalloc(&sc->d_hits, chunk * sizeof(SceneHit32)));
+    NRT_CUDA(cudaMalloc(&sc->d_mask, chunk));
+    sc->stage = chunk;
+  }
+  const char *src = static_cast<const char *>(rays_36B);
+  char *dst = static_cast<char *>(hits_32B);
+  for (size_t done = 0; done < n_rays; done += chunk) {
+    const size_t m = std::min(chunk, n_rays - done);
+    NRT_CUDA(cudaMemcpyAsync(sc->d_rays, src + done * sizeof(Ray36), m * sizeof(Ray36), cudaMemcpyHostToDevice,
+                             sc->stream));
+    int rc = scene_launch(sc, static_cast<const Ray36 *>(sc->d_rays), m, static_cast<SceneHit32 *>(sc->d_hits),
+                          static_cast<uint8_t *>(sc->d_mask), flags, sc->stream);
+    if (rc != NRT_OK) return rc;
+    NRT_CUDA(cudaMemcpyAsync(dst + done * sizeof(SceneHit32), sc->d_hits, m * sizeof(SceneHit32),
+                             cudaMemcpyDeviceToHost, sc->stream));
+    if (hit_mask) NRT_CUDA(cudaMemcpyAsync(hit_mask + done, sc->d_mask, m, cudaMemcpyDeviceToHost, sc->stream));
+    NRT_CUDA(cudaStreamSynchronize(sc->stream));
+  }
+  return NRT_OK;
+}
+
+}  // extern "C"

@@ -204,6 +204,57 @@ def instanced(copies_x=10, copies_z=10):
     return np.concatenate(vs).astype(np.float32), np.concatenate(fs).astype(np.uint32)
 
 
+def xform(translate=(0, 0, 0), scale=(1, 1, 1), yaw=0.0, pitch=0.0):
+    """4x4 float32 in the reference scene graph's convention (examples/nanosg/nanosg.h:214-222): row-vector
+    form, p' = p . M, translation in row 3."""
+    cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    ry = np.array([[cy, 0, -sy], [0, 1, 0], [sy, 0, cy]])
+    rx = np.array([[1, 0, 0], [0, cp, sp], [0, -sp, cp]])
+    m = np.eye(4)
+    m[:3, :3] = np.diag(scale) @ rx @ ry
+    m[3, :3] = translate
+    return m.astype(np.float32)
+
+
+def instances_grid(copies_x=10, copies_z=10, base=None):
+    """Config 4 as a two-level scene: copies_x*copies_z translated instances of ONE config-2 sphere grid
+    (the same placement `instanced()` flattens)."""
+    v0, f0 = base if base is not None else sphere_grid()
+    out = []
+    for iz in range(copies_z):
+        for ix in range(copies_x):
+            off = ((ix - 0.5 * (copies_x - 1)) * 11.0, 0.0, (iz - 0.5 * (copies_z - 1)) * 11.0)
+            out.append((v0, f0, xform(translate=off)))
+    return out
+
+
+def instances_mixed(n=24, seed=11, tris_per_sphere=(9, 7)):
+    """Small two-level parity scene: n instances over three base meshes (two spheres of different
+    tessellation and the Cornell box) with translation, non-uniform scale and rotation; boxes overlap."""
+    a = uv_sphere(*tris_per_sphere, radius=1.0)
+    b = uv_sphere(13, 11, radius=0.7)
+    c = cornell()
+    bases = [a, b, (c[0] * np.float32(0.2), c[1])]
+    i = np.arange(n, dtype=np.int64)
+    r = [rand01(i, k, seed) for k in range(9)]
+    out = []
+    for k in range(n):
+        v, f = bases[k % 3]
+        t = ((r[0][k] - 0.5) * 12.0, (r[1][k] - 0.5) * 4.0, (r[2][k] - 0.5) * 12.0)
+        sc = (0.5 + 1.5 * r[3][k], 0.5 + 1.5 * r[4][k], 0.5 + 1.5 * r[5][k])
+        out.append((v, f, xform(t, sc, yaw=float(r[6][k]) * 6.2831853, pitch=(float(r[7][k]) - 0.5) * 1.5)))
+    return out
+
+
+def instances_row(n=80):
+    """n unit-ish spheres in a row along x plus exact duplicates: a ray down the row pierces more than the 64
+    boxes the reference keeps (nanosg.h:787) and meets exact box-entry ties."""
+    v, f = uv_sphere(9, 7, radius=0.45)
+    out = [(v, f, xform(translate=(float(k), 0.0, 0.0))) for k in range(n)]
+    out += [(v, f, xform(translate=(float(k), 0.0, 0.0))) for k in (3, 3, 10, 40)]  # coincident instances
+    return out
+
+
 def with_area_light(verts, faces, center, half_x, half_z):
     """Appends a downward-facing emissive quad (2 triangles, the LAST two faces) -- the mesh light the
     reference path tracer samples (examples/path_tracer/main.cc:323-392).  Returns (verts, faces,

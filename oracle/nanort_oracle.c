@@ -131,6 +131,9 @@ typedef struct {
   const unsigned char *verts;
   size_t stride;
   const uint32_t *faces;
+  /* box primitives (the two-level scene's top-level build): boxes[6*i] = bmin.xyz bmax.xyz; when set, the
+   * accessors below follow NodeBBoxGeometry / NodeBBoxPred (examples/nanosg/nanosg.h:511-573) instead */
+  const float *boxes;
 } orc_mesh;
 
 static inline const float *vtx(const orc_mesh *m, uint32_t i) {
@@ -138,6 +141,13 @@ static inline const float *vtx(const orc_mesh *m, uint32_t i) {
 }
 
 static void orc_prim_bbox(const orc_mesh *m, uint32_t prim, float bmin[3], float bmax[3]) {
+  if (m->boxes) {
+    for (int k = 0; k < 3; k++) {
+      bmin[k] = m->boxes[6 * (size_t)prim + k];
+      bmax[k] = m->boxes[6 * (size_t)prim + 3 + k];
+    }
+    return;
+  }
   const float *p = vtx(m, m->faces[3 * (size_t)prim]);
   for (int k = 0; k < 3; k++) bmin[k] = bmax[k] = p[k];
   for (int c = 1; c < 3; c++) {
@@ -151,6 +161,11 @@ static void orc_prim_bbox(const orc_mesh *m, uint32_t prim, float bmin[3], float
 
 static void orc_prim_bbox_center(const orc_mesh *m, uint32_t prim, float bmin[3], float bmax[3],
                                  float ctr[3]) {
+  if (m->boxes) {
+    orc_prim_bbox(m, prim, bmin, bmax);
+    for (int k = 0; k < 3; k++) ctr[k] = (bmax[k] + bmin[k]) / 2.0f;
+    return;
+  }
   const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
   const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
   const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
@@ -277,6 +292,10 @@ static void orc_find_cut(orc_bin *bins, uint32_t B, const float nmin[3], const f
 }
 
 static inline int orc_pred(const orc_mesh *m, uint32_t prim, int axis, float pos) {
+  if (m->boxes) {
+    const float *b = m->boxes + 6 * (size_t)prim;
+    return (b[axis] + b[3 + axis]) / 2.0f < pos;
+  }
   const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
   const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
   const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
@@ -455,14 +474,12 @@ static uint32_t orc_build_shallow_rec(build_ctx *c, orc_stats *st, node_vec *out
  * must hold n_prims entries.  Returns the node count, 0 when n_prims == 0
  * (reference Build returns false, nanort.h:1907-1909).
  */
-size_t orc_build(const float *verts, size_t stride, const uint32_t *faces, uint32_t n_prims,
-                 const orc_build_options *opts, uint32_t mode, orc_node **nodes_out,
-                 uint32_t *indices_out, orc_stats *stats_out) {
+static size_t orc_build_core(const orc_mesh *mesh, uint32_t n_prims, const orc_build_options *opts,
+                             uint32_t mode, orc_node **nodes_out, uint32_t *indices_out,
+                             orc_stats *stats_out) {
   build_ctx c;
   memset(&c, 0, sizeof(c));
-  c.mesh.verts = (const unsigned char *)verts;
-  c.mesh.stride = stride;
-  c.mesh.faces = faces;
+  c.mesh = *mesh;
   if (opts)
     c.opt = *opts;
   else
@@ -508,6 +525,21 @@ size_t orc_build(const float *verts, size_t stride, const uint32_t *faces, uint3
   *nodes_out = out.v;
   if (stats_out) *stats_out = st;
   return out.n;
+}
+
+size_t orc_build(const float *verts, size_t stride, const uint32_t *faces, uint32_t n_prims,
+                 const orc_build_options *opts, uint32_t mode, orc_node **nodes_out,
+                 uint32_t *indices_out, orc_stats *stats_out) {
+  orc_mesh m = {(const unsigned char *)verts, stride, faces, NULL};
+  return orc_build_core(&m, n_prims, opts, mode, nodes_out, indices_out, stats_out);
+}
+
+/* the same Build over axis-aligned boxes as primitives (Scene::Commit's top-level build with
+ * NodeBBoxGeometry / NodeBBoxPred, examples/nanosg/nanosg.h:722-737) */
+size_t orc_build_boxes(const float *boxes6, uint32_t n_prims, const orc_build_options *opts, uint32_t mode,
+                       orc_node **nodes_out, uint32_t *indices_out, orc_stats *stats_out) {
+  orc_mesh m = {NULL, 0, NULL, boxes6};
+  return orc_build_core(&m, n_prims, opts, mode, nodes_out, indices_out, stats_out);
 }
 
 void orc_free(void *p) { free(p); }
@@ -642,7 +674,7 @@ static inline int orc_tri(ray_state *s, const orc_mesh *m, uint32_t prim, float 
 int orc_traverse_one(const orc_node *nodes, const uint32_t *indices, const float *verts,
                      size_t stride, const uint32_t *faces, const orc_ray *ray,
                      const orc_trace_options *topt, int cpp11, orc_hit *hit, orc_counters *ctr) {
-  orc_mesh m = {(const unsigned char *)verts, stride, faces};
+  orc_mesh m = {(const unsigned char *)verts, stride, faces, NULL};
   orc_trace_options dflt;
   if (!topt) {
     orc_default_trace_options(&dflt);
@@ -788,7 +820,7 @@ size_t orc_traverse_batch(const orc_node *nodes, const uint32_t *indices, const 
  * (t,u,v) this primitive alone would report with t_inout = max_t. */
 int orc_test_prim(const float *verts, size_t stride, const uint32_t *faces, const orc_ray *ray,
                   const orc_trace_options *topt, int cpp11, uint32_t prim, orc_hit *out) {
-  orc_mesh m = {(const unsigned char *)verts, stride, faces};
+  orc_mesh m = {(const unsigned char *)verts, stride, faces, NULL};
   orc_trace_options dflt;
   if (!topt) {
     orc_default_trace_options(&dflt);
@@ -803,4 +835,350 @@ int orc_test_prim(const float *verts, size_t stride, const uint32_t *faces, cons
   out->v = s.v;
   out->prim_id = prim;
   return 1;
+}
+
+/* ====================================================================== two-level scene
+ * Restatement of the reference's scene-graph example (examples/nanosg/nanosg.h) for the instancing row:
+ *   orc_mat_inverse            Matrix::Inverse (Cramer's rule)          nanosg.h:92-184
+ *   orc_mat_mult / orc_multv   Matrix::Mult / Matrix::MultV             nanosg.h:203-222
+ *   orc_xform_bbox             XformBoundingBox                         nanosg.h:241-299
+ *   orc_sg_node_update         Node::Update                             nanosg.h:400-445
+ *   orc_build_boxes            Scene::Commit top-level Build            nanosg.h:722-737
+ *   orc_sg_list                BVHAccel::ListNodeIntersections + TestLeafNodeIntersections with
+ *                              NodeBBoxIntersector                      nanort.h:2558-2692, nanosg.h:592-660
+ *   orc_sg_traverse_one        Scene::Traverse                          nanosg.h:779-875
+ * Parity status: PINNED against oracle/_ref/libnanosg_ref*.so (tests/test_oracle_scene.py).
+ *
+ * Reference behaviours restated as they are (none is "fixed" here):
+ *   S1  Matrix::Inverse's last cofactor reads tsrc[0] where Cramer's rule has tsrc[10] (nanosg.h:173);
+ *       only m[3][3] is affected and MultV never reads it.
+ *   S2  Scene::Traverse builds trace_options.cull_back_face but calls the instance's Traverse with the
+ *       default options (nanosg.h:800-829): the flag has no effect.
+ *   S3  at most kMaxIntersections = 64 instance boxes (the nearest by box entry t) are considered per ray.
+ *   S4  the local ray is {min_t 0, max_t FLT_MAX}: the caller's min_t / max_t only gate the top-level walk.
+ */
+typedef struct {
+  float xform[4][4];   /* parent x local; parent is the identity for scene roots */
+  float inv[4][4];     /* world -> local */
+  float inv33[4][4];   /* same with the translation cleared first (directions) */
+  float invT33[4][4];  /* transpose of inv33 (normals) */
+  float lbmin[3], lbmax[3];
+  float xbmin[3], xbmax[3];
+} orc_sg_node; /* 76 floats */
+
+typedef struct {
+  const orc_node *nodes;
+  const uint32_t *indices;
+  const float *verts;
+  size_t stride;
+  const uint32_t *faces;
+} orc_sg_blas;
+
+typedef struct {
+  float u, v, t;
+  uint32_t prim_id, node_id;
+  float P[3];
+} orc_sg_hit; /* 32 B */
+
+/* pairs / cofactor tables of the Cramer's-rule inverse: every cofactor is
+ * (p0*s0 + p1*s1 + p2*s2) - (q0*s0' + q1*s1' + q2*s2') with p/q from the pair table */
+static const uint8_t kPairs[2][12][2] = {
+    {{10, 15}, {11, 14}, {9, 15}, {11, 13}, {9, 14}, {10, 13}, {8, 15}, {11, 12}, {8, 14}, {10, 12}, {8, 13}, {9, 12}},
+    {{2, 7}, {3, 6}, {1, 7}, {3, 5}, {1, 6}, {2, 5}, {0, 7}, {3, 4}, {0, 6}, {2, 4}, {0, 5}, {1, 4}}};
+/* [element][plus/minus][term] = {pair index, source index} */
+static const uint8_t kCof[16][2][3][2] = {
+    {{{0, 5}, {3, 6}, {4, 7}}, {{1, 5}, {2, 6}, {5, 7}}},
+    {{{1, 4}, {6, 6}, {9, 7}}, {{0, 4}, {7, 6}, {8, 7}}},
+    {{{2, 4}, {7, 5}, {10, 7}}, {{3, 4}, {6, 5}, {11, 7}}},
+    {{{5, 4}, {8, 5}, {11, 6}}, {{4, 4}, {9, 5}, {10, 6}}},
+    {{{1, 1}, {2, 2}, {5, 3}}, {{0, 1}, {3, 2}, {4, 3}}},
+    {{{0, 0}, {7, 2}, {8, 3}}, {{1, 0}, {6, 2}, {9, 3}}},
+    {{{3, 0}, {6, 1}, {11, 3}}, {{2, 0}, {7, 1}, {10, 3}}},
+    {{{4, 0}, {9, 1}, {10, 2}}, {{5, 0}, {8, 1}, {11, 2}}},
+    {{{0, 13}, {3, 14}, {4, 15}}, {{1, 13}, {2, 14}, {5, 15}}},
+    {{{1, 12}, {6, 14}, {9, 15}}, {{0, 12}, {7, 14}, {8, 15}}},
+    {{{2, 12}, {7, 13}, {10, 15}}, {{3, 12}, {6, 13}, {11, 15}}},
+    {{{5, 12}, {8, 13}, {11, 14}}, {{4, 12}, {9, 13}, {10, 14}}},
+    {{{2, 10}, {5, 11}, {1, 9}}, {{4, 11}, {0, 9}, {3, 10}}},
+    {{{8, 11}, {0, 8}, {7, 10}}, {{6, 10}, {9, 11}, {1, 8}}},
+    {{{6, 9}, {11, 11}, {3, 8}}, {{10, 11}, {2, 8}, {7, 9}}},
+    {{{10, 10}, {4, 8}, {9, 9}}, {{8, 9}, {11, 0} /* S1 */, {5, 8}}}};
+
+void orc_mat_inverse(float m[4][4]) {
+  float src[16], pr[12], out[16];
+  for (int i = 0; i < 4; i++)
+    for (int c = 0; c < 4; c++) src[i + 4 * c] = m[i][c];
+  for (int half = 0; half < 2; half++) {
+    for (int k = 0; k < 12; k++) pr[k] = src[kPairs[half][k][0]] * src[kPairs[half][k][1]];
+    for (int e = 8 * half; e < 8 * half + 8; e++) {
+      float acc[2];
+      for (int sgn = 0; sgn < 2; sgn++) {
+        const uint8_t(*t)[2] = kCof[e][sgn];
+        acc[sgn] = (pr[t[0][0]] * src[t[0][1]] + pr[t[1][0]] * src[t[1][1]]) + pr[t[2][0]] * src[t[2][1]];
+      }
+      out[e] = acc[0] - acc[1];
+    }
+  }
+  float det = ((src[0] * out[0] + src[1] * out[1]) + src[2] * out[2]) + src[3] * out[3];
+  det = 1.0f / det;
+  for (int e = 0; e < 16; e++) m[e / 4][e % 4] = out[e] * det;
+}
+
+static void orc_mat_mult(float dst[4][4], const float m0[4][4], const float m1[4][4]) {
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      float acc = 0.0f;
+      for (int k = 0; k < 4; k++) acc += m0[k][j] * m1[i][k];
+      dst[i][j] = acc;
+    }
+}
+
+static void orc_multv(float dst[3], const float m[4][4], const float v[3]) {
+  float t[3];
+  for (int k = 0; k < 3; k++) t[k] = ((m[0][k] * v[0] + m[1][k] * v[1]) + m[2][k] * v[2]) + m[3][k];
+  dst[0] = t[0];
+  dst[1] = t[1];
+  dst[2] = t[2];
+}
+
+static void orc_xform_bbox(float xbmin[3], float xbmax[3], const float bmin[3], const float bmax[3],
+                           const float m[4][4]) {
+  for (int i = 0; i < 8; i++) {
+    float c[3] = {(i & 1) ? bmax[0] : bmin[0], (i & 2) ? bmax[1] : bmin[1], (i & 4) ? bmax[2] : bmin[2]};
+    float x[3];
+    orc_multv(x, m, c);
+    for (int k = 0; k < 3; k++) {
+      if (i == 0) {
+        xbmin[k] = xbmax[k] = x[k];
+      } else {
+        xbmin[k] = stdmin(x[k], xbmin[k]);
+        xbmax[k] = stdmax(x[k], xbmax[k]);
+      }
+    }
+  }
+}
+
+/* Node::Update for a scene root: parent transform = identity */
+void orc_sg_node_update(orc_sg_node *nd, const float local_xform[16], const float lbmin[3], const float lbmax[3]) {
+  float ident[4][4], local[4][4];
+  memset(ident, 0, sizeof(ident));
+  for (int i = 0; i < 4; i++) ident[i][i] = 1.0f;
+  memcpy(local, local_xform, sizeof(local));
+  for (int k = 0; k < 3; k++) {
+    nd->lbmin[k] = lbmin[k];
+    nd->lbmax[k] = lbmax[k];
+  }
+  orc_mat_mult(nd->xform, ident, local);
+  orc_xform_bbox(nd->xbmin, nd->xbmax, nd->lbmin, nd->lbmax, nd->xform);
+  memcpy(nd->inv, nd->xform, sizeof(nd->inv));
+  orc_mat_inverse(nd->inv);
+  memcpy(nd->inv33, nd->xform, sizeof(nd->inv33));
+  nd->inv33[3][0] = nd->inv33[3][1] = nd->inv33[3][2] = 0.0f;
+  orc_mat_inverse(nd->inv33);
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) nd->invT33[j][i] = nd->inv33[i][j];
+}
+
+/* ---- std::priority_queue<NodeHit, vector, NodeHitComparator> as libstdc++ implements it
+ * (bits/stl_heap.h __push_heap / __adjust_heap); comp(a, b) = a.t_min < b.t_min, so the top is the
+ * farthest entry.  The order among equal t_min follows from these exact sift rules. */
+typedef struct {
+  float t_min, t_max;
+  uint32_t id;
+} sg_nodehit;
+
+static void heap_sift_up(sg_nodehit *h, int hole, int top, sg_nodehit v) {
+  int parent = (hole - 1) / 2;
+  while (hole > top && h[parent].t_min < v.t_min) {
+    h[hole] = h[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  h[hole] = v;
+}
+
+static void heap_push(sg_nodehit *h, int *n, sg_nodehit v) {
+  (*n)++;
+  heap_sift_up(h, *n - 1, 0, v);
+}
+
+static void heap_pop(sg_nodehit *h, int *n) { /* moves the top to h[*n - 1] and shrinks */
+  int len = *n - 1;
+  sg_nodehit v = h[len];
+  h[len] = h[0];
+  int hole = 0, child = 0;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (h[child].t_min < h[child - 1].t_min) child--;
+    h[hole] = h[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    h[hole] = h[child - 1];
+    hole = child - 1;
+  }
+  heap_sift_up(h, hole, 0, v);
+  *n = len;
+}
+
+/* first stage of Scene::Traverse: the (at most max_hits <= 128) nearest instance boxes, nearest first */
+int orc_sg_list(const orc_node *top, const uint32_t *top_idx, const orc_sg_node *sg, const orc_ray *ray,
+                int max_hits, int cpp11, float *tmin_out, float *tmax_out, uint32_t *ids_out) {
+  ray_state s;
+  for (int k = 0; k < 3; k++) {
+    s.org[k] = ray->org[k];
+    s.sign[k] = ray->dir[k] < 0.0f ? 1 : 0;
+    s.inv[k] = orc_safe_inverse(ray->dir[k], cpp11);
+  }
+  /* NodeBBoxIntersector::PrepareTraversal: plain reciprocal, no zero guard (nanosg.h:645-647) */
+  const float rinv[3] = {1.0f / ray->dir[0], 1.0f / ray->dir[1], 1.0f / ray->dir[2]};
+  sg_nodehit heap[129];
+  int nh = 0;
+  uint32_t stack[ORC_STACK];
+  int sp = 0;
+  stack[0] = 0;
+  while (sp >= 0) {
+    const orc_node *nd = &top[stack[sp]];
+    sp--;
+    if (!orc_slab(&s, nd, ray->min_t, ray->max_t)) continue; /* hit_t never shrinks here */
+    if (nd->flag == 0) {
+      int nearc = s.sign[nd->axis];
+      stack[++sp] = nd->data[1 - nearc];
+      stack[++sp] = nd->data[nearc];
+      continue;
+    }
+    for (uint32_t i = 0; i < nd->data[0]; i++) {
+      const uint32_t id = top_idx[nd->data[1] + i];
+      const orc_sg_node *b = &sg[id];
+      float tn[3], tf[3];
+      for (int k = 0; k < 3; k++) {
+        const float lo = s.sign[k] ? b->xbmax[k] : b->xbmin[k];
+        const float hi = s.sign[k] ? b->xbmin[k] : b->xbmax[k];
+        tn[k] = (lo - ray->org[k]) * rinv[k];
+        tf[k] = (hi - ray->org[k]) * rinv[k];
+      }
+      const float tmin = smax(tn[2], smax(tn[1], tn[0]));
+      const float tmax = smin(tf[2], smin(tf[1], tf[0]));
+      if (!(tmin <= tmax)) continue;
+      sg_nodehit v = {tmin, tmax, id};
+      if (nh < max_hits) {
+        heap_push(heap, &nh, v);
+      } else if (tmin < heap[0].t_min) {
+        heap_pop(heap, &nh);
+        heap_push(heap, &nh, v);
+      }
+    }
+  }
+  const int n = nh;
+  for (int i = 0; i < n; i++) { /* pop farthest first, store back to front */
+    const sg_nodehit topv = heap[0];
+    heap_pop(heap, &nh);
+    tmin_out[n - i - 1] = topv.t_min;
+    if (tmax_out) tmax_out[n - i - 1] = topv.t_max;
+    ids_out[n - i - 1] = topv.id;
+  }
+  return n;
+}
+
+int orc_sg_traverse_one(const orc_node *top, const uint32_t *top_idx, const orc_sg_node *sg,
+                        const orc_sg_blas *blas, const orc_ray *ray, int cpp11, orc_sg_hit *hit) {
+  float tmin[128];
+  uint32_t ids[128];
+  const int n = orc_sg_list(top, top_idx, sg, ray, 64, cpp11, tmin, NULL, ids);
+  float t_nearest = FLT_MAX;
+  int has_hit = 0;
+  for (int i = 0; i < n; i++) {
+    if (t_nearest < tmin[i]) continue;
+    const orc_sg_node *nd = &sg[ids[i]];
+    const orc_sg_blas *b = &blas[ids[i]];
+    orc_ray lr;
+    orc_multv(lr.org, nd->inv, ray->org);
+    orc_multv(lr.dir, nd->inv33, ray->dir);
+    lr.min_t = 0.0f;
+    lr.max_t = FLT_MAX;
+    lr.type = 0;
+    orc_hit lh;
+    if (!orc_traverse_one(b->nodes, b->indices, b->verts, b->stride, b->faces, &lr, NULL, cpp11, &lh, NULL))
+      continue;
+    float lp[3], wp[3];
+    for (int k = 0; k < 3; k++) lp[k] = lr.org[k] + lh.t * lr.dir[k];
+    orc_multv(wp, nd->xform, lp);
+    const float px = wp[0] - ray->org[0], py = wp[1] - ray->org[1], pz = wp[2] - ray->org[2];
+    const float t_world = sqrtf((px * px + py * py) + pz * pz);
+    if (t_world < t_nearest) {
+      t_nearest = t_world;
+      has_hit = 1;
+      hit->u = lh.u;
+      hit->v = lh.v;
+      hit->t = t_world;
+      hit->prim_id = lh.prim_id;
+      hit->node_id = ids[i];
+      hit->P[0] = wp[0];
+      hit->P[1] = wp[1];
+      hit->P[2] = wp[2];
+    }
+  }
+  return has_hit;
+}
+
+typedef struct {
+  const orc_node *top;
+  const uint32_t *top_idx;
+  const orc_sg_node *sg;
+  const orc_sg_blas *blas;
+  const orc_ray *rays;
+  size_t n_rays;
+  orc_sg_hit *hits;
+  uint8_t *mask;
+  int cpp11;
+  size_t *next;
+  pthread_mutex_t *mu;
+  size_t n_hits;
+} sg_job;
+
+static void *sg_worker(void *arg) {
+  sg_job *j = (sg_job *)arg;
+  for (;;) {
+    pthread_mutex_lock(j->mu);
+    size_t b = *j->next;
+    *j->next = b + 256;
+    pthread_mutex_unlock(j->mu);
+    if (b >= j->n_rays) break;
+    size_t e = b + 256 < j->n_rays ? b + 256 : j->n_rays;
+    for (size_t i = b; i < e; i++) {
+      orc_sg_hit h;
+      int hit = orc_sg_traverse_one(j->top, j->top_idx, j->sg, j->blas, &j->rays[i], j->cpp11, &h);
+      if (hit) {
+        j->hits[i] = h;
+        j->n_hits++;
+      }
+      if (j->mask) j->mask[i] = (uint8_t)hit;
+    }
+  }
+  return NULL;
+}
+
+/* Scene::Traverse over a batch; hits[i] is written only where mask[i] == 1 */
+size_t orc_sg_traverse_batch(const orc_node *top, const uint32_t *top_idx, const orc_sg_node *sg,
+                             const orc_sg_blas *blas, const orc_ray *rays, size_t n_rays, orc_sg_hit *hits,
+                             uint8_t *mask, int cpp11, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  size_t next = 0, total = 0;
+  sg_job jobs[256];
+  pthread_t th[256];
+  for (int t = 0; t < n_threads; t++) {
+    sg_job j = {top, top_idx, sg, blas, rays, n_rays, hits, mask, cpp11, &next, &mu, 0};
+    jobs[t] = j;
+  }
+  if (n_threads == 1) {
+    sg_worker(&jobs[0]);
+  } else {
+    for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, sg_worker, &jobs[t]);
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  }
+  for (int t = 0; t < n_threads; t++) total += jobs[t].n_hits;
+  return total;
 }

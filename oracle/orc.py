@@ -260,3 +260,163 @@ class Reference:
         r = self.lib.ref_traverse_one_f64(_p(verts), _p(faces), len(faces), _p(org), _p(dir), min_t, max_t,
                                           _p(out), _p(prim))
         return r, out, int(prim[0])
+
+
+# ------------------------------------------------------------------ two-level scene (examples/nanosg)
+SG_HIT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("t", "<f4"), ("prim_id", "<u4"), ("node_id", "<u4"),
+                         ("P", "<f4", (3,))])
+SG_NODE_DTYPE = np.dtype([("xform", "<f4", (4, 4)), ("inv", "<f4", (4, 4)), ("inv33", "<f4", (4, 4)),
+                          ("invT33", "<f4", (4, 4)), ("lbmin", "<f4", (3,)), ("lbmax", "<f4", (3,)),
+                          ("xbmin", "<f4", (3,)), ("xbmax", "<f4", (3,))])
+assert SG_HIT_DTYPE.itemsize == 32 and SG_NODE_DTYPE.itemsize == 76 * 4
+
+
+class _SgBlas(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("indices", C.c_void_p), ("verts", C.c_void_p), ("stride", C.c_size_t),
+                ("faces", C.c_void_p)]
+
+
+class PortScene:
+    """Port of nanosg::Scene: instances = [(verts, faces, xform4x4)], Commit() at construction.
+    Every instance builds its own bottom-level tree, like Node::Update does."""
+
+    def __init__(self, instances, cpp11=True, port=None):
+        self.port = port or Port()
+        L = self.port.lib
+        L.orc_build_boxes.restype = C.c_size_t
+        L.orc_build_boxes.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p),
+                                      C.c_void_p, C.c_void_p]
+        L.orc_sg_node_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_sg_list.restype = C.c_int
+        L.orc_sg_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+        L.orc_sg_traverse_batch.restype = C.c_size_t
+        L.orc_sg_traverse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        self.cpp11 = cpp11
+        mode = MODE_CPP11 if cpp11 else 0
+        n = len(instances)
+        self.sg = np.zeros(n, SG_NODE_DTYPE)
+        self.blas = []  # (nodes, indices, verts, faces) kept alive
+        self._blas_c = (_SgBlas * n)()
+        cache = {}
+        for i, (v, f, x) in enumerate(instances):
+            v = np.ascontiguousarray(v, np.float32)
+            f = np.ascontiguousarray(f, np.uint32)
+            key = (v.ctypes.data, f.ctypes.data, len(f))
+            if key not in cache:  # identical arrays give identical trees: build once
+                nodes, idx, _ = self.port.build(v, f, None, mode)
+                cache[key] = (nodes, idx, v, f)
+            nodes, idx, v, f = cache[key]
+            self.blas.append(cache[key])
+            self._blas_c[i] = _SgBlas(nodes.ctypes.data, idx.ctypes.data, v.ctypes.data, 12, f.ctypes.data)
+            x = np.ascontiguousarray(x, np.float32).reshape(16)
+            lb0 = np.ascontiguousarray(nodes["bmin"][0])
+            lb1 = np.ascontiguousarray(nodes["bmax"][0])
+            L.orc_sg_node_update(self.sg[i:i + 1].ctypes.data, _p(x), _p(lb0), _p(lb1))
+        boxes = np.ascontiguousarray(np.concatenate([self.sg["xbmin"], self.sg["xbmax"]], axis=1), np.float32)
+        self.top_idx = np.zeros(n, np.uint32)
+        out = C.c_void_p()
+        o = build_options(min_leaf_primitives=1)
+        nn = L.orc_build_boxes(_p(boxes), n, _p(o), mode, C.byref(out), _p(self.top_idx), None)
+        assert nn > 0
+        self.top = np.frombuffer((C.c_char * (nn * 40)).from_address(out.value), NODE_DTYPE).copy()
+        L.orc_free(out)
+
+    def list_node_intersections(self, ray, max_hits=64):
+        ray = np.ascontiguousarray(ray).reshape(1)
+        tmin, tmax, ids = np.zeros(128, np.float32), np.zeros(128, np.float32), np.zeros(128, np.uint32)
+        n = self.port.lib.orc_sg_list(_p(self.top), _p(self.top_idx), _p(self.sg), _p(ray), max_hits,
+                                      1 if self.cpp11 else 0, _p(tmin), _p(tmax), _p(ids))
+        return tmin[:n], tmax[:n], ids[:n]
+
+    def traverse(self, rays, threads=1):
+        rays = np.ascontiguousarray(rays)
+        n = len(rays)
+        hits, mask = np.zeros(n, SG_HIT_DTYPE), np.zeros(n, np.uint8)
+        self.port.lib.orc_sg_traverse_batch(_p(self.top), _p(self.top_idx), _p(self.sg),
+                                            C.addressof(self._blas_c), _p(rays), n, _p(hits), _p(mask),
+                                            1 if self.cpp11 else 0, threads)
+        return hits, mask
+
+
+class ReferenceScene:
+    """The unmodified nanosg::Scene (oracle/_ref/libnanosg_ref*.so)."""
+
+    @staticmethod
+    def available(cpp11=True):
+        return os.path.exists(os.path.join(HERE, "_ref", "libnanosg_ref.so" if cpp11 else "libnanosg_ref03.so"))
+
+    def __init__(self, instances, cpp11=True):
+        path = os.path.join(HERE, "_ref", "libnanosg_ref.so" if cpp11 else "libnanosg_ref03.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = L = C.CDLL(path)
+        L.refsg_create.restype = C.c_void_p
+        L.refsg_free.argtypes = [C.c_void_p]
+        L.refsg_add_node.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.refsg_commit.argtypes = [C.c_void_p]
+        L.refsg_bounding_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refsg_node_state.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.refsg_top_num_nodes.restype = C.c_size_t
+        L.refsg_top_num_nodes.argtypes = [C.c_void_p]
+        L.refsg_top_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refsg_node_num_nodes.restype = C.c_size_t
+        L.refsg_node_num_nodes.argtypes = [C.c_void_p, C.c_size_t]
+        L.refsg_node_copy.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.refsg_list_node_intersections.restype = C.c_int
+        L.refsg_list_node_intersections.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p]
+        L.refsg_traverse_batch.restype = C.c_size_t
+        L.refsg_traverse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        self.h = L.refsg_create()
+        self.n = len(instances)
+        self.n_prims = []
+        for v, f, x in instances:
+            v = np.ascontiguousarray(v, np.float32)
+            f = np.ascontiguousarray(f, np.uint32)
+            x = np.ascontiguousarray(x, np.float32).reshape(16)
+            assert L.refsg_add_node(self.h, _p(v), len(v), _p(f), len(f), _p(x)) == 0
+            self.n_prims.append(len(f))
+        assert L.refsg_commit(self.h) == 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.refsg_free(self.h)
+            self.h = None
+
+    def bounding_box(self):
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self.lib.refsg_bounding_box(self.h, _p(a), _p(b))
+        return a, b
+
+    def node_states(self):
+        out = np.zeros(self.n, SG_NODE_DTYPE)
+        for i in range(self.n):
+            self.lib.refsg_node_state(self.h, i, out[i:i + 1].ctypes.data)
+        return out
+
+    def top(self):
+        nn = self.lib.refsg_top_num_nodes(self.h)
+        nodes, idx = np.zeros(nn, NODE_DTYPE), np.zeros(self.n, np.uint32)
+        self.lib.refsg_top_copy(self.h, _p(nodes), _p(idx))
+        return nodes, idx
+
+    def node_tree(self, i):
+        nn = self.lib.refsg_node_num_nodes(self.h, i)
+        nodes, idx = np.zeros(nn, NODE_DTYPE), np.zeros(self.n_prims[i], np.uint32)
+        self.lib.refsg_node_copy(self.h, i, _p(nodes), _p(idx))
+        return nodes, idx
+
+    def list_node_intersections(self, ray, max_hits=64):
+        ray = np.ascontiguousarray(ray).reshape(1)
+        tmin, tmax, ids = np.zeros(128, np.float32), np.zeros(128, np.float32), np.zeros(128, np.uint32)
+        n = self.lib.refsg_list_node_intersections(self.h, _p(ray), max_hits, _p(tmin), _p(tmax), _p(ids))
+        return tmin[:n], tmax[:n], ids[:n]
+
+    def traverse(self, rays, threads=1):
+        rays = np.ascontiguousarray(rays)
+        n = len(rays)
+        hits, mask = np.zeros(n, SG_HIT_DTYPE), np.zeros(n, np.uint8)
+        self.lib.refsg_traverse_batch(self.h, _p(rays), n, _p(hits), _p(mask), threads)
+        return hits, mask
