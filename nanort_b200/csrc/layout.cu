@@ -25,6 +25,21 @@ __global__ void pack_tris_kernel(const uint32_t *__restrict__ indices, const uin
   out[slot] = t;
 }
 
+// Box primitives (top-level tree of a two-level scene): the same 48-byte slot carries the instance's world box,
+//   bmin.xyz, instance id | bmax.xyz, last_in_leaf flag | unused
+__global__ void pack_boxes_kernel(const uint32_t *__restrict__ indices, const float *__restrict__ boxes6, uint32_t n,
+                                  PackedTri *__restrict__ out) {
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n) return;
+  const uint32_t prim = indices[slot];
+  const float *b = boxes6 + 6 * (size_t)prim;
+  PackedTri t;
+  t.a = make_float4(b[0], b[1], b[2], __uint_as_float(prim));
+  t.b = make_float4(b[3], b[4], b[5], __uint_as_float(0u));
+  t.c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  out[slot] = t;
+}
+
 __global__ void branch_flags_kernel(const Node40 *__restrict__ nodes, uint32_t n, uint32_t *__restrict__ flags) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[i] = nodes[i].flag == 0 ? 1u : 0u;
@@ -158,7 +173,10 @@ int derive_private_layout(Accel *a, cudaStream_t s) {
   a->d_tris = nullptr;
   a->d_wide = nullptr;
   NRT_CUDA(cudaMalloc(&a->d_tris, sizeof(PackedTri) * (size_t)n_prims));
-  pack_tris_kernel<<<(n_prims + 255) / 256, 256, 0, s>>>(a->d_indices, a->d_faces, a->d_verts, n_prims, a->d_tris);
+  if (a->d_prim_boxes)
+    pack_boxes_kernel<<<(n_prims + 255) / 256, 256, 0, s>>>(a->d_indices, a->d_prim_boxes, n_prims, a->d_tris);
+  else
+    pack_tris_kernel<<<(n_prims + 255) / 256, 256, 0, s>>>(a->d_indices, a->d_faces, a->d_verts, n_prims, a->d_tris);
   NRT_CUDA(cudaGetLastError());
 
   uint32_t *d_flags = nullptr, *d_widx = nullptr;

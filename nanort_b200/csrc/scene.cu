@@ -60,6 +60,8 @@ struct SceneDev {
   const Node40 *top_nodes;
   const uint32_t *top_idx;
   const InstanceDev *inst;
+  const WideNode *top_wide;    // top-level tree as child-pair nodes
+  const PackedTri *top_slots;  // its leaves: {world bmin, instance id | world bmax, last flag | -}
 };
 
 struct SceneHit32 {
@@ -700,6 +702,273 @@ __global__ void __launch_bounds__(kSceneBlock, 5)
   }
 }
 
+// ---- production kernel, unified walk ------------------------------------------------------------------------------
+// The top-level tree is laid out as the same 64-byte child-pair nodes as every instance tree, so that ONE node step
+// serves lanes that walk the top level and lanes that are inside an instance: the per-lane ray constants `c` are the
+// world ray's or the local ray's, the per-lane base pointers select the tree, and a single per-lane stack holds the
+// top-level entries, a sentinel, and the instance's entries above it.  A top-level leaf is an instance slot: the
+// reference's box test decides whether the lane enters (transform the ray, push the sentinel, start at the
+// instance's root); popping the sentinel ends the visit (world distance of the local hit, restore the world
+// constants from shared memory).  Lanes never wait for each other's instance visits.
+//   top-level step: pass iff the widened slab test over [min_t, max_t] passes (nanort.h:2284-2325) and the
+//                   unclamped entry distance is not behind the nearest hit (every instance box below starts later)
+//   instance step:  pass iff the slab test over [0, best.t] passes; stack entries are culled against best.t
+constexpr int kUnifiedMinBlocks = 7;
+constexpr int kSentinel = (int)0x80000001;  // ~kSentinel = 0x7FFFFFFE is never a slot
+
+__device__ __forceinline__ bool is_leaf_ref(int r) { return r < 0 && r != kNoLeaf && r != kSentinel; }
+
+// slab test that also returns the entry distance before the clamp to lo_clip
+__device__ __forceinline__ bool slab_e(const RayCtx &c, float lox, float loy, float loz, float hix, float hiy,
+                                       float hiz, float lo_clip, float hi_clip, float &te) {
+  const float nx = c.sx ? hix : lox, fx = c.sx ? lox : hix;
+  const float ny = c.sy ? hiy : loy, fy = c.sy ? loy : hiy;
+  const float nz = c.sz ? hiz : loz, fz = c.sz ? loz : hiz;
+  const float tnx = (nx - c.ox) * c.ix;
+  const float tny = (ny - c.oy) * c.iy;
+  const float tnz = (nz - c.oz) * c.iz;
+  const float tfx = ((fx - c.ox) * c.ix) * 1.00000024f;
+  const float tfy = ((fy - c.oy) * c.iy) * 1.00000024f;
+  const float tfz = ((fz - c.oz) * c.iz) * 1.00000024f;
+  te = fmaxf(tnz, fmaxf(tny, tnx));  // NaN operands drop out like in slab(); all-NaN stays NaN
+  const float tmin = fmaxf(te, lo_clip);
+  const float tmax = fminf(tfz, fminf(tfy, fminf(tfx, hi_clip)));
+  return tmin <= tmax;
+}
+
+template <int LOCAL_DEPTH, int MINB>
+__global__ void __launch_bounds__(kSceneBlock, MINB)
+    scene_unified_kernel(SceneDev sc, const Ray36 *__restrict__ rays, size_t n, SceneHit32 *__restrict__ hits,
+                         uint8_t *__restrict__ mask, uint32_t flags, unsigned long long *cursor,
+                         uint32_t *__restrict__ overflow, unsigned long long *overflow_count) {
+  __shared__ float wsave[16 * kSceneBlock];  // world-ray constants of lanes that are inside an instance
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
+  const TraceOptions16 opt = local_trace_options();
+
+  long long ray_idx = -1;
+  bool exhausted = false;
+  WorldRay w;
+  SceneBest nearest;
+  uint32_t n_boxes = 0;
+  int inst = -1;
+  RayCtx c;
+  Best best;
+  const WideNode *wide = sc.top_wide;
+  const PackedTri *tris = sc.top_slots;
+  uint2 lstk[LOCAL_DEPTH];
+  int sp = 0, cur = kNoLeaf, leaf = kNoLeaf;
+
+  auto push = [&](int ref, float t) {
+    if (sp < LOCAL_DEPTH) lstk[sp] = make_uint2((uint32_t)ref, __float_as_uint(t));
+    sp++;
+  };
+  // next entry that does not start behind the current bound (instance: best.t, top level: nearest.t); the sentinel
+  // is stored with -inf and always comes back
+  auto pop = [&]() -> int {
+    const float bound = inst >= 0 ? best.t : nearest.t;
+    while (sp > 0) {
+      --sp;
+      if (sp >= LOCAL_DEPTH) continue;
+      const uint2 e = lstk[sp];
+      if (!(__uint_as_float(e.y) > bound)) return (int)e.x;
+    }
+    return kNoLeaf;
+  };
+  auto save_world = [&]() {
+    float *q = wsave + tid;
+    q[0 * kSceneBlock] = c.ox, q[1 * kSceneBlock] = c.oy, q[2 * kSceneBlock] = c.oz;
+    q[3 * kSceneBlock] = c.ix, q[4 * kSceneBlock] = c.iy, q[5 * kSceneBlock] = c.iz;
+    q[6 * kSceneBlock] = c.Sx, q[7 * kSceneBlock] = c.Sy, q[8 * kSceneBlock] = c.Sz;
+    q[9 * kSceneBlock] = c.t_min;
+    q[10 * kSceneBlock] = __int_as_float(c.sx | (c.sy << 1) | (c.sz << 2) | (c.kx << 4) | (c.ky << 6) | (c.kz << 8));
+  };
+  auto restore_world = [&]() {
+    const float *q = wsave + tid;
+    c.ox = q[0 * kSceneBlock], c.oy = q[1 * kSceneBlock], c.oz = q[2 * kSceneBlock];
+    c.ix = q[3 * kSceneBlock], c.iy = q[4 * kSceneBlock], c.iz = q[5 * kSceneBlock];
+    c.Sx = q[6 * kSceneBlock], c.Sy = q[7 * kSceneBlock], c.Sz = q[8 * kSceneBlock];
+    c.t_min = q[9 * kSceneBlock];
+    const int b = __float_as_int(q[10 * kSceneBlock]);
+    c.sx = b & 1, c.sy = (b >> 1) & 1, c.sz = (b >> 2) & 1;
+    c.kx = (b >> 4) & 3, c.ky = (b >> 6) & 3, c.kz = (b >> 8) & 3;
+  };
+
+  for (;;) {
+    // ---- replace retired rays
+    const unsigned dead = __ballot_sync(FULL_MASK, ray_idx < 0);
+    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= 16)) {
+      const int cnt = __popc(dead);
+      const int leader = __ffs(dead) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(cursor, (unsigned long long)cnt);
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
+      if (ray_idx < 0) {
+        const unsigned long long mine = base + (unsigned long long)__popc(dead & lt_mask);
+        if (mine < (unsigned long long)n) {
+          w = load_world(rays, (size_t)mine);
+          setup_ray(c, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, w.min_t, cpp03);
+          nearest.t = FLT_MAX;
+          nearest.node = 0xFFFFFFFFu;
+          best.t = FLT_MAX;
+          ray_idx = (long long)mine;
+          n_boxes = 0;
+          inst = -1;
+          wide = sc.top_wide;
+          tris = sc.top_slots;
+          sp = 0;
+          cur = 0;
+          leaf = kNoLeaf;
+          // see scene_fast_kernel: a direction that is not unit length goes to the list kernel
+          const float len2 = (w.dx * w.dx + w.dy * w.dy) + w.dz * w.dz;
+          if (!(fabsf(len2 - 1.0f) <= 1e-5f)) {
+            cur = kNoLeaf;
+            n_boxes = (uint32_t)kMaxNodeHits + 1u;
+          }
+        }
+      }
+    }
+    if (__all_sync(FULL_MASK, ray_idx < 0)) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- node steps (top level and instances alike)
+    for (;;) {
+      const unsigned desc = __ballot_sync(FULL_MASK, cur >= 0);
+      if (desc == 0u) break;
+      if (__popc(desc) < 8 && __any_sync(FULL_MASK, leaf != kNoLeaf || cur == kSentinel)) break;
+      if (cur >= 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
+        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
+        const bool in_inst = inst >= 0;
+        const float lo_clip = in_inst ? 0.0f : w.min_t;
+        const float hi_clip = in_inst ? best.t : w.max_t;
+        const float bound = in_inst ? best.t : nearest.t;
+        float t0, t1;
+        bool h0 = slab_e(c, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, lo_clip, hi_clip, t0);
+        bool h1 = slab_e(c, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, lo_clip, hi_clip, t1);
+        h0 &= !(t0 > bound);
+        h1 &= !(t1 > bound);
+        const bool both = h0 & h1;
+        const bool swap = t1 < t0;
+        const int nearr = swap ? q3.y : q3.x;
+        const int farr = swap ? q3.x : q3.y;
+        if (both) push(farr, swap ? t0 : t1);
+        int next = both ? nearr : (h0 ? q3.x : q3.y);
+        if (!(h0 | h1)) next = pop();
+        if (is_leaf_ref(next) && leaf == kNoLeaf) {  // postpone the first leaf, keep descending
+          leaf = next;
+          next = pop();
+        }
+        cur = next;
+      }
+    }
+
+    // ---- leaves: triangles inside an instance, instance slots at the top level; then instance exits
+    for (;;) {
+      if (!__any_sync(FULL_MASK, leaf != kNoLeaf || cur == kSentinel)) break;
+      if (leaf != kNoLeaf) {
+        const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)(~leaf));
+        if (inst >= 0) {
+          for (;;) {
+            const float4 a = __ldg(t), b = __ldg(t + 1), cc = __ldg(t + 2);
+            tri_test2(c, opt, a, b, cc, best);
+            if (__float_as_uint(b.w) != 0u) break;
+            t += 3;
+          }
+          leaf = kNoLeaf;
+        } else {
+          const float4 a = __ldg(t), b = __ldg(t + 1);
+          const int slot = ~leaf;
+          leaf = kNoLeaf;
+          if (__float_as_uint(b.w) == 0u) {  // more instances in this top-level leaf (depth-limit leaves only)
+            if (cur != kNoLeaf) push(cur, -CUDART_INF_F);
+            cur = ~(slot + 1);
+          }
+          // NodeBBoxIntersector::Intersect on the world box (nanosg.h:597-637)
+          const float rix = 1.0f / w.dx, riy = 1.0f / w.dy, riz = 1.0f / w.dz;
+          const bool sx = w.dx < 0.0f, sy = w.dy < 0.0f, sz = w.dz < 0.0f;
+          const float tnx = ((sx ? b.x : a.x) - w.ox) * rix, tfx = ((sx ? a.x : b.x) - w.ox) * rix;
+          const float tny = ((sy ? b.y : a.y) - w.oy) * riy, tfy = ((sy ? a.y : b.y) - w.oy) * riy;
+          const float tnz = ((sz ? b.z : a.z) - w.oz) * riz, tfz = ((sz ? a.z : b.z) - w.oz) * riz;
+          const float tmin = smax(tnz, smax(tny, tnx));
+          const float tmax = smin(tfz, smin(tfy, tfx));
+          if (tmin <= tmax) {
+            n_boxes++;
+            if (!(nearest.t < tmin)) {  // early cull (nanosg.h:803-807)
+              const uint32_t id = __float_as_uint(a.w);
+              const InstanceDev *I = sc.inst + id;
+              const Mat43 minv = load_mat(&I->inv), minv33 = load_mat(&I->inv33);
+              float lox, loy, loz, ldx, ldy, ldz;
+              multv(minv, w.ox, w.oy, w.oz, lox, loy, loz);
+              multv(minv33, w.dx, w.dy, w.dz, ldx, ldy, ldz);
+              if (cur != kNoLeaf) push(cur, -CUDART_INF_F);  // what this lane was about to do at the top level
+              push(kSentinel, -CUDART_INF_F);
+              save_world();
+              setup_ray(c, lox, loy, loz, ldx, ldy, ldz, 0.0f, cpp03);
+              best.t = FLT_MAX;
+              best.u = 0.0f;
+              best.v = 0.0f;
+              best.prim = 0xFFFFFFFFu;
+              wide = I->wide;
+              tris = I->tris;
+              inst = (int)id;
+              cur = 0;
+            }
+          }
+        }
+        if (leaf == kNoLeaf && is_leaf_ref(cur)) {
+          leaf = cur;
+          cur = pop();
+        }
+      } else if (cur == kSentinel) {
+        // instance exit: world distance of the local hit (nanosg.h:832-870), back to the top-level walk
+        if (best.t < FLT_MAX) {
+          const InstanceDev *I = sc.inst + inst;
+          const Mat43 minv33 = load_mat(&I->inv33), mxf = load_mat(&I->xf);
+          float ldx, ldy, ldz, px, py, pz;
+          multv(minv33, w.dx, w.dy, w.dz, ldx, ldy, ldz);
+          const float tw = world_hit(mxf, w, c.ox, c.oy, c.oz, ldx, ldy, ldz, best.t, px, py, pz);
+          if (tw < nearest.t) {
+            nearest.t = tw;
+            nearest.u = best.u;
+            nearest.v = best.v;
+            nearest.prim = best.prim;
+            nearest.node = (uint32_t)inst;
+            nearest.px = px;
+            nearest.py = py;
+            nearest.pz = pz;
+          }
+        }
+        restore_world();
+        inst = -1;
+        wide = sc.top_wide;
+        tris = sc.top_slots;
+        cur = pop();
+        if (is_leaf_ref(cur)) {
+          leaf = cur;
+          cur = pop();
+        }
+      }
+    }
+
+    // ---- retire
+    if (ray_idx >= 0 && inst < 0 && cur == kNoLeaf && leaf == kNoLeaf) {
+      store_scene_hit(hits, mask, (size_t)ray_idx, nearest, nearest.node != 0xFFFFFFFFu, w.max_t);
+      if (n_boxes > (uint32_t)kMaxNodeHits) {
+        const unsigned long long slot = atomicAdd(overflow_count, 1ull);
+        overflow[slot] = (uint32_t)ray_idx;
+      }
+      ray_idx = -1;
+    }
+  }
+}
+
 }  // namespace
 
 // ---- scene object -------------------------------------------------------------------------------------------------
@@ -727,6 +996,8 @@ static void scene_destroy(Scene *s) {
     cudaFree(s->top->d_nodes);
     cudaFree(s->top->d_indices);
     cudaFree(s->top->d_prim_boxes);
+    cudaFree(s->top->d_wide);
+    cudaFree(s->top->d_tris);
     delete s->top;
   }
   cudaFree(s->d_inst);
@@ -747,9 +1018,11 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
     set_error("nrt_scene_traverse: more than 2^32-1 rays in one call");
     return NRT_ERR_INVALID;
   }
-  const SceneDev dev{sc->top->d_nodes, sc->top->d_indices, sc->d_inst};
-  const bool list_only = (flags & NRT_TRAVERSE_CONFORMANCE) != 0 ||
-                         sc->top->stats.max_tree_depth + 2 > (uint32_t)kTopStack;
+  const SceneDev dev{sc->top->d_nodes, sc->top->d_indices, sc->d_inst, sc->top->d_wide, sc->top->d_tris};
+  const uint32_t variant = (flags >> 8) & 0xFFu;  // 1 = first-generation phase kernel (A/B runs)
+  const uint32_t stack_need = sc->top->stats.max_tree_depth + sc->max_blas_depth + 6;
+  const bool list_only = (flags & NRT_TRAVERSE_CONFORMANCE) != 0 || stack_need > 1024 ||
+                         (variant == 1 && sc->top->stats.max_tree_depth + 2 > (uint32_t)kTopStack);
   const int sms = device_sm_count(sc->device);
   if (list_only) {
     const size_t blocks = std::min<size_t>((n + 127) / 128, (size_t)sms * 32);
@@ -771,8 +1044,23 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
   unsigned long long *ovf = sc->d_counters + 16;
   NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
   NRT_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned long long), s));
-  size_t grid = (size_t)sms * 5;
   const size_t need = ((n + 31) / 32 + 3) / 4;
+  if (variant != 1) {
+    size_t grid = (size_t)sms * (stack_need > 64 ? 2 : kUnifiedMinBlocks);
+    if (grid > need) grid = need;
+    if (stack_need > 64)
+      scene_unified_kernel<1024, 2><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
+                                                                        sc->d_overflow, ovf);
+    else
+      scene_unified_kernel<64, kUnifiedMinBlocks><<<(unsigned)grid, kSceneBlock, 0, s>>>(
+          dev, d_rays, n, d_hits, d_mask, flags, cursor, sc->d_overflow, ovf);
+    NRT_CUDA(cudaGetLastError());
+    scene_list_kernel<<<(unsigned)std::min<size_t>((n + 127) / 128, (size_t)sms * 4), 128, 0, s>>>(
+        dev, d_rays, n, sc->d_overflow, ovf, d_hits, d_mask, flags);
+    NRT_CUDA(cudaGetLastError());
+    return NRT_OK;
+  }
+  size_t grid = (size_t)sms * 5;
   if (grid > need) grid = need;
   if (sc->max_blas_depth + 2 > 48)
     scene_fast_kernel<512><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
@@ -869,6 +1157,7 @@ int nrt_scene_commit(const nrt_instance *instances, uint32_t n_instances, uint32
   rc = (flags & NRT_BUILD_REFERENCE_TREE)
            ? build_reference_tree_on_device(sc->top, !(flags & NRT_BUILD_REFERENCE_CPP03_ORDER), sc->stream)
            : build_on_device(sc->top, sc->stream);
+  if (rc == NRT_OK) rc = derive_private_layout(sc->top, sc->stream);
   if (rc == NRT_OK) {
     e = cudaStreamSynchronize(sc->stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "nrt_scene_commit build", __FILE__, __LINE__);
