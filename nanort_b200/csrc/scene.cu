@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(kSceneBlock, 5)
 //   top-level step: pass iff the widened slab test over [min_t, max_t] passes (nanort.h:2284-2325) and the
 //                   unclamped entry distance is not behind the nearest hit (every instance box below starts later)
 //   instance step:  pass iff the slab test over [0, best.t] passes; stack entries are culled against best.t
-constexpr int kUnifiedMinBlocks = 7;
+constexpr int kUnifiedMinBlocks = 8;  // 64 registers; sweep in profiles/r01_scene_sweep.md
 constexpr int kSentinel = (int)0x80000001;  // ~kSentinel = 0x7FFFFFFE is never a slot
 
 __device__ __forceinline__ bool is_leaf_ref(int r) { return r < 0 && r != kNoLeaf && r != kSentinel; }
@@ -736,7 +736,7 @@ __device__ __forceinline__ bool slab_e(const RayCtx &c, float lox, float loy, fl
   return tmin <= tmax;
 }
 
-template <int LOCAL_DEPTH, int MINB>
+template <int LOCAL_DEPTH, int MINB, int REFILL = 16, int NODE_EXIT = 8>
 __global__ void __launch_bounds__(kSceneBlock, MINB)
     scene_unified_kernel(SceneDev sc, const Ray36 *__restrict__ rays, size_t n, SceneHit32 *__restrict__ hits,
                          uint8_t *__restrict__ mask, uint32_t flags, unsigned long long *cursor,
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(kSceneBlock, MINB)
   for (;;) {
     // ---- replace retired rays
     const unsigned dead = __ballot_sync(FULL_MASK, ray_idx < 0);
-    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= 16)) {
+    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= REFILL)) {
       const int cnt = __popc(dead);
       const int leader = __ffs(dead) - 1;
       unsigned long long base = 0;
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(kSceneBlock, MINB)
     for (;;) {
       const unsigned desc = __ballot_sync(FULL_MASK, cur >= 0);
       if (desc == 0u) break;
-      if (__popc(desc) < 8 && __any_sync(FULL_MASK, leaf != kNoLeaf || cur == kSentinel)) break;
+      if (__popc(desc) < NODE_EXIT && __any_sync(FULL_MASK, leaf != kNoLeaf || cur == kSentinel)) break;
       if (cur >= 0) {
         const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
         const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
@@ -1011,6 +1011,11 @@ static void scene_destroy(Scene *s) {
   delete s;
 }
 
+template <int A, int... R>
+struct FirstArg {
+  static constexpr int value = A;
+};
+
 static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_hits, uint8_t *d_mask, uint32_t flags,
                         cudaStream_t s) {
   if (n == 0) return NRT_OK;
@@ -1051,7 +1056,28 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
     if (stack_need > 64)
       scene_unified_kernel<1024, 2><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
                                                                         sc->d_overflow, ovf);
-    else
+    else if (variant >= 2) {
+#define NRT_SCENE_VARIANT(id, ...)                                                                              \
+  case id: {                                                                                                    \
+    size_t g = std::min(need, (size_t)sms * (FirstArg<__VA_ARGS__>::value));                                    \
+    scene_unified_kernel<64, __VA_ARGS__><<<(unsigned)g, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask,   \
+                                                                              flags, cursor, sc->d_overflow, ovf); \
+  } break;
+      switch (variant) {
+        NRT_SCENE_VARIANT(2, 6, 16, 8)
+        NRT_SCENE_VARIANT(3, 8, 16, 8)
+        NRT_SCENE_VARIANT(4, 5, 16, 8)
+        NRT_SCENE_VARIANT(5, 7, 8, 8)
+        NRT_SCENE_VARIANT(6, 7, 24, 8)
+        NRT_SCENE_VARIANT(7, 7, 16, 4)
+        NRT_SCENE_VARIANT(8, 7, 16, 12)
+        NRT_SCENE_VARIANT(9, 7, 16, 16)
+        default:
+          set_error("nrt_scene_traverse: unknown kernel variant in flags");
+          return NRT_ERR_INVALID;
+      }
+#undef NRT_SCENE_VARIANT
+    } else
       scene_unified_kernel<64, kUnifiedMinBlocks><<<(unsigned)grid, kSceneBlock, 0, s>>>(
           dev, d_rays, n, d_hits, d_mask, flags, cursor, sc->d_overflow, ovf);
     NRT_CUDA(cudaGetLastError());
