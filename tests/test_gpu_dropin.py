@@ -69,3 +69,35 @@ def test_concurrent_per_ray_traverse_from_worker_threads():
         subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
     out = _run("threads_check")
     assert out[-1].endswith("mismatches 0"), out
+
+
+def _nanosg_golden():
+    import gzip
+
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "nanosg_check_ref.txt.gz"), "rt") as f:
+        return f.read().strip().splitlines()
+
+
+def test_nanosg_drop_in_conformance_is_identical():
+    """examples/nanosg_check.cc against include/nanosg.h with -DNANORT_B200_CONFORMANCE must print exactly what the
+    same source prints against the reference's examples/nanosg/nanosg.h: scene box, node matrices, and for every
+    ray node_id / prim_id / t / u / v / P / transformed Ng as raw bits."""
+    if not os.path.exists(os.path.join(BIN, "nanosg_check_b200_conf")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
+    got = _run("nanosg_check_b200_conf")
+    want = _nanosg_golden()
+    assert len(want) > 2000 and got == want
+
+
+def test_nanosg_drop_in_fast_mode_same_hits():
+    """Default (fast) mode: same lines except where two surfaces lie at exactly the same distance."""
+    if not os.path.exists(os.path.join(BIN, "nanosg_check_b200")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
+    got = _run("nanosg_check_b200")
+    want = _nanosg_golden()
+    assert got[:2] == want[:2] and got[-1] == want[-1]  # scene box, node state, hit count
+    assert [g.split(":")[0] for g in got] == [w.split(":")[0] for w in want]  # the same rays hit
+    diff = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert len(diff) <= 0.01 * len(want)
+    for i in diff:  # only the pick differs, not the distance
+        assert got[i].split(" t ")[1].split()[0] == want[i].split(" t ")[1].split()[0]
