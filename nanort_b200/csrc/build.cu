@@ -44,6 +44,7 @@ constexpr int kSubWarps = 4;      // warps (= subtrees) per phase-B CTA
 __global__ void prim_setup_kernel(const float *__restrict__ verts, const uint32_t *__restrict__ faces, uint32_t n,
                                   float4 *__restrict__ plo, float4 *__restrict__ phi, float *__restrict__ pcz,
                                   uint32_t *__restrict__ scene_keys /*6*/) {
+  __shared__ float s_box[8][6];  // per-warp partial scene box (256-thread CTAs)
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   if (i < n) {
@@ -71,9 +72,19 @@ __global__ void prim_setup_kernel(const float *__restrict__ verts, const uint32_
       b = fmaxf(b, __shfl_xor_sync(0xFFFFFFFFu, b, o));
     }
     if ((threadIdx.x & 31) == 0) {
-      atomicMin(scene_keys + k, fkey(a));
-      atomicMax(scene_keys + 3 + k, fkey(b));
+      s_box[threadIdx.x >> 5][k] = a;
+      s_box[threadIdx.x >> 5][3 + k] = b;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {  // one atomic per CTA and component
+    const int k = threadIdx.x;
+    float v = s_box[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = k < 3 ? fminf(v, s_box[w][k]) : fmaxf(v, s_box[w][k]);
+    if (k < 3)
+      atomicMin(scene_keys + k, fkey(v));
+    else
+      atomicMax(scene_keys + k, fkey(v));
   }
 }
 
@@ -82,6 +93,7 @@ __global__ void prim_setup_kernel(const float *__restrict__ verts, const uint32_
 __global__ void box_setup_kernel(const float *__restrict__ boxes6, uint32_t n, float4 *__restrict__ plo,
                                  float4 *__restrict__ phi, float *__restrict__ pcz,
                                  uint32_t *__restrict__ scene_keys /*6*/) {
+  __shared__ float s_box[8][6];  // per-warp partial scene box (256-thread CTAs)
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   if (i < n) {
@@ -104,9 +116,19 @@ __global__ void box_setup_kernel(const float *__restrict__ boxes6, uint32_t n, f
       b = fmaxf(b, __shfl_xor_sync(0xFFFFFFFFu, b, o));
     }
     if ((threadIdx.x & 31) == 0) {
-      atomicMin(scene_keys + k, fkey(a));
-      atomicMax(scene_keys + 3 + k, fkey(b));
+      s_box[threadIdx.x >> 5][k] = a;
+      s_box[threadIdx.x >> 5][3 + k] = b;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {  // one atomic per CTA and component
+    const int k = threadIdx.x;
+    float v = s_box[0][k];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = k < 3 ? fminf(v, s_box[w][k]) : fmaxf(v, s_box[w][k]);
+    if (k < 3)
+      atomicMin(scene_keys + k, fkey(v));
+    else
+      atomicMax(scene_keys + k, fkey(v));
   }
 }
 
@@ -176,22 +198,24 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     float ivx = inv_extent(nd.bmin[0], nd.bmax[0], B), ivy = inv_extent(nd.bmin[1], nd.bmax[1], B),
           ivz = inv_extent(nd.bmin[2], nd.bmax[2], B);
-    for (uint32_t p = tile0 + threadIdx.x; p < tile1; p += 256) {
-      uint32_t s = idx[p];
-      float4 lo = plo[s], hi = phi[s];
-      float cz = pcz[s];
-      int b3[3] = {bin_of(lo.w, nd.bmin[0], ivx, B), bin_of(hi.w, nd.bmin[1], ivy, B), bin_of(cz, nd.bmin[2], ivz, B)};
-      uint32_t kl[3] = {fkey(lo.x), fkey(lo.y), fkey(lo.z)}, kh[3] = {fkey(hi.x), fkey(hi.y), fkey(hi.z)};
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        uint32_t *w = sbin + ((size_t)a * B + b3[a]) * kBinWords;
-        atomicAdd(w, 1u);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          atomicMin(w + 1 + k, kl[k]);
-          atomicMax(w + 4 + k, kh[k]);
-        }
+    for (uint32_t p0 = tile0; p0 < tile1; p0 += 256) {  // whole warps iterate: the aggregation is warp-collective
+      const uint32_t p = p0 + threadIdx.x;
+      const bool valid = p < tile1;
+      int b3[3] = {0, 0, 0};
+      uint32_t kl[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, kh[3] = {0u, 0u, 0u};
+      if (valid) {
+        uint32_t s = idx[p];
+        float4 lo = plo[s], hi = phi[s];
+        float cz = pcz[s];
+        b3[0] = bin_of(lo.w, nd.bmin[0], ivx, B);
+        b3[1] = bin_of(hi.w, nd.bmin[1], ivy, B);
+        b3[2] = bin_of(cz, nd.bmin[2], ivz, B);
+        kl[0] = fkey(lo.x), kl[1] = fkey(lo.y), kl[2] = fkey(lo.z);
+        kh[0] = fkey(hi.x), kh[1] = fkey(hi.y), kh[2] = fkey(hi.z);
       }
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+        bin_add_aggregated(sbin + ((size_t)a * B + b3[a]) * kBinWords, (uint32_t)b3[a], valid, kl, kh);
     }
     __syncthreads();
     uint32_t *g = bins + (size_t)nd.slot * 3 * B * kBinWords;
@@ -207,27 +231,31 @@ __global__ void __launch_bounds__(256)
       }
     }
   } else {
-    for (uint32_t p = tile0 + threadIdx.x; p < tile1; p += 256) {
-      BNode nd = pool[node_of[p]];
-      if (nd.slot == kInactive) continue;
-      uint32_t s = idx[p];
-      float4 lo = plo[s], hi = phi[s];
-      float cz = pcz[s];
-      int b3[3] = {bin_of(lo.w, nd.bmin[0], inv_extent(nd.bmin[0], nd.bmax[0], B), B),
-                   bin_of(hi.w, nd.bmin[1], inv_extent(nd.bmin[1], nd.bmax[1], B), B),
-                   bin_of(cz, nd.bmin[2], inv_extent(nd.bmin[2], nd.bmax[2], B), B)};
-      uint32_t kl[3] = {fkey(lo.x), fkey(lo.y), fkey(lo.z)}, kh[3] = {fkey(hi.x), fkey(hi.y), fkey(hi.z)};
-      uint32_t *g = bins + (size_t)nd.slot * 3 * B * kBinWords;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        uint32_t *w = g + ((size_t)a * B + b3[a]) * kBinWords;
-        atomicAdd(w, 1u);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          atomicMin(w + 1 + k, kl[k]);
-          atomicMax(w + 4 + k, kh[k]);
+    for (uint32_t p0 = tile0; p0 < tile1; p0 += 256) {
+      const uint32_t p = p0 + threadIdx.x;
+      bool valid = p < tile1;
+      int b3[3] = {0, 0, 0};
+      uint32_t kl[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, kh[3] = {0u, 0u, 0u};
+      uint32_t slot = 0;
+      if (valid) {
+        BNode nd = pool[node_of[p]];
+        slot = nd.slot;
+        valid = slot != kInactive;
+        if (valid) {
+          uint32_t s = idx[p];
+          float4 lo = plo[s], hi = phi[s];
+          float cz = pcz[s];
+          b3[0] = bin_of(lo.w, nd.bmin[0], inv_extent(nd.bmin[0], nd.bmax[0], B), B);
+          b3[1] = bin_of(hi.w, nd.bmin[1], inv_extent(nd.bmin[1], nd.bmax[1], B), B);
+          b3[2] = bin_of(cz, nd.bmin[2], inv_extent(nd.bmin[2], nd.bmax[2], B), B);
+          kl[0] = fkey(lo.x), kl[1] = fkey(lo.y), kl[2] = fkey(lo.z);
+          kh[0] = fkey(hi.x), kh[1] = fkey(hi.y), kh[2] = fkey(hi.z);
         }
       }
+      uint32_t *g = bins + (size_t)(valid ? slot : 0u) * 3 * B * kBinWords;
+#pragma unroll
+      for (int a = 0; a < 3; a++)  // key = record index: equal only for the same (node, axis, bin)
+        bin_add_aggregated(g + ((size_t)a * B + b3[a]) * kBinWords, slot * (uint32_t)B + (uint32_t)b3[a], valid, kl, kh);
     }
   }
 }
@@ -441,15 +469,16 @@ __global__ void __launch_bounds__(kSubWarps * 32)
     const uint32_t nid = S.stack[--sp];
     const BNode nd = pool[nid];
     const uint32_t lo = nd.l - base, n = nd.r - nd.l;
-    // ---- bins
-    for (int i = lane; i < 3 * B * kBinWords; i += 32) {
+    const bool small = n <= 32u;
+    const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
+                         inv_extent(nd.bmin[2], nd.bmax[2], B)};
+    // ---- bins (nodes with more than 32 primitives)
+    for (int i = lane; !small && i < 3 * B * kBinWords; i += 32) {
       const int w = i & (kBinWords - 1);
       sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
     }
     __syncwarp();
-    const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
-                         inv_extent(nd.bmin[2], nd.bmax[2], B)};
-    for (uint32_t i = lane; i < n; i += 32) {
+    for (uint32_t i = lane; !small && i < n; i += 32) {
       const uint32_t q = S.ids[lo + i];
       const float4 l4 = S.plo[q], h4 = S.phi[q];
       const float c3[3] = {l4.w, h4.w, S.pcz[q]};
@@ -469,16 +498,99 @@ __global__ void __launch_bounds__(kSubWarps * 32)
     // ---- sweep the three axes, pick the split
     float cost[3];
     int cut[3];
-    for (int a = 0; a < 3; a++) sweep_axis(sbin + (size_t)a * B * kBinWords, B, sweep, sweep + B, cost[a], cut[a]);
     int ax = 0;
-    if (cost[0] > cost[1]) ax = 1;
-    if (cost[ax] > cost[2]) ax = 2;
-    const bool median = !(cost[ax] < FLT_MAX);
     Box6 lb, rb;
-    uint32_t nl, nr;
+    uint32_t nl = 0, nr = 0;
+    if (small) {
+      // n <= 32: one primitive per lane, no bins in memory.  Per axis: sort the lanes by bin, scan boxes along the
+      // sorted order; a boundary exists wherever the bin changes, its left count is the sorted position.  Same
+      // candidates, same cost arithmetic and same tie rule (lowest boundary) as the binned sweep below.
+      Box6 mine;
+      box_empty(mine);
+      float c3[3] = {0.0f, 0.0f, 0.0f};
+      const bool valid = (uint32_t)lane < n;
+      if (valid) {
+        const uint32_t q = S.ids[lo + lane];
+        const float4 l4 = S.plo[q], h4 = S.phi[q];
+        mine.v[0] = l4.x, mine.v[1] = l4.y, mine.v[2] = l4.z, mine.v[3] = h4.x, mine.v[4] = h4.y, mine.v[5] = h4.z;
+        c3[0] = l4.w, c3[1] = h4.w, c3[2] = S.pcz[q];
+      }
+      float best = FLT_MAX;
+      cost[0] = cost[1] = cost[2] = FLT_MAX;
+      cut[0] = cut[1] = cut[2] = 0x7FFFFFFF;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const uint32_t bin = valid ? (uint32_t)bin_of(c3[a], nd.bmin[a], iv[a], B) : 0x03FFFFFFu;
+        uint32_t key = (bin << 5) | (uint32_t)lane;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, key, j);
+            const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+            key = keep_min ? min(key, other) : max(key, other);
+          }
+        }
+        const int src = (int)(key & 31u);
+        const uint32_t sb = key >> 5;
+        Box6 pre, suf;
+#pragma unroll
+        for (int k = 0; k < 6; k++) pre.v[k] = suf.v[k] = __shfl_sync(0xFFFFFFFFu, mine.v[k], src);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          Box6 t, u;
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            t.v[k] = __shfl_up_sync(0xFFFFFFFFu, pre.v[k], o);
+            u.v[k] = __shfl_down_sync(0xFFFFFFFFu, suf.v[k], o);
+          }
+          if (lane >= o) box_merge(pre, t);
+          if (lane + o < 32) box_merge(suf, u);
+        }
+        Box6 epre;
+#pragma unroll
+        for (int k = 0; k < 6; k++) epre.v[k] = __shfl_up_sync(0xFFFFFFFFu, pre.v[k], 1);
+        const uint32_t prev_bin = __shfl_up_sync(0xFFFFFFFFu, sb, 1);
+        const bool cand = lane >= 1 && (uint32_t)lane < n && sb != prev_bin;
+        float cst = FLT_MAX;
+        if (cand)
+          cst = (float)lane * box_area(epre.v[0], epre.v[1], epre.v[2], epre.v[3], epre.v[4], epre.v[5]) +
+                (float)(n - (uint32_t)lane) * box_area(suf.v[0], suf.v[1], suf.v[2], suf.v[3], suf.v[4], suf.v[5]);
+        float bc = cst;
+        int bp = cand ? lane : 0x7FFFFFFF;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float oc = __shfl_xor_sync(0xFFFFFFFFu, bc, o);
+          const int op = __shfl_xor_sync(0xFFFFFFFFu, bp, o);
+          if (oc < bc || (oc == bc && op < bp)) {
+            bc = oc;
+            bp = op;
+          }
+        }
+        cost[a] = bc;
+        if (bc < best) {  // warp-uniform; strict, so a tie keeps the lower axis
+          best = bc;
+          ax = a;
+          cut[a] = (int)__shfl_sync(0xFFFFFFFFu, prev_bin, bp) + 1;
+          nl = (uint32_t)bp;
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            lb.v[k] = __shfl_sync(0xFFFFFFFFu, epre.v[k], bp);
+            rb.v[k] = __shfl_sync(0xFFFFFFFFu, suf.v[k], bp);
+          }
+        }
+      }
+    } else {
+      for (int a = 0; a < 3; a++) sweep_axis(sbin + (size_t)a * B * kBinWords, B, sweep, sweep + B, cost[a], cut[a]);
+      if (cost[0] > cost[1]) ax = 1;
+      if (cost[ax] > cost[2]) ax = 2;
+    }
+    const bool median = !(cost[ax] < FLT_MAX);
     if (!median) {
-      range_union(sbin + (size_t)ax * B * kBinWords, 0, cut[ax], lb, nl);
-      range_union(sbin + (size_t)ax * B * kBinWords, cut[ax], B, rb, nr);
+      if (!small) {
+        range_union(sbin + (size_t)ax * B * kBinWords, 0, cut[ax], lb, nl);
+        range_union(sbin + (size_t)ax * B * kBinWords, cut[ax], B, rb, nr);
+      }
     } else {
       nl = n >> 1;
       box_empty(lb);

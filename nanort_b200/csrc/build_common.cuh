@@ -67,6 +67,42 @@ __device__ __forceinline__ float inv_extent(float lo, float hi, int B) {
   return sz > 0.0f ? (float)B / sz : 0.0f;
 }
 
+constexpr int kAggregateMin = 6;
+
+// One primitive into its bin record {count, kmin xyz, kmax xyz} -- warp-aggregated: lanes whose primitives fall
+// into the same record (after the Morton pre-sort that is most of the warp) are combined with match_any + redux
+// first, then ONE lane per distinct record issues the seven atomics.  `key` identifies the record (any value that
+// is equal exactly for equal `rec`); every lane of the warp must call, lanes without a primitive pass valid=false.
+__device__ __forceinline__ void bin_add_aggregated(uint32_t *rec, uint32_t key, bool valid, const uint32_t kl[3],
+                                                   const uint32_t kh[3]) {
+  const unsigned group = __match_any_sync(0xFFFFFFFFu, valid ? key : 0xFFFFFFFFu);
+  if (!valid) return;
+  const int members = __popc(group);
+  if (members < kAggregateMin) {  // few lanes share the record: plain atomics are cheaper than six reductions
+    atomicAdd(rec, 1u);
+    atomicMin(rec + 1, kl[0]);
+    atomicMin(rec + 2, kl[1]);
+    atomicMin(rec + 3, kl[2]);
+    atomicMax(rec + 4, kh[0]);
+    atomicMax(rec + 5, kh[1]);
+    atomicMax(rec + 6, kh[2]);
+    return;
+  }
+  const uint32_t l0 = __reduce_min_sync(group, kl[0]), l1 = __reduce_min_sync(group, kl[1]),
+                 l2 = __reduce_min_sync(group, kl[2]);
+  const uint32_t h0 = __reduce_max_sync(group, kh[0]), h1 = __reduce_max_sync(group, kh[1]),
+                 h2 = __reduce_max_sync(group, kh[2]);
+  if ((int)(threadIdx.x & 31) == __ffs(group) - 1) {
+    atomicAdd(rec, (uint32_t)members);
+    atomicMin(rec + 1, l0);
+    atomicMin(rec + 2, l1);
+    atomicMin(rec + 3, l2);
+    atomicMax(rec + 4, h0);
+    atomicMax(rec + 5, h1);
+    atomicMax(rec + 6, h2);
+  }
+}
+
 // ------------------------------------------------------------------ SAH sweep (one warp, one axis)
 struct Box6 {
   float v[6];  // min xyz, max xyz
