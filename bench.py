@@ -359,7 +359,12 @@ def main():
     achieved = alg_bytes / (trav_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traverse_traffic.json")))["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traverse_traffic.json")))
+        # the capture's launches are smaller than a bench wave: scale its DRAM bytes per ray to this run's launch size
+        if tj.get("dram_bytes_per_ray"):
+            traffic = tj["dram_bytes_per_ray"] * (n_primary + n_ao) / max(1, r.traverse_launches)
+        else:
+            traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {

@@ -70,7 +70,15 @@ for r in rows[2:]:
         u = units[hdr.index(k)].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
     dram.append(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
-json.dump({"dram_bytes_per_launch": sum(dram) / len(dram), "per_launch": dram,
+# rays of the captured launches: last line of the target's log ("scene primary_rays ao_rays ...")
+rays = None
+try:
+    last = [l for l in open(os.path.join(root, "gpurun_out", "pt2.log")).read().splitlines() if l.startswith("sphere_grid")][-1].split()
+    rays = [int(last[1]), int(last[2])][:len(dram)]
+except Exception:
+    pass
+json.dump({"dram_bytes_per_launch": sum(dram) / len(dram), "per_launch": dram, "rays_per_launch": rays,
+           "dram_bytes_per_ray": (sum(dram) / sum(rays)) if rays else None,
            "source": f"profiles/{tag}_traverse_fast_ncu{suffix}.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
           open(os.path.join(out, f"{tag}_traverse_traffic.json"), "w"), indent=1)
 print("wrote", sorted(os.listdir(out)))
