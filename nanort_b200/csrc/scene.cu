@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(128)
     NodeHitHeap heap;
     heap.n = 0;
     uint32_t stack[kListStack];
-    int sp = 0;
+    int sp = range_has_nan(w.min_t, w.max_t) ? -1 : 0;
     stack[0] = 0;
     while (sp >= 0) {  // ListNodeIntersections: hit_t stays at ray.max_t
       const Node40 *nd = sc.top_nodes + stack[sp];
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(kSceneBlock, 5)
           nearest.node = 0xFFFFFFFFu;
           ray_idx = (long long)mine;
           tstk[0] = 0;
-          tsp = 1;
+          tsp = range_has_nan(w.min_t, w.max_t) ? 0 : 1;
           leaf_pos = leaf_end = 0;
           n_boxes = 0;
           // Scene::Traverse compares world DISTANCES of hits with ray PARAMETERS of box entries (nanosg.h:803, 848):
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(kSceneBlock, MINB)
           wide = sc.top_wide;
           tris = sc.top_slots;
           sp = 0;
-          cur = 0;
+          cur = range_has_nan(w.min_t, w.max_t) ? kNoLeaf : 0;
           leaf = kNoLeaf;
           // see scene_fast_kernel: a direction that is not unit length goes to the list kernel
           const float len2 = (w.dx * w.dx + w.dy * w.dy) + w.dz * w.dz;

@@ -69,9 +69,14 @@ __device__ __forceinline__ void setup_ray(RayCtx &c, float ox, float oy, float o
   c.t_min = min_t;
 }
 
+// A NaN in min_t or max_t poisons the reference's safemax / safemin chains (the range value sits in the slot whose
+// NaN is NOT dropped, nanort.h:2316-2321): every slab test fails, the ray misses everything.  The kernels' fmaxf /
+// fminf would drop that NaN, so such rays are retired before they start.
+__device__ __forceinline__ bool range_has_nan(float min_t, float max_t) { return (min_t != min_t) | (max_t != max_t); }
+
 // Slab test of one box (nanort.h:2284-2325).  fmaxf/fminf drop a NaN operand
 // exactly like the reference's safemax/safemin do for the per-axis value in
-// the first slot; the running value is never NaN.
+// the first slot; the running value is never NaN (range_has_nan() rays never get here).
 __device__ __forceinline__ bool slab(const RayCtx &c, float lox, float loy, float loz, float hix,
                                      float hiy, float hiz, float min_t, float max_t, float &tnear) {
   float nx = c.sx ? hix : lox, fx = c.sx ? lox : hix;

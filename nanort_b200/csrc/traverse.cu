@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128)
     best.prim = 0xFFFFFFFFu;
     float hit_t = max_t;
     uint32_t stack[kConfStack];
-    int sp = 0;
+    int sp = range_has_nan(min_t, max_t) ? -1 : 0;
     stack[0] = 0;
     while (sp >= 0) {
       const Node40 *nd = nodes + stack[sp];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kFastBlock)
           best.prim = 0xFFFFFFFFu;
           ray_idx = (long long)mine;
           st.sp = 0;
-          cur = 0;  // root pair
+          cur = range_has_nan(min_t, max_t) ? kNone : 0;  // root pair
           leaf = kNone;
           if (COUNT) n_boxes += 1;  // the root box the reference pops first
         }
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
           best.prim = 0xFFFFFFFFu;
           ray_idx = (long long)mine;
           sp = 0;
-          cur = 0;
+          cur = range_has_nan(min_t, max_t) ? kNone : 0;
           leaf = kNone;
           if (COUNT) n_boxes += 1;
         }

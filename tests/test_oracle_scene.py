@@ -89,3 +89,18 @@ def test_cull_back_face_flag_is_inert_and_local_ray_is_unbounded():
     ph, pm = port.traverse(rays)
     assert np.array_equal(rm, pm) and _same_bits(rh[rm == 1], ph[pm == 1])
     assert (rh["t"][rm == 1] > 0.75).any()  # hits beyond the world max_t are still reported
+
+
+def test_port_scene_matches_reference_on_hostile_rays():
+    """Non-finite, zero-length and far-from-unit directions through Scene::Traverse: raw bits must match."""
+    from edge_cases import hostile_rays
+
+    insts = S.instances_mixed(12)
+    ref = orc.ReferenceScene(insts)
+    port = orc.PortScene(insts)
+    rays = hostile_rays(np.float32([-8, -4, -8]), np.float32([8, 4, 8]), n=8000, seed=5)
+    rays["min_t"] = np.where(np.isnan(rays["min_t"]), rays["min_t"], 0.0)
+    rh, rm = ref.traverse(rays, threads=4)
+    ph, pm = port.traverse(rays, threads=4)
+    assert np.array_equal(rm, pm) and _same_bits(rh[rm == 1], ph[pm == 1])
+    assert rm.sum() > 300

@@ -64,3 +64,25 @@ def test_reference_option_variants(port):
         assert np.array_equal(rm, pm)
         hit = rm.astype(bool)
         assert np.array_equal(rh[hit].view(np.uint32), ph[hit].view(np.uint32))
+
+
+@pytest.mark.parametrize("cpp11", [True, False])
+def test_port_equals_reference_on_hostile_rays_and_degenerate_triangles(port, cpp11):
+    """Non-finite / zero / denormal ray components, inverted ranges, zero-area triangles: the restatement must
+    follow the reference through every IEEE corner (raw bits, NaN payloads included)."""
+    from oracle import orc
+    from edge_cases import degenerate_mesh, hostile_rays
+
+    if not orc.Reference.available(cpp11):
+        pytest.skip("oracle/_ref not built")
+    ref = orc.Reference(cpp11)
+    v, f = degenerate_mesh()
+    acc = ref.build(v, f)
+    nodes, idx, _ = port.build(v, f, None, orc.MODE_CPP11 if cpp11 else 0)
+    _cmp_nodes(acc.nodes(), nodes)
+    assert np.array_equal(acc.indices(), idx)
+    rays = hostile_rays(v[:34 * 3].min(axis=0) - 1, v[:34 * 3].max(axis=0) + 1)
+    rh, rm = acc.traverse(rays)
+    ph, pm = port.traverse(nodes, idx, v, f, rays, cpp11=cpp11)
+    assert np.array_equal(rm, pm)
+    assert rh[rm == 1].tobytes() == ph[pm == 1].tobytes()
