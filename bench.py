@@ -21,6 +21,7 @@ reference's CheckForOccluder does).  One "step" = one pass over all samples of t
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -408,6 +409,29 @@ def main():
         e2e = {"value": rays_all * args.steps / float(tt.item()) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(36 * (n_primary + n_ao)), "d2h_bytes_per_step": int(17 * (n_primary + n_ao)),
                "api": "nrt_traverse (host rays -> host hits), pinned buffers, 2 calls per step"}
+        # for comparison, the wavefront entry point end to end: camera parameters in (host struct), framebuffer out to
+        # pinned host memory every step -- what a renderer pays when it hands the whole pass to the library
+        fb_host = torch.empty(WIDTH * HEIGHT, dtype=torch.float32).pin_memory()
+
+        def render_step():
+            accum.zero_()
+            acc.RenderAO(p, accum.data_ptr(), want_result=False)
+            fb_host.copy_(accum, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        for _ in range(2):
+            render_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            render_step()
+        dt = time.perf_counter() - t0
+        tr = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        e2e["render_api"] = {"value": rays_all * args.steps / float(tr.item()) / 1e6, "unit": UNIT,
+                             "api": "nrt_render_ao_device + framebuffer D2H per step",
+                             "h2d_bytes_per_step": C.sizeof(api.AoParams), "d2h_bytes_per_step": WIDTH * HEIGHT * 4}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same rays
     cpu_baseline = None

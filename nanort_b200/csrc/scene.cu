@@ -979,9 +979,12 @@ struct Scene {
   InstanceDev *d_inst = nullptr;
   float *d_state = nullptr;  // 76 floats per instance
   uint32_t max_blas_depth = 0;
-  uint32_t *d_overflow = nullptr;
-  size_t overflow_cap = 0;
-  unsigned long long *d_counters = nullptr;  // [0..15] cursor ring, [16] overflow count
+  // per-launch scratch, handed out round-robin so that traversals in flight on different streams never share it:
+  // slot k owns the ray cursor d_counters[k], the overflow count d_counters[4 + k] and its own overflow list
+  static constexpr int kSlots = 4;
+  uint32_t *d_overflow[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t overflow_cap[kSlots] = {0, 0, 0, 0};
+  unsigned long long *d_counters = nullptr;
   std::atomic<uint32_t> ring{0};
   cudaStream_t stream = nullptr;
   void *d_rays = nullptr, *d_hits = nullptr, *d_mask = nullptr;
@@ -1002,7 +1005,7 @@ static void scene_destroy(Scene *s) {
   }
   cudaFree(s->d_inst);
   cudaFree(s->d_state);
-  cudaFree(s->d_overflow);
+  for (int k = 0; k < Scene::kSlots; k++) cudaFree(s->d_overflow[k]);
   cudaFree(s->d_counters);
   cudaFree(s->d_rays);
   cudaFree(s->d_hits);
@@ -1035,18 +1038,21 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
     NRT_CUDA(cudaGetLastError());
     return NRT_OK;
   }
+  const int slot = (int)(sc->ring.fetch_add(1) % (uint32_t)Scene::kSlots);
+  uint32_t *d_overflow = nullptr;
   {
     std::lock_guard<std::mutex> lock(sc->mu);
-    if (sc->overflow_cap < n) {  // grows rarely; the free synchronises with launches still using the old list
-      cudaFree(sc->d_overflow);
-      sc->d_overflow = nullptr;
-      sc->overflow_cap = 0;
-      NRT_CUDA(cudaMalloc(&sc->d_overflow, sizeof(uint32_t) * n));
-      sc->overflow_cap = n;
+    if (sc->overflow_cap[slot] < n) {  // grows rarely; cudaFree waits for launches still using the old list
+      cudaFree(sc->d_overflow[slot]);
+      sc->d_overflow[slot] = nullptr;
+      sc->overflow_cap[slot] = 0;
+      NRT_CUDA(cudaMalloc(&sc->d_overflow[slot], sizeof(uint32_t) * n));
+      sc->overflow_cap[slot] = n;
     }
+    d_overflow = sc->d_overflow[slot];
   }
-  unsigned long long *cursor = sc->d_counters + (sc->ring.fetch_add(1) & 15u);
-  unsigned long long *ovf = sc->d_counters + 16;
+  unsigned long long *cursor = sc->d_counters + slot;
+  unsigned long long *ovf = sc->d_counters + Scene::kSlots + slot;
   NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
   NRT_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned long long), s));
   const size_t need = ((n + 31) / 32 + 3) / 4;
@@ -1055,13 +1061,13 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
     if (grid > need) grid = need;
     if (stack_need > 64)
       scene_unified_kernel<1024, 2><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
-                                                                        sc->d_overflow, ovf);
+                                                                        d_overflow, ovf);
     else if (variant >= 2) {
 #define NRT_SCENE_VARIANT(id, ...)                                                                              \
   case id: {                                                                                                    \
     size_t g = std::min(need, (size_t)sms * (FirstArg<__VA_ARGS__>::value));                                    \
     scene_unified_kernel<64, __VA_ARGS__><<<(unsigned)g, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask,   \
-                                                                              flags, cursor, sc->d_overflow, ovf); \
+                                                                              flags, cursor, d_overflow, ovf); \
   } break;
       switch (variant) {
         NRT_SCENE_VARIANT(2, 6, 16, 8)
@@ -1079,10 +1085,10 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
 #undef NRT_SCENE_VARIANT
     } else
       scene_unified_kernel<64, kUnifiedMinBlocks><<<(unsigned)grid, kSceneBlock, 0, s>>>(
-          dev, d_rays, n, d_hits, d_mask, flags, cursor, sc->d_overflow, ovf);
+          dev, d_rays, n, d_hits, d_mask, flags, cursor, d_overflow, ovf);
     NRT_CUDA(cudaGetLastError());
     scene_list_kernel<<<(unsigned)std::min<size_t>((n + 127) / 128, (size_t)sms * 4), 128, 0, s>>>(
-        dev, d_rays, n, sc->d_overflow, ovf, d_hits, d_mask, flags);
+        dev, d_rays, n, d_overflow, ovf, d_hits, d_mask, flags);
     NRT_CUDA(cudaGetLastError());
     return NRT_OK;
   }
@@ -1090,14 +1096,14 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
   if (grid > need) grid = need;
   if (sc->max_blas_depth + 2 > 48)
     scene_fast_kernel<512><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
-                                                                  sc->d_overflow, ovf);
+                                                                  d_overflow, ovf);
   else
     scene_fast_kernel<48><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
-                                                                 sc->d_overflow, ovf);
+                                                                 d_overflow, ovf);
   NRT_CUDA(cudaGetLastError());
   // rays that pierced more than 64 instance boxes (device-side count, usually zero)
   scene_list_kernel<<<(unsigned)std::min<size_t>((n + 127) / 128, (size_t)sms * 4), 128, 0, s>>>(
-      dev, d_rays, n, sc->d_overflow, ovf, d_hits, d_mask, flags);
+      dev, d_rays, n, d_overflow, ovf, d_hits, d_mask, flags);
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
 }
