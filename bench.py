@@ -222,6 +222,25 @@ class CpuReference:
 
 
 # ----------------------------------------------------------------------------------- main
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Multi-rank runs: keep this rank's threads -- and with them its pinned host buffers (first touch) -- on the CPUs
+    NVML reports as local to the rank's GPU, so that the host-buffer arm of 8 ranks does not cross the socket
+    interconnect.  Best effort; any failure leaves the default affinity."""
+    try:
+        import pynvml
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +296,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(torch, local_rank)
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
