@@ -129,203 +129,23 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------ fast path
-// Persistent warps pull rays from a global cursor and replace finished rays
-// with new ones once enough lanes of the warp have retired (warp-ballot
-// compaction of the ray pool).  Traversal is while-while with one postponed
-// leaf per lane over the 64-byte child-pair nodes; the per-lane stack keeps
-// (ref, entry distance) so that a popped subtree that now lies behind the
-// current best is skipped without touching memory -- the same visit set the
-// reference obtains by re-testing the box when it is popped (nanort.h:2532).
-// The first kStackSmem stack entries of every lane live in shared memory
-// ([entry][lane] -> bank == lane, conflict free); deeper entries spill to
-// thread-local memory.
-constexpr int kNone = kEmptyLeaf;
-constexpr int kFastBlock = 128;
-constexpr int kStackSmem = 16;
-
-template <int LOCAL_DEPTH>
-struct LaneStack {
-  uint2 *smem;  // &stk[0][threadIdx.x]; stride kFastBlock
-  uint2 local[LOCAL_DEPTH];
-  int sp;
-  __device__ __forceinline__ void push(int ref, float t) {
-    uint2 e = make_uint2((uint32_t)ref, __float_as_uint(t));
-    if (sp < kStackSmem)
-      smem[sp * kFastBlock] = e;
-    else if (sp - kStackSmem < LOCAL_DEPTH)
-      local[sp - kStackSmem] = e;
-    sp++;
-  }
-  __device__ __forceinline__ uint2 pop_raw() {
-    sp--;
-    if (sp < kStackSmem) return smem[sp * kFastBlock];
-    if (sp - kStackSmem < LOCAL_DEPTH) return local[sp - kStackSmem];
-    return make_uint2((uint32_t)kNone, 0u);
-  }
-};
-
-template <class Rays, int LOCAL_DEPTH, bool COUNT>
-__global__ void __launch_bounds__(kFastBlock)
-    traverse_fast_kernel(const WideNode *__restrict__ wide, const PackedTri *__restrict__ tris, Rays rays,
-                         size_t n, Hit16 *__restrict__ hits, uint8_t *__restrict__ mask, TraceOptions16 opt,
-                         uint32_t flags, unsigned long long *cursor, unsigned long long *counts,
-                         int refill_min, const unsigned long long *n_ptr) {
-  __shared__ uint2 stk[kStackSmem][kFastBlock];
-  if (n_ptr) n = (size_t)*n_ptr;  // ray count produced on the device (compacted AO queue)
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
-
-  LaneStack<LOCAL_DEPTH> st;
-  st.smem = &stk[0][threadIdx.x];
-  st.sp = 0;
-
-  RayCtx c;
-  Best best;
-  float max_t = 0.0f, min_t = 0.0f;
-  long long ray_idx = -1;
-  int cur = kNone, leaf = kNone;
-  bool exhausted = false;
-  unsigned long long n_boxes = 0, n_prims = 0;
-
-  for (;;) {
-    // ---- replace retired rays
-    unsigned dead = __ballot_sync(FULL_MASK, ray_idx < 0);
-    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= refill_min)) {
-      int cnt = __popc(dead);
-      int leader = __ffs(dead) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(cursor, (unsigned long long)cnt);
-      base = __shfl_sync(FULL_MASK, base, leader);
-      if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
-      if (ray_idx < 0) {
-        unsigned long long mine = base + (unsigned long long)__popc(dead & lt_mask);
-        if (mine < (unsigned long long)n) {
-          float ox, oy, oz, dx, dy, dz;
-          rays.load((size_t)mine, ox, oy, oz, dx, dy, dz, min_t, max_t);
-          setup_ray(c, ox, oy, oz, dx, dy, dz, min_t, cpp03);
-          best.t = max_t;
-          best.u = 0.0f;
-          best.v = 0.0f;
-          best.prim = 0xFFFFFFFFu;
-          ray_idx = (long long)mine;
-          st.sp = 0;
-          cur = range_has_nan(min_t, max_t) ? kNone : 0;  // root pair
-          leaf = kNone;
-          if (COUNT) n_boxes += 1;  // the root box the reference pops first
-        }
-      }
-    }
-    if (__all_sync(FULL_MASK, ray_idx < 0)) {
-      if (exhausted) break;
-      continue;
-    }
-
-    // ---- inner nodes: until every lane holds a leaf (or nothing)
-    while (__any_sync(FULL_MASK, cur >= 0)) {
-      if (cur >= 0) {
-        const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
-        float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-        int4 q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
-        float t0, t1;
-        bool h0 = slab(c, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, min_t, best.t, t0);
-        bool h1 = slab(c, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, min_t, best.t, t1);
-        if (COUNT) n_boxes += 2;
-        h0 = h0 && (q3.x != kNone);
-        h1 = h1 && (q3.y != kNone);
-        int next = kNone;
-        if (h0 && h1) {
-          bool swap = t1 < t0;
-          int nearr = swap ? q3.y : q3.x;
-          int farr = swap ? q3.x : q3.y;
-          st.push(farr, swap ? t0 : t1);
-          next = nearr;
-        } else if (h0) {
-          next = q3.x;
-        } else if (h1) {
-          next = q3.y;
-        } else {
-          // pop, skipping entries that now start behind the best hit
-          while (st.sp > 0) {
-            uint2 e = st.pop_raw();
-            if (__uint_as_float(e.y) <= best.t) {
-              next = (int)e.x;
-              break;
-            }
-          }
-        }
-        cur = next;
-        if (cur < 0 && cur != kNone && leaf == kNone) {
-          // postpone the first leaf and keep descending
-          leaf = cur;
-          cur = kNone;
-          while (st.sp > 0) {
-            uint2 e = st.pop_raw();
-            if (__uint_as_float(e.y) <= best.t) {
-              cur = (int)e.x;
-              break;
-            }
-          }
-        }
-      }
-    }
-
-    // ---- leaves
-    while (__any_sync(FULL_MASK, leaf != kNone)) {
-      if (leaf != kNone) {
-        const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)(~leaf));
-        for (;;) {
-          float4 a = __ldg(t), b = __ldg(t + 1), cc = __ldg(t + 2);
-          if (COUNT) n_prims++;
-          tri_test(c, opt, a, b, cc, best);
-          if (__float_as_uint(b.w) != 0u) break;  // last triangle of this leaf
-          t += 3;
-        }
-        leaf = kNone;
-        if (cur < 0 && cur != kNone) {
-          leaf = cur;
-          cur = kNone;
-          while (st.sp > 0) {
-            uint2 e = st.pop_raw();
-            if (__uint_as_float(e.y) <= best.t) {
-              cur = (int)e.x;
-              break;
-            }
-          }
-        }
-      }
-    }
-
-    // ---- retire
-    if (ray_idx >= 0 && cur == kNone && leaf == kNone) {
-      // cur == kNone with a non-empty stack can only mean all remaining entries were culled above
-      if (hits) write_result(hits, mask, (size_t)ray_idx, best, max_t);
-      ray_idx = -1;
-    }
-  }
-
-  if (COUNT) {
-    for (int o = 16; o > 0; o >>= 1) {
-      n_boxes += __shfl_down_sync(FULL_MASK, n_boxes, o);
-      n_prims += __shfl_down_sync(FULL_MASK, n_prims, o);
-    }
-    if (lane == 0) {
-      atomicAdd(counts + 0, n_boxes);
-      atomicAdd(counts + 1, n_prims);
-    }
-  }
-}
-
-// ------------------------------------------------------------------ fast path, second generation
-// Same algorithm and the same arithmetic as traverse_fast_kernel; restructured after the round-1 ncu
-// capture (profiles/r01_*): the kernel is issue bound with ~29 % of the issued instructions being
-// control flow (BRA/BSSY/BSYNC/ISETP) and 18 (primary) / 12 (AO) of 32 lanes active.  Changes:
+// Persistent warps pull rays from a global cursor and replace finished rays with new ones once enough lanes of the
+// warp have retired (warp-ballot compaction of the ray pool).  Traversal is while-while with one postponed leaf per
+// lane over the 64-byte child-pair nodes; the per-lane stack keeps (ref, entry distance) so that a popped subtree
+// that now lies behind the current best is skipped without touching memory -- the same visit set the reference
+// obtains by re-testing the box when it is popped (nanort.h:2532).
+//
+// Shaped by the round-1 ncu captures (profiles/r01_*): the first version of this kernel was issue bound with ~29 % of
+// the issued instructions being control flow and 18 (primary) / 12 (AO) of 32 lanes active.  Hence:
 //   * triangle test without early returns (one predicate at the end; only the fp64 fallback branches)
 //   * empty children carry an inverted box, so no reference checks in the node step
 //   * child selection by selects, one predicated push
-//   * the stack is addressed as a __shared__ array (LDS/STS instead of generic LD/ST)
-//   * policy knobs: lanes that must have retired before a refill, lanes that must still be descending
-//     for the node phase to continue, CTA size / minimum CTAs per SM
+//   * policy knobs: lanes that must have retired before a refill, lanes that must still be descending for the node
+//     phase to continue, CTA size / minimum CTAs per SM, stack entries kept in shared memory, TMA-staged top treelet
+constexpr int kNone = kEmptyLeaf;
+constexpr int kFastBlock = 128;
+constexpr int kStackSmem = 16;  // upper bound of the per-lane stack entries a policy may keep in shared memory
+
 template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_, int TREELET_ = 0, int STACK_SMEM_ = 16>
 struct FastPolicy {
   static constexpr int kStackEntries = STACK_SMEM_;  // stack entries per lane kept in shared memory (<= 16)
@@ -599,46 +419,18 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
                                                                 n_ptr, s);                                          \
     break;
     switch (variant) {
-      NRT_VARIANT(1, 128, 8, 8, 0)
       NRT_VARIANT(2, 128, 8, 1, 0)
-      NRT_VARIANT(3, 128, 8, 4, 0)
       NRT_VARIANT(4, 128, 8, 16, 0)
       NRT_VARIANT(5, 128, 8, 8, 8)
       NRT_VARIANT(6, 128, 8, 8, 16)
-      NRT_VARIANT(7, 128, 8, 8, 4)
       NRT_VARIANT(8, 64, 16, 8, 0)
       NRT_VARIANT(9, 256, 4, 8, 0)
       NRT_VARIANT(10, 128, 6, 8, 0)
       NRT_VARIANT(11, 128, 10, 8, 0)
-      NRT_VARIANT(12, 128, 8, 12, 12)
-      NRT_VARIANT(13, 128, 8, 4, 24)
-      NRT_VARIANT(14, 128, 10, 8, 8)
-      NRT_VARIANT(15, 128, 10, 8, 4)
-      NRT_VARIANT(16, 128, 12, 8, 8)
-      NRT_VARIANT(17, 64, 20, 8, 8)
-      NRT_VARIANT(18, 128, 10, 16, 8)
-      NRT_VARIANT(19, 128, 10, 8, 12)
-      NRT_VARIANT(20, 256, 5, 8, 8)
       NRT_VARIANT(21, 128, 9, 8, 8)
       NRT_VARIANT(30, 128, 10, 16, 8, 64)
-      NRT_VARIANT(31, 256, 5, 16, 8, 128)
-      NRT_VARIANT(32, 256, 5, 16, 8, 0)
-      NRT_VARIANT(33, 128, 9, 16, 8, 128)
       NRT_VARIANT(40, 128, 10, 16, 8, 0, 8)
-      NRT_VARIANT(41, 128, 10, 16, 8, 0, 0)
       NRT_VARIANT(42, 128, 10, 16, 8, 0, 4)
-      NRT_VARIANT(43, 128, 12, 16, 8, 0, 8)
-      case 255: {  // first-generation kernel, kept for A/B runs
-        const int sms = device_sm_count(a->device);
-        size_t grid = (size_t)sms * 8;
-        const size_t need_blocks = ((n + 31) / 32 + 3) / 4;
-        if (grid > need_blocks) grid = need_blocks;
-        if (grid == 0) grid = 1;
-        traverse_fast_kernel<Rays, 48, false><<<(unsigned)grid, kFastBlock, 0, s>>>(
-            a->d_wide, a->d_tris, rays, n, d_hits, d_mask, opt, flags, cursor, d_counts, 8, n_ptr);
-        e = cudaGetLastError();
-        break;
-      }
       default:
         set_error("nrt_traverse: unknown kernel variant in flags");
         return NRT_ERR_INVALID;
