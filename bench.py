@@ -372,7 +372,7 @@ def main():
     ms_max, rays_all = float(t.item()), float(tot.item())
     value = rays_all * args.steps / (ms_max * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (traverse_fast_kernel): algorithmic bytes / in-kernel time
+    # ---- roofline of the dominant kernel (traverse_fast2_kernel, both instantiations of a wave): algorithmic bytes / in-kernel time
     boxes_p, prims_p = acc.CountDevice(d_primary.data_ptr(), n_primary)
     boxes_a, prims_a = acc.CountDevice(d_ao.data_ptr(), n_ao)
     alg_bytes = 52.0 * (n_primary + n_ao) + 40.0 * (boxes_p + boxes_a) + 52.0 * (prims_p + prims_a)
@@ -390,7 +390,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "hbm", "kernel": "traverse_fast2_kernel<SoaRays, ..., PrimaryToAoEpilogue | AoAccumulateEpilogue>",
+        "bound": "hbm", "kernel": "traverse_fast2_kernel<CameraRays, ..., PrimaryToAoEpilogue> + traverse_fast2_kernel<SoaRays, ..., AoAccumulateEpilogue>",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
         "launches_per_step": int(r.traverse_launches), "avg_launch_ms": trav_ms / max(1, r.traverse_launches),
