@@ -21,8 +21,8 @@
 // :839-854 -- compiles unchanged and links against -lnanort_b200.  Extension: BVHAccel::TraverseBatch, the
 // batched form of Traverse that a wavefront renderer should use (one call per bounce, not per ray).
 //
-// Only float and the built-in triangle classes are supported (custom Prim/Pred/Intersector models would
-// need device-side user code).  There is no CPU fallback: without a CUDA device Build
+// float and double with the built-in triangle classes are supported (custom Prim/Pred/Intersector models would
+// need device-side user code); BVHAccel<double> is at the end of this file.  There is no CPU fallback: without a CUDA device Build
 // returns false and Traverse reports a miss after printing nrt_last_error() to stderr.
 #ifndef NANORT_H_
 #define NANORT_H_
@@ -312,7 +312,8 @@ class TriangleIntersector {
 // ---- BVHAccel ------------------------------------------------------------------------------------
 template <typename T>
 class BVHAccel {
-  static_assert(std::is_same<T, float>::value, "nanort_b200: only BVHAccel<float> runs on the GPU");
+  static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value,
+                "nanort_b200: BVHAccel runs on the GPU for float and double");
 };
 
 template <>
@@ -507,6 +508,123 @@ class BVHAccel<float> {
   BVHBuildOptions<float> options_;
   mutable BVHBuildStatistics stats_;
   unsigned int n_prims_;
+};
+
+// ---- BVHAccel<double> ----------------------------------------------------------------------------
+// The fp64 instantiation (nrt_build_f64 / nrt_traverse_f64): same members as above minus Dump / Load.  The tree's
+// topology comes from the production builder, every node box is exact in double, Traverse computes in double in the
+// reference's visiting order -- t / u / v carry the reference's bits for the reported primitive.
+static_assert(sizeof(Ray<double>) == 72, "nanort::Ray<double> layout");
+static_assert(sizeof(BVHNode<double>) == 64, "nanort::BVHNode<double> layout");
+static_assert(sizeof(BVHBuildOptions<double>) == 32, "nanort::BVHBuildOptions<double> layout");
+static_assert(sizeof(TriangleIntersection<double>) == 32, "nanort::TriangleIntersection<double> layout");
+
+template <>
+class BVHAccel<double> {
+ public:
+  BVHAccel() : mirrors_(false) {}
+
+  template <class Prim, class Pred>
+  bool Build(const unsigned int num_primitives, const Prim &p, const Pred &pred,
+             const BVHBuildOptions<double> &options = BVHBuildOptions<double>()) {
+    static_assert(std::is_same<Prim, TriangleMesh<double> >::value && std::is_same<Pred, TriangleSAHPred<double> >::value,
+                  "nanort_b200: Build runs on the GPU for TriangleMesh<double> + TriangleSAHPred<double> only");
+    (void)pred;
+    handle_.reset();
+    nodes_.clear();
+    indices_.clear();
+    mirrors_ = false;
+    stats_ = BVHBuildStatistics();
+    if (num_primitives == 0) return false;
+    nrt_accel_f64 *h = NULL;
+    if (nrt_build_f64(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), num_primitives, &options, &h) !=
+        NRT_OK) {
+      fprintf(stderr, "nanort_b200: Build<double> failed: %s\n", nrt_last_error());
+      return false;
+    }
+    handle_ = std::shared_ptr<nrt_accel_f64>(h, nrt_free_f64);
+    nrt_stats_f64(h, &stats_);
+    return true;
+  }
+
+  BVHBuildStatistics GetStatistics() const { return stats_; }
+  bool IsValid() const { return handle_ != NULL; }
+
+  template <class I, class H>
+  bool Traverse(const Ray<double> &ray, const I &intersector, H *isect,
+                const BVHTraceOptions &options = BVHTraceOptions()) const {
+    (void)intersector;
+    if (!handle_) return false;
+    TriangleIntersection<double> rec;
+    unsigned char hit = 0;
+    if (nrt_traverse_f64(handle_.get(), &ray, 1, &rec, &hit, &options, NANORT_B200_INVERSE_FLAG) != NRT_OK) {
+      fprintf(stderr, "nanort_b200: Traverse<double> failed: %s\n", nrt_last_error());
+      return false;
+    }
+    if (hit && isect) {
+      isect->t = rec.t;
+      isect->u = rec.u;
+      isect->v = rec.v;
+      isect->prim_id = rec.prim_id;
+    }
+    return hit != 0;
+  }
+
+  /// Extension: n rays at once (see BVHAccel<float>::TraverseBatch).
+  template <class I>
+  size_t TraverseBatch(const Ray<double> *rays, size_t n, const I &intersector, TriangleIntersection<double> *hits,
+                       unsigned char *hit_mask, const BVHTraceOptions &options = BVHTraceOptions()) const {
+    (void)intersector;
+    if (!handle_) return static_cast<size_t>(-1);
+    std::vector<unsigned char> tmp;
+    if (!hit_mask) {
+      tmp.resize(n);
+      hit_mask = tmp.data();
+    }
+    if (nrt_traverse_f64(handle_.get(), rays, n, hits, hit_mask, &options, NANORT_B200_INVERSE_FLAG) != NRT_OK) {
+      fprintf(stderr, "nanort_b200: TraverseBatch<double> failed: %s\n", nrt_last_error());
+      return static_cast<size_t>(-1);
+    }
+    size_t c = 0;
+    for (size_t i = 0; i < n; i++) c += hit_mask[i] ? 1 : 0;
+    return c;
+  }
+
+  const std::vector<BVHNode<double> > &GetNodes() const {
+    Mirror();
+    return nodes_;
+  }
+  const std::vector<unsigned int> &GetIndices() const {
+    Mirror();
+    return indices_;
+  }
+
+  void BoundingBox(double bmin[3], double bmax[3]) const {
+    if (!handle_) {
+      bmin[0] = bmin[1] = bmin[2] = std::numeric_limits<double>::max();
+      bmax[0] = bmax[1] = bmax[2] = -std::numeric_limits<double>::max();
+      return;
+    }
+    nrt_bounding_box_f64(handle_.get(), bmin, bmax);
+  }
+
+ private:
+  void Mirror() const {
+    if (mirrors_ || !handle_) return;
+    const void *pn = NULL;
+    const uint32_t *pi = NULL;
+    size_t nn = 0, ni = 0;
+    if (nrt_nodes_f64(handle_.get(), &pn, &nn, &pi, &ni) != NRT_OK) return;
+    nodes_.resize(nn);
+    if (nn) memcpy(nodes_.data(), pn, nn * sizeof(BVHNode<double>));
+    indices_.assign(pi, pi + ni);
+    mirrors_ = true;
+  }
+  mutable std::shared_ptr<nrt_accel_f64> handle_;
+  mutable std::vector<BVHNode<double> > nodes_;
+  mutable std::vector<unsigned int> indices_;
+  mutable bool mirrors_;
+  mutable BVHBuildStatistics stats_;
 };
 
 }  // namespace nanort

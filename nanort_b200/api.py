@@ -53,6 +53,7 @@ EXPORTS = [
     "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device", "nrt_render_path_device",
     "nrt_scene_commit", "nrt_scene_free", "nrt_scene_bounding_box", "nrt_scene_nodes", "nrt_scene_instance_state",
     "nrt_scene_traverse", "nrt_scene_traverse_device",
+    "nrt_build_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
 ]
 
 
@@ -148,6 +149,13 @@ def lib():
     L.nrt_scene_instance_state.argtypes = [vp, u32, vp]
     L.nrt_scene_traverse.argtypes = [vp, vp, sz, vp, vp, u32]
     L.nrt_scene_traverse_device.argtypes = [vp, vp, sz, vp, vp, u32, vp]
+    L.nrt_build_f64.argtypes = [vp, sz, sz, vp, u32, vp, C.POINTER(vp)]
+    L.nrt_free_f64.argtypes = [vp]
+    L.nrt_free_f64.restype = None
+    L.nrt_stats_f64.argtypes = [vp, vp]
+    L.nrt_bounding_box_f64.argtypes = [vp, vp, vp]
+    L.nrt_nodes_f64.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
+    L.nrt_traverse_f64.argtypes = [vp, vp, sz, vp, vp, vp, u32]
     _lib = L
     return L
 
@@ -430,3 +438,80 @@ class Scene:
         _check(lib().nrt_scene_traverse_device(self._h, C.c_void_p(d_rays_ptr), int(n), C.c_void_p(d_hits_ptr),
                                                C.c_void_p(d_mask_ptr) if d_mask_ptr else None, int(flags),
                                                C.c_void_p(stream) if stream else None))
+
+
+# ------------------------------------------------------------------ BVHAccel<double>
+RAY64_DTYPE = np.dtype([("org", "<f8", (3,)), ("dir", "<f8", (3,)), ("min_t", "<f8"), ("max_t", "<f8"),
+                        ("type", "<u4"), ("pad", "<u4")])
+HIT64_DTYPE = np.dtype([("u", "<f8"), ("v", "<f8"), ("t", "<f8"), ("prim_id", "<u4"), ("pad", "<u4")])
+NODE64_DTYPE = np.dtype([("bmin", "<f8", (3,)), ("bmax", "<f8", (3,)), ("flag", "<i4"), ("axis", "<i4"),
+                         ("data", "<u4", (2,))])
+BUILD_OPT64_DTYPE = np.dtype([("cost_t_aabb", "<f8"), ("min_leaf_primitives", "<u4"), ("max_tree_depth", "<u4"),
+                              ("bin_size", "<u4"), ("shallow_depth", "<u4"),
+                              ("min_primitives_for_parallel_build", "<u4"), ("cache_bbox", "u1"), ("pad", "u1", (3,))])
+assert (RAY64_DTYPE.itemsize, HIT64_DTYPE.itemsize, NODE64_DTYPE.itemsize, BUILD_OPT64_DTYPE.itemsize) == (72, 32, 64, 32)
+
+
+class BVHAccelF64:
+    """Mirror of nanort::BVHAccel<double> (nrt_build_f64 / nrt_traverse_f64)."""
+
+    def __init__(self, device=None):
+        self._h = None
+        self._device = device
+
+    def free(self):
+        if self._h:
+            lib().nrt_free_f64(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def Build(self, num_primitives, vertices, faces, options=None, vertex_stride_bytes=24):
+        self.free()
+        if num_primitives == 0:
+            return False
+        vertices = np.ascontiguousarray(vertices, np.float64)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        if self._device is not None:
+            _check(lib().nrt_set_device(int(self._device)))
+        h = C.c_void_p()
+        n_verts = vertices.size * 8 // vertex_stride_bytes
+        _check(lib().nrt_build_f64(_p(vertices), vertex_stride_bytes, n_verts, _p(faces), int(num_primitives),
+                                   _p(options), C.byref(h)))
+        self._h = h
+        return True
+
+    def GetStatistics(self):
+        s = np.zeros(1, STATS_DTYPE)
+        _check(lib().nrt_stats_f64(self._h, _p(s)))
+        return {k: s[k][0].item() for k in STATS_DTYPE.names}
+
+    def BoundingBox(self):
+        a, b = np.zeros(3, np.float64), np.zeros(3, np.float64)
+        _check(lib().nrt_bounding_box_f64(self._h, _p(a), _p(b)))
+        return a, b
+
+    def GetNodes(self):
+        return self._mirror()[0]
+
+    def GetIndices(self):
+        return self._mirror()[1]
+
+    def _mirror(self):
+        pn, nn, pi, ni = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        _check(lib().nrt_nodes_f64(self._h, C.byref(pn), C.byref(nn), C.byref(pi), C.byref(ni)))
+        nodes = np.frombuffer((C.c_char * (nn.value * 64)).from_address(pn.value), NODE64_DTYPE).copy()
+        idx = np.frombuffer((C.c_char * (ni.value * 4)).from_address(pi.value), np.uint32).copy()
+        return nodes, idx
+
+    def Traverse(self, rays, options=None, flags=0):
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype.itemsize == 72
+        n = len(rays)
+        hits, mask = np.zeros(n, HIT64_DTYPE), np.zeros(n, np.uint8)
+        _check(lib().nrt_traverse_f64(self._h, _p(rays), n, _p(hits), _p(mask), _p(options), int(flags)))
+        return hits, mask

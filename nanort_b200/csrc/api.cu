@@ -20,7 +20,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   return e == cudaErrorMemoryAllocation ? NRT_ERR_NOMEM : NRT_ERR_CUDA;
 }
 
-static int select_device() {
+int select_device(int *device_out) {
+  if (device_out) *device_out = g_device;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0) {
@@ -151,7 +152,7 @@ int nrt_build_ex(const float *verts, size_t stride_bytes, size_t n_verts, const 
     g_err = "nrt_build: bad geometry pointers / stride";
     return NRT_ERR_INVALID;
   }
-  int rc = select_device();
+  int rc = select_device(nullptr);
   if (rc != NRT_OK) return rc;
   Accel *a = new (std::nothrow) Accel();
   if (!a) return NRT_ERR_NOMEM;
@@ -196,7 +197,7 @@ int nrt_adopt(const void *nodes_40B, size_t n_nodes, const uint32_t *indices, si
     g_err = "nrt_adopt: bad arguments";
     return NRT_ERR_INVALID;
   }
-  int rc = select_device();
+  int rc = select_device(nullptr);
   if (rc != NRT_OK) return rc;
   Accel *a = new (std::nothrow) Accel();
   if (!a) return NRT_ERR_NOMEM;

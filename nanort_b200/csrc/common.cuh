@@ -179,5 +179,7 @@ int build_on_device(Accel *a, cudaStream_t s);
 int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s);
 
 int device_sm_count(int device);
+// api.cu: makes the calling thread's selected device current (nrt_set_device); NRT_ERR_CUDA without a usable device
+int select_device(int *device_out);
 
 }  // namespace nrt

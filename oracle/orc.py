@@ -420,3 +420,95 @@ class ReferenceScene:
         hits, mask = np.zeros(n, SG_HIT_DTYPE), np.zeros(n, np.uint8)
         self.lib.refsg_traverse_batch(self.h, _p(rays), n, _p(hits), _p(mask), threads)
         return hits, mask
+
+
+# ------------------------------------------------------------------ BVHAccel<double>: the reference itself is the checker
+RAY64_DTYPE = np.dtype([("org", "<f8", (3,)), ("dir", "<f8", (3,)), ("min_t", "<f8"), ("max_t", "<f8"),
+                        ("type", "<u4"), ("pad", "<u4")])
+HIT64_DTYPE = np.dtype([("u", "<f8"), ("v", "<f8"), ("t", "<f8"), ("prim_id", "<u4"), ("pad", "<u4")])
+NODE64_DTYPE = np.dtype([("bmin", "<f8", (3,)), ("bmax", "<f8", (3,)), ("flag", "<i4"), ("axis", "<i4"),
+                         ("data", "<u4", (2,))])
+
+
+class ReferenceF64:
+    """nanort::BVHAccel<double> of the unmodified reference (oracle/_ref, ref64_* in oracle/ref_shim.cc).  There is
+    no C restatement of the fp64 instantiation: fp64 parity is checked against the reference directly and against
+    the committed golden vectors (tests/golden/regression30.npz)."""
+
+    def __init__(self, cpp11=True):
+        name = "libnanort_ref.so" if cpp11 else "libnanort_ref03.so"
+        path = os.path.join(HERE, "_ref", name)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = L = C.CDLL(path)
+        L.ref64_sizes.argtypes = [C.c_void_p]
+        L.ref64_build.restype = C.c_void_p
+        L.ref64_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.ref64_adopt.restype = C.c_void_p
+        L.ref64_adopt.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ref64_free.argtypes = [C.c_void_p]
+        L.ref64_num_nodes.restype = C.c_size_t
+        L.ref64_num_nodes.argtypes = [C.c_void_p]
+        L.ref64_copy_nodes.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref64_copy_indices.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref64_bounding_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref64_traverse_batch.restype = C.c_size_t
+        L.ref64_traverse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int]
+
+    def sizes(self):
+        s = np.zeros(5, np.uint32)
+        self.lib.ref64_sizes(_p(s))
+        return [int(x) for x in s]
+
+    class Accel:
+        def __init__(self, ref, handle, verts, faces):
+            self.ref, self.h, self.verts, self.faces = ref, handle, verts, faces
+
+        def __del__(self):
+            if self.h:
+                self.ref.lib.ref64_free(self.h)
+                self.h = None
+
+        def nodes(self):
+            n = self.ref.lib.ref64_num_nodes(self.h)
+            out = np.zeros(n, NODE64_DTYPE)
+            self.ref.lib.ref64_copy_nodes(self.h, _p(out))
+            return out
+
+        def indices(self):
+            out = np.zeros(len(self.faces), np.uint32)
+            self.ref.lib.ref64_copy_indices(self.h, _p(out))
+            return out
+
+        def bounding_box(self):
+            a, b = np.zeros(3), np.zeros(3)
+            self.ref.lib.ref64_bounding_box(self.h, _p(a), _p(b))
+            return a, b
+
+        def traverse(self, rays, topts=None, threads=1):
+            rays = np.ascontiguousarray(rays)
+            assert rays.dtype.itemsize == 72
+            n = len(rays)
+            hits, mask = np.zeros(n, HIT64_DTYPE), np.zeros(n, np.uint8)
+            self.ref.lib.ref64_traverse_batch(self.h, _p(rays), n, _p(hits), _p(mask),
+                                              _p(topts) if topts is not None else None, threads)
+            return hits, mask
+
+    def build(self, verts, faces, opts=None):
+        verts = np.ascontiguousarray(verts, np.float64)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        h = self.lib.ref64_build(_p(verts), 24, _p(faces), len(faces), _p(opts) if opts is not None else None)
+        return self.Accel(self, h, verts, faces) if h else None
+
+    def adopt(self, nodes, indices, verts, faces):
+        nodes = np.ascontiguousarray(nodes)
+        assert nodes.dtype.itemsize == 64
+        indices = np.ascontiguousarray(indices, np.uint32)
+        verts = np.ascontiguousarray(verts, np.float64)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        h = self.lib.ref64_adopt(_p(nodes), len(nodes), _p(indices), len(indices), _p(verts), 24, _p(faces))
+        acc = self.Accel(self, h, verts, faces) if h else None
+        if acc:
+            acc._keep = (nodes, indices)
+        return acc

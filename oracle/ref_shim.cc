@@ -221,4 +221,118 @@ int ref_traverse_one_f64(const double *verts, const uint32_t *faces, uint32_t n_
   return hit ? 1 : 0;
 }
 
+// ---- BVHAccel<double>: the same entry points for the fp64 instantiation of the reference -------------------
+struct RefAccelD {
+  nanort::BVHAccel<double> accel;
+  const double *verts;
+  const unsigned int *faces;
+  size_t stride;
+};
+
+void ref64_sizes(uint32_t out[5]) {
+  out[0] = sizeof(nanort::BVHNode<double>);
+  out[1] = sizeof(nanort::Ray<double>);
+  out[2] = sizeof(nanort::TriangleIntersection<double>);
+  out[3] = sizeof(nanort::BVHBuildOptions<double>);
+  out[4] = sizeof(nanort::BVHTraceOptions);
+}
+
+void *ref64_build(const double *verts, size_t stride, const uint32_t *faces, uint32_t n_prims,
+                  const void *build_opts32) {
+  RefAccelD *r = new RefAccelD();
+  r->verts = verts;
+  r->faces = faces;
+  r->stride = stride;
+  nanort::BVHBuildOptions<double> o;
+  if (build_opts32) std::memcpy(&o, build_opts32, sizeof(o));
+  nanort::TriangleMesh<double> mesh(verts, faces, stride);
+  nanort::TriangleSAHPred<double> pred(verts, faces, stride);
+  if (!r->accel.Build(n_prims, mesh, pred, o)) {
+    delete r;
+    return NULL;
+  }
+  return r;
+}
+
+// a (nodes, indices) pair from elsewhere -- e.g. the GPU's fp64 tree -- through the reference's own Load
+void *ref64_adopt(const void *nodes64, size_t n_nodes, const uint32_t *indices, size_t n_indices,
+                  const double *verts, size_t stride, const uint32_t *faces) {
+  size_t bytes = 2 * sizeof(size_t) + n_nodes * sizeof(nanort::BVHNode<double>) + n_indices * sizeof(uint32_t);
+  std::vector<unsigned char> buf(bytes);
+  unsigned char *p = buf.data();
+  std::memcpy(p, &n_nodes, sizeof(size_t));
+  p += sizeof(size_t);
+  std::memcpy(p, nodes64, n_nodes * sizeof(nanort::BVHNode<double>));
+  p += n_nodes * sizeof(nanort::BVHNode<double>);
+  std::memcpy(p, &n_indices, sizeof(size_t));
+  p += sizeof(size_t);
+  std::memcpy(p, indices, n_indices * sizeof(uint32_t));
+  FILE *fp = fmemopen(buf.data(), bytes, "rb");
+  if (!fp) return NULL;
+  RefAccelD *r = new RefAccelD();
+  r->verts = verts;
+  r->faces = faces;
+  r->stride = stride;
+  bool ok = r->accel.Load(fp);
+  fclose(fp);
+  if (!ok) {
+    delete r;
+    return NULL;
+  }
+  return r;
+}
+
+void ref64_free(void *h) { delete static_cast<RefAccelD *>(h); }
+size_t ref64_num_nodes(const void *h) { return static_cast<const RefAccelD *>(h)->accel.GetNodes().size(); }
+void ref64_copy_nodes(const void *h, void *out64) {
+  const std::vector<nanort::BVHNode<double> > &n = static_cast<const RefAccelD *>(h)->accel.GetNodes();
+  std::memcpy(out64, n.data(), n.size() * sizeof(nanort::BVHNode<double>));
+}
+void ref64_copy_indices(const void *h, uint32_t *out) {
+  const std::vector<unsigned int> &n = static_cast<const RefAccelD *>(h)->accel.GetIndices();
+  std::memcpy(out, n.data(), n.size() * sizeof(uint32_t));
+}
+void ref64_bounding_box(const void *h, double bmin[3], double bmax[3]) {
+  static_cast<const RefAccelD *>(h)->accel.BoundingBox(bmin, bmax);
+}
+
+size_t ref64_traverse_batch(const void *h, const void *rays72, size_t n_rays, void *hits32, uint8_t *mask,
+                            const void *trace_opts16, int n_threads) {
+  const RefAccelD *r = static_cast<const RefAccelD *>(h);
+  const nanort::Ray<double> *rays = static_cast<const nanort::Ray<double> *>(rays72);
+  nanort::TriangleIntersection<double> *hits = static_cast<nanort::TriangleIntersection<double> *>(hits32);
+  nanort::BVHTraceOptions topt;
+  if (trace_opts16) std::memcpy(&topt, trace_opts16, sizeof(topt));
+  if (n_threads < 1) n_threads = 1;
+  std::atomic<size_t> next(0), total(0);
+  auto work = [&]() {
+    size_t local = 0;
+    for (;;) {
+      size_t b = next.fetch_add(1024);
+      if (b >= n_rays) break;
+      size_t e = b + 1024 < n_rays ? b + 1024 : n_rays;
+      for (size_t i = b; i < e; i++) {
+        nanort::TriangleIntersector<double, nanort::TriangleIntersection<double> > isector(r->verts, r->faces,
+                                                                                           r->stride);
+        nanort::TriangleIntersection<double> isect;
+        bool hit = r->accel.Traverse(rays[i], isector, &isect, topt);
+        if (hit) {
+          hits[i] = isect;
+          local++;
+        }
+        if (mask) mask[i] = hit ? 1 : 0;
+      }
+    }
+    total += local;
+  };
+  if (n_threads == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work);
+    for (auto &t : th) t.join();
+  }
+  return total.load();
+}
+
 }  // extern "C"

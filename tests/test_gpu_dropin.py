@@ -101,3 +101,17 @@ def test_nanosg_drop_in_fast_mode_same_hits():
     assert len(diff) <= 0.01 * len(want)
     for i in diff:  # only the pick differs, not the distance
         assert got[i].split(" t ")[1].split()[0] == want[i].split(" t ")[1].split()[0]
+
+
+def test_f64_drop_in_prints_the_reference_output():
+    """examples/f64_check.cc (BVHAccel<double>: the reference's regression scenario + 2,000 double rays over a
+    height field) against include/nanort.h must print what it prints against the reference header: every t / u / v
+    as raw 64-bit patterns.  (The mesh has no coincident surfaces, so no tie can pick another triangle.)"""
+    import gzip
+
+    if not os.path.exists(os.path.join(BIN, "f64_check_b200")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
+    got = _run("f64_check_b200")
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "f64_check_ref.txt.gz"), "rt") as f:
+        want = f.read().strip().splitlines()
+    assert len(want) > 1500 and got == want

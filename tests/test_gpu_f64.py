@@ -1,0 +1,124 @@
+"""BVHAccel<double> on the GPU (nrt_build_f64 / nrt_traverse_f64).  Checker: the unmodified reference's fp64
+instantiation (oracle/_ref, ref64_*) and the committed golden vectors of the reference's regression program."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _ray64(org, d, min_t=0.0, max_t=1e30):
+    from nanort_b200 import api
+
+    r = np.zeros(1, api.RAY64_DTYPE)
+    r["org"], r["dir"], r["min_t"], r["max_t"] = org, d, min_t, max_t
+    return r
+
+
+def test_regression30_in_double_matches_the_reference_bits():
+    """test/regression/possible-accuracy-problem-30/main.cc:24-76 in its native precision: hit, u = 0.68,
+    v = 0.131201, and t / u / v bit-equal to what the reference computed (tests/golden/regression30.npz)."""
+    from nanort_b200 import api
+
+    d = np.load(os.path.join(G, "regression30.npz"))
+    acc = api.BVHAccelF64()
+    assert acc.Build(1, d["verts"], d["faces"])
+    org = np.array([-0.36, 7.93890843, 1.2160368])
+    for k, dx in (("plain", 0.0), ("bug", -5.30287619e-17)):
+        dd = np.array([dx, -8.66025404e-01, -0.5])
+        dd = dd / np.sqrt((dd * dd).sum())
+        h, m = acc.Traverse(_ray64(org, dd))
+        want = d[f"f64_{k}"]  # [hit, t, u, v, prim]
+        assert m[0] == 1 == int(want[0])
+        assert (h["t"][0], h["u"][0], h["v"][0]) == (want[1], want[2], want[3]) and h["prim_id"][0] == int(want[4])
+        assert abs(h["u"][0] - 0.68) < 1e-6 and abs(h["v"][0] - 0.131201) < 1e-6
+
+
+def _scene64(seed=3):
+    """Sphere grid with coordinates that do not survive a round trip through float."""
+    from nanort_b200 import scenes as S
+
+    v, f = S.sphere_grid(nx=3, nz=3)
+    rng = np.random.default_rng(seed)
+    v64 = v.astype(np.float64) * (1.0 + 1e-9 * rng.standard_normal(v.shape)) + 1e-11 * rng.standard_normal(v.shape)
+    assert not np.array_equal(v64.astype(np.float32).astype(np.float64), v64)
+    return v64, f
+
+
+def _rays64(v64, n, seed):
+    from nanort_b200 import api, scenes as S
+
+    r32 = S.incoherent_rays(v64.min(axis=0).astype(np.float32), v64.max(axis=0).astype(np.float32), n, seed=seed)
+    rng = np.random.default_rng(seed)
+    r = np.zeros(n, api.RAY64_DTYPE)
+    r["org"] = r32["org"].astype(np.float64) + 1e-10 * rng.standard_normal((n, 3))
+    d = r32["dir"].astype(np.float64)
+    nz = d != 0.0
+    d = np.where(nz, d + 1e-12 * rng.standard_normal((n, 3)), d)  # keep the exact zeros / -0.0 of the family
+    r["dir"] = d
+    r["min_t"], r["max_t"] = r32["min_t"], r32["max_t"]
+    return r
+
+
+def test_f64_tree_is_valid_and_exact():
+    from nanort_b200 import api
+
+    v64, f = _scene64()
+    acc = api.BVHAccelF64()
+    acc.Build(len(f), v64, f)
+    nodes, idx = acc.GetNodes(), acc.GetIndices()
+    st = acc.GetStatistics()
+    assert st["num_leaf_nodes"] == st["num_branch_nodes"] + 1 == (nodes["flag"] == 1).sum()
+    assert np.array_equal(np.sort(idx), np.arange(len(f), dtype=np.uint32))
+    tri = v64[f]  # (n, 3, 3)
+    tmin, tmax = tri.min(axis=1), tri.max(axis=1)
+    for i in np.nonzero(nodes["flag"] == 1)[0]:  # leaf boxes: exact double min / max of their triangles
+        p = idx[nodes["data"][i, 1]: nodes["data"][i, 1] + nodes["data"][i, 0]]
+        assert np.array_equal(nodes["bmin"][i], tmin[p].min(axis=0)) and np.array_equal(nodes["bmax"][i], tmax[p].max(axis=0))
+    br = np.nonzero(nodes["flag"] == 0)[0]
+    l, r = nodes["data"][br, 0], nodes["data"][br, 1]  # branch boxes: exact unions of their children
+    assert np.array_equal(nodes["bmin"][br], np.minimum(nodes["bmin"][l], nodes["bmin"][r]))
+    assert np.array_equal(nodes["bmax"][br], np.maximum(nodes["bmax"][l], nodes["bmax"][r]))
+    a, b = acc.BoundingBox()
+    assert np.array_equal(a, v64[f.ravel()].min(axis=0)) and np.array_equal(b, v64[f.ravel()].max(axis=0))
+
+
+@pytest.mark.parametrize("cpp11", [True, False])
+def test_f64_hits_match_the_reference(cpp11):
+    from nanort_b200 import api
+    from oracle import orc
+
+    if not orc.Reference.available(cpp11):
+        pytest.skip("oracle/_ref not built")
+    ref = orc.ReferenceF64(cpp11)
+    assert ref.sizes() == [64, 72, 32, 32, 16]
+    v64, f = _scene64()
+    rays = _rays64(v64, 60000, seed=4)
+    acc = api.BVHAccelF64()
+    acc.Build(len(f), v64, f)
+    flags = 0 if cpp11 else api.TRAVERSE_CPP03_INVERSE
+    gh, gm = acc.Traverse(rays, flags=flags)
+    # (1) the reference's own Build + Traverse in double: same hits; same bits for the same primitive
+    racc = ref.build(v64, f)
+    rh, rm = racc.traverse(rays, threads=8)
+    assert rm.sum() > 5000 and np.array_equal(rm, gm)
+    hit = rm == 1
+    same = hit & (rh["prim_id"] == gh["prim_id"])
+    for k in ("t", "u", "v"):
+        assert np.array_equal(rh[k][same].view(np.uint64), gh[k][same].view(np.uint64)), k
+    other = hit & ~same  # a different primitive only at exactly the same distance (shared edges)
+    assert other.sum() <= 0.002 * hit.sum() and np.array_equal(rh["t"][other], gh["t"][other])
+    # (2) the reference walking the GPU's node array (its own Load): everything bit-equal, ties included
+    adopted = ref.adopt(acc.GetNodes(), acc.GetIndices(), v64, f)
+    ah, am = adopted.traverse(rays, threads=8)
+    assert np.array_equal(am, gm)
+    for k in ("t", "u", "v", "prim_id"):
+        assert ah[k][hit].tobytes() == gh[k][hit].tobytes(), k
+    # (3) trace options
+    o = orc.trace_options(cull_back_face=1, skip_prim_id=int(gh["prim_id"][hit][0]))
+    gh2, gm2 = acc.Traverse(rays[:8000], options=o, flags=flags)
+    ah2, am2 = adopted.traverse(rays[:8000], topts=o, threads=4)
+    assert np.array_equal(am2, gm2) and ah2[am2 == 1].tobytes() == gh2[gm2 == 1].tobytes()
+    assert gm2.sum() < gm[:8000].sum()
