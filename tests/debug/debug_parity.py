@@ -1,6 +1,6 @@
 """Dumps fast-path vs oracle mismatches for offline analysis (gpurun_out/mismatch_*.npz)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import orc
 from nanort_b200 import api, scenes as S

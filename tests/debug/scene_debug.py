@@ -1,7 +1,7 @@
 """Debug helper: fast two-level traversal vs the oracle on the row scene; prints the mismatch classes."""
 import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from nanort_b200 import api, scenes as S
 from oracle import orc

@@ -59,20 +59,3 @@ if cx <= 10:
     nf = len(base[1])
     same = (h2["node_id"][both].astype(np.int64) * nf + h2["prim_id"][both]) == h1["prim_id"][both]
     print("same triangle", same.mean(), "max rel dt", (np.abs(h2["t"][both][same] - h1["t"][both][same]) / h1["t"][both][same]).max())
-
-if "--cpu" in sys.argv:
-    # the unmodified reference scene graph on the host cores, on a sample of the same rays
-    from oracle import orc
-    import os as _os
-    t0 = time.time(); ref = orc.ReferenceScene(insts, cpp11=True); t1 = time.time()
-    print(f"reference nanosg: AddNode+Commit of {len(insts)} nodes ({len(base[1])} tris each) wall {t1-t0:.2f} s")
-    sample = rays[:: max(1, n // 400000)]
-    th = _os.cpu_count()
-    t0 = time.time(); rh, rm = ref.traverse(sample, threads=th); t1 = time.time()
-    print(f"reference nanosg Scene::Traverse: {len(sample)} rays, {th} threads, {len(sample)/(t1-t0)/1e6:.3f} Mrays/s")
-    idx = np.arange(0, n, max(1, n // 400000))
-    print("mask agreement vs reference", (rm == m2[idx]).mean())
-    both = (rm == 1) & (m2[idx] == 1)
-    same = (rh["node_id"][both] == h2["node_id"][idx][both]) & (rh["prim_id"][both] == h2["prim_id"][idx][both])
-    print("same (instance, triangle)", same.mean(), "records bit-equal where same:",
-          rh[both][same].tobytes() == h2[idx][both][same].tobytes())
