@@ -9,12 +9,12 @@
 //   BVHAccel::ListNodeIntersections +
 //   TestLeafNodeIntersections                 nanort.h:2558-2692                 scene_list_kernel
 //   NodeBBoxIntersector::Intersect            examples/nanosg/nanosg.h:597-637   raw_box()
-//   nanosg::Scene::Traverse                   examples/nanosg/nanosg.h:779-875   scene_list_kernel / scene_fast_kernel
+//   nanosg::Scene::Traverse                   examples/nanosg/nanosg.h:779-875   scene_list_kernel / scene_unified_kernel
 //
 // Two kernels.  scene_list_kernel is the reference's algorithm verbatim, one thread per ray: collect the (at most 64)
 // nearest instance boxes in a max-heap that follows libstdc++'s push_heap / pop_heap sift rules, visit them nearest
-// first, walk each instance's nanort-layout tree in the reference's order.  scene_fast_kernel is the production path:
-// persistent warps, one pass over the top-level tree (sub-trees that start behind the current nearest hit are
+// first, walk each instance's nanort-layout tree in the reference's order.  scene_unified_kernel is the production
+// path: persistent warps, one pass over the top-level tree (sub-trees that start behind the current nearest hit are
 // skipped), each candidate instance traversed with the 64-byte child-pair nodes exactly like traverse_fast2_kernel.
 // Both compute the local ray, the world hit point and the world distance with the reference's operation order, so a
 // hit record is bit-identical to the reference's whenever both pick the same (instance, triangle); the pick itself
@@ -474,233 +474,7 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// ---- production kernel ---------------------------------------------------------------------------------------------
-// Lane states: dead (ray < 0) | top-level walk (inst < 0) | inside an instance (inst >= 0, while-while over the
-// instance's WideNodes).  One outer iteration = refill, top-level steps until every walking lane has entered an
-// instance or finished, inner nodes, leaves, instance exits, retirement.
-constexpr int kTopStack = 64;   // the host falls back to the list kernel for deeper top-level trees
 constexpr int kSceneBlock = 128;
-
-template <int LOCAL_DEPTH>
-__global__ void __launch_bounds__(kSceneBlock, 5)
-    scene_fast_kernel(SceneDev sc, const Ray36 *__restrict__ rays, size_t n, SceneHit32 *__restrict__ hits,
-                      uint8_t *__restrict__ mask, uint32_t flags, unsigned long long *cursor,
-                      uint32_t *__restrict__ overflow, unsigned long long *overflow_count) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const bool cpp03 = (flags & NRT_TRAVERSE_CPP03_INVERSE) != 0;
-  const TraceOptions16 opt = local_trace_options();
-
-  long long ray_idx = -1;
-  bool exhausted = false;
-  WorldRay w;
-  RayCtx wc;             // top-level walk constants (safe inverse, signs)
-  float rix = 0.0f, riy = 0.0f, riz = 0.0f;
-  SceneBest nearest;
-  uint32_t tstk[kTopStack];
-  int tsp = 0;
-  uint32_t leaf_pos = 0, leaf_end = 0, n_boxes = 0;
-  // instance state
-  int inst = -1;
-  RayCtx c;
-  Best best;
-  const WideNode *wide = nullptr;
-  const PackedTri *tris = nullptr;
-  uint2 lstk[LOCAL_DEPTH];
-  int sp = 0, cur = kNoLeaf, leaf = kNoLeaf;
-
-  auto push = [&](int ref, float t) {
-    if (sp < LOCAL_DEPTH) lstk[sp] = make_uint2((uint32_t)ref, __float_as_uint(t));
-    sp++;
-  };
-  auto pop = [&]() -> int {
-    while (sp > 0) {
-      --sp;
-      if (sp >= LOCAL_DEPTH) continue;
-      const uint2 e = lstk[sp];
-      if (__uint_as_float(e.y) <= best.t) return (int)e.x;
-    }
-    return kNoLeaf;
-  };
-
-  for (;;) {
-    // ---- replace retired rays
-    const unsigned dead = __ballot_sync(FULL_MASK, ray_idx < 0);
-    if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= 8)) {
-      const int cnt = __popc(dead);
-      const int leader = __ffs(dead) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(cursor, (unsigned long long)cnt);
-      base = __shfl_sync(FULL_MASK, base, leader);
-      if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
-      if (ray_idx < 0) {
-        const unsigned long long mine = base + (unsigned long long)__popc(dead & lt_mask);
-        if (mine < (unsigned long long)n) {
-          w = load_world(rays, (size_t)mine);
-          setup_ray(wc, w.ox, w.oy, w.oz, w.dx, w.dy, w.dz, w.min_t, cpp03);
-          rix = 1.0f / w.dx;
-          riy = 1.0f / w.dy;
-          riz = 1.0f / w.dz;
-          nearest.t = FLT_MAX;
-          nearest.node = 0xFFFFFFFFu;
-          ray_idx = (long long)mine;
-          tstk[0] = 0;
-          tsp = range_has_nan(w.min_t, w.max_t) ? 0 : 1;
-          leaf_pos = leaf_end = 0;
-          n_boxes = 0;
-          // Scene::Traverse compares world DISTANCES of hits with ray PARAMETERS of box entries (nanosg.h:803, 848):
-          // for a direction that is not unit length its answer depends on the visiting order, which only the list
-          // kernel reproduces.  Such a ray skips the walk and is handed over like a > 64-box ray.
-          const float len2 = (w.dx * w.dx + w.dy * w.dy) + w.dz * w.dz;
-          if (!(fabsf(len2 - 1.0f) <= 1e-5f)) {
-            tsp = 0;
-            n_boxes = (uint32_t)kMaxNodeHits + 1u;
-          }
-          inst = -1;
-          cur = leaf = kNoLeaf;
-        }
-      }
-    }
-    if (__all_sync(FULL_MASK, ray_idx < 0)) {
-      if (exhausted) break;
-      continue;
-    }
-
-    // ---- top-level walk
-    for (;;) {
-      const bool walking = ray_idx >= 0 && inst < 0 && (leaf_pos < leaf_end || tsp > 0);
-      if (!__any_sync(FULL_MASK, walking)) break;
-      if (!walking) continue;
-      if (leaf_pos < leaf_end) {
-        const uint32_t id = __ldg(sc.top_idx + leaf_pos);
-        leaf_pos++;
-        const InstanceDev *I = sc.inst + id;
-        float tmin;
-        if (!raw_box(w, rix, riy, riz, I->bmin, I->bmax, tmin)) continue;
-        n_boxes++;
-        if (nearest.t < tmin) continue;  // early cull (nanosg.h:803-807)
-        const Mat43 minv = load_mat(&I->inv), minv33 = load_mat(&I->inv33);
-        float lox, loy, loz, ldx, ldy, ldz;
-        multv(minv, w.ox, w.oy, w.oz, lox, loy, loz);
-        multv(minv33, w.dx, w.dy, w.dz, ldx, ldy, ldz);
-        setup_ray(c, lox, loy, loz, ldx, ldy, ldz, 0.0f, cpp03);
-        best.t = FLT_MAX;
-        best.u = 0.0f;
-        best.v = 0.0f;
-        best.prim = 0xFFFFFFFFu;
-        wide = I->wide;
-        tris = I->tris;
-        inst = (int)id;
-        sp = 0;
-        cur = 0;
-        leaf = kNoLeaf;
-      } else {
-        const Node40 *nd = sc.top_nodes + tstk[--tsp];
-        const float *f = reinterpret_cast<const float *>(nd);
-        const float lox = __ldg(f + 0), loy = __ldg(f + 1), loz = __ldg(f + 2);
-        const float hix = __ldg(f + 3), hiy = __ldg(f + 4), hiz = __ldg(f + 5);
-        float tn;
-        if (!slab(wc, lox, loy, loz, hix, hiy, hiz, w.min_t, w.max_t, tn)) continue;
-        // entry distance without the min_t clamp: every instance box below starts at or after it, and an instance
-        // whose box starts behind the nearest hit is never visited (same rule as the early cull above)
-        const float enx = ((wc.sx ? hix : lox) - wc.ox) * wc.ix;
-        const float eny = ((wc.sy ? hiy : loy) - wc.oy) * wc.iy;
-        const float enz = ((wc.sz ? hiz : loz) - wc.oz) * wc.iz;
-        if (fmaxf(enx, fmaxf(eny, enz)) > nearest.t) continue;
-        const uint32_t d0 = __ldg(&nd->data[0]), d1 = __ldg(&nd->data[1]);
-        if (__ldg(&nd->flag) == 0) {
-          const int axis = __ldg(&nd->axis);
-          const int sgn = axis == 0 ? wc.sx : (axis == 1 ? wc.sy : wc.sz);
-          if (tsp + 2 <= kTopStack) {
-            tstk[tsp++] = sgn ? d0 : d1;
-            tstk[tsp++] = sgn ? d1 : d0;
-          }
-        } else {
-          leaf_pos = d1;
-          leaf_end = d1 + d0;
-        }
-      }
-    }
-
-    // ---- instance: inner nodes
-    for (;;) {
-      const unsigned desc = __ballot_sync(FULL_MASK, cur >= 0);
-      if (desc == 0u) break;
-      if (__popc(desc) < 8 && __any_sync(FULL_MASK, leaf != kNoLeaf)) break;
-      if (cur >= 0) {
-        const float4 *p = reinterpret_cast<const float4 *>(wide + cur);
-        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(p + 3));
-        float t0, t1;
-        const bool h0 = slab(c, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, 0.0f, best.t, t0);
-        const bool h1 = slab(c, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, 0.0f, best.t, t1);
-        const bool both = h0 & h1;
-        const bool swap = t1 < t0;
-        const int nearr = swap ? q3.y : q3.x;
-        const int farr = swap ? q3.x : q3.y;
-        if (both) push(farr, swap ? t0 : t1);
-        int next = both ? nearr : (h0 ? q3.x : q3.y);
-        if (!(h0 | h1)) next = pop();
-        if (next < 0 && next != kNoLeaf && leaf == kNoLeaf) {
-          leaf = next;
-          next = pop();
-        }
-        cur = next;
-      }
-    }
-
-    // ---- instance: leaves
-    for (;;) {
-      if (!__any_sync(FULL_MASK, leaf != kNoLeaf)) break;
-      if (leaf != kNoLeaf) {
-        const float4 *t = reinterpret_cast<const float4 *>(tris + (size_t)(~leaf));
-        for (;;) {
-          const float4 a = __ldg(t), b = __ldg(t + 1), cc = __ldg(t + 2);
-          tri_test2(c, opt, a, b, cc, best);
-          if (__float_as_uint(b.w) != 0u) break;
-          t += 3;
-        }
-        leaf = kNoLeaf;
-        if (cur < 0 && cur != kNoLeaf) {
-          leaf = cur;
-          cur = pop();
-        }
-      }
-    }
-
-    // ---- instance exit: world distance of the local hit, keep the nearest
-    if (ray_idx >= 0 && inst >= 0 && cur == kNoLeaf && leaf == kNoLeaf) {
-      if (best.t < FLT_MAX) {
-        const InstanceDev *I = sc.inst + inst;
-        const Mat43 minv33 = load_mat(&I->inv33), mxf = load_mat(&I->xf);
-        float ldx, ldy, ldz, px, py, pz;
-        multv(minv33, w.dx, w.dy, w.dz, ldx, ldy, ldz);
-        const float tw = world_hit(mxf, w, c.ox, c.oy, c.oz, ldx, ldy, ldz, best.t, px, py, pz);
-        if (tw < nearest.t) {
-          nearest.t = tw;
-          nearest.u = best.u;
-          nearest.v = best.v;
-          nearest.prim = best.prim;
-          nearest.node = (uint32_t)inst;
-          nearest.px = px;
-          nearest.py = py;
-          nearest.pz = pz;
-        }
-      }
-      inst = -1;
-    }
-
-    // ---- retire
-    if (ray_idx >= 0 && inst < 0 && tsp == 0 && leaf_pos >= leaf_end) {
-      store_scene_hit(hits, mask, (size_t)ray_idx, nearest, nearest.node != 0xFFFFFFFFu, w.max_t);
-      if (n_boxes > (uint32_t)kMaxNodeHits) {  // the reference keeps only the 64 nearest boxes: redo exactly
-        const unsigned long long slot = atomicAdd(overflow_count, 1ull);
-        overflow[slot] = (uint32_t)ray_idx;
-      }
-      ray_idx = -1;
-    }
-  }
-}
 
 // ---- production kernel, unified walk ------------------------------------------------------------------------------
 // The top-level tree is laid out as the same 64-byte child-pair nodes as every instance tree, so that ONE node step
@@ -822,7 +596,9 @@ __global__ void __launch_bounds__(kSceneBlock, MINB)
           sp = 0;
           cur = range_has_nan(w.min_t, w.max_t) ? kNoLeaf : 0;
           leaf = kNoLeaf;
-          // see scene_fast_kernel: a direction that is not unit length goes to the list kernel
+          // Scene::Traverse compares world DISTANCES of hits with ray PARAMETERS of box entries (nanosg.h:803, 848):
+          // for a direction that is not unit length its answer depends on the visiting order, which only the list
+          // kernel reproduces; such a ray is handed over like a > 64-box ray
           const float len2 = (w.dx * w.dx + w.dy * w.dy) + w.dz * w.dz;
           if (!(fabsf(len2 - 1.0f) <= 1e-5f)) {
             cur = kNoLeaf;
@@ -1027,10 +803,9 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
     return NRT_ERR_INVALID;
   }
   const SceneDev dev{sc->top->d_nodes, sc->top->d_indices, sc->d_inst, sc->top->d_wide, sc->top->d_tris};
-  const uint32_t variant = (flags >> 8) & 0xFFu;  // 1 = first-generation phase kernel (A/B runs)
+  const uint32_t variant = (flags >> 8) & 0xFFu;  // policy variants for A/B runs (tools/scene_sweep.py); 0 = default
   const uint32_t stack_need = sc->top->stats.max_tree_depth + sc->max_blas_depth + 6;
-  const bool list_only = (flags & NRT_TRAVERSE_CONFORMANCE) != 0 || stack_need > 1024 ||
-                         (variant == 1 && sc->top->stats.max_tree_depth + 2 > (uint32_t)kTopStack);
+  const bool list_only = (flags & NRT_TRAVERSE_CONFORMANCE) != 0 || stack_need > 1024;
   const int sms = device_sm_count(sc->device);
   if (list_only) {
     const size_t blocks = std::min<size_t>((n + 127) / 128, (size_t)sms * 32);
@@ -1056,13 +831,13 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
   NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
   NRT_CUDA(cudaMemsetAsync(ovf, 0, sizeof(unsigned long long), s));
   const size_t need = ((n + 31) / 32 + 3) / 4;
-  if (variant != 1) {
+  {
     size_t grid = (size_t)sms * (stack_need > 64 ? 2 : kUnifiedMinBlocks);
     if (grid > need) grid = need;
     if (stack_need > 64)
       scene_unified_kernel<1024, 2><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
                                                                         d_overflow, ovf);
-    else if (variant >= 2) {
+    else if (variant != 0) {
 #define NRT_SCENE_VARIANT(id, ...)                                                                              \
   case id: {                                                                                                    \
     size_t g = std::min(need, (size_t)sms * (FirstArg<__VA_ARGS__>::value));                                    \
@@ -1092,19 +867,6 @@ static int scene_launch(Scene *sc, const Ray36 *d_rays, size_t n, SceneHit32 *d_
     NRT_CUDA(cudaGetLastError());
     return NRT_OK;
   }
-  size_t grid = (size_t)sms * 5;
-  if (grid > need) grid = need;
-  if (sc->max_blas_depth + 2 > 48)
-    scene_fast_kernel<512><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
-                                                                  d_overflow, ovf);
-  else
-    scene_fast_kernel<48><<<(unsigned)grid, kSceneBlock, 0, s>>>(dev, d_rays, n, d_hits, d_mask, flags, cursor,
-                                                                 d_overflow, ovf);
-  NRT_CUDA(cudaGetLastError());
-  // rays that pierced more than 64 instance boxes (device-side count, usually zero)
-  scene_list_kernel<<<(unsigned)std::min<size_t>((n + 127) / 128, (size_t)sms * 4), 128, 0, s>>>(
-      dev, d_rays, n, d_overflow, ovf, d_hits, d_mask, flags);
-  NRT_CUDA(cudaGetLastError());
   return NRT_OK;
 }
 

@@ -39,8 +39,6 @@ def timed(fn, reps=10):
 ms = timed(lambda: sc.TraverseDevice(d_rays.data_ptr(), n, d_hits.data_ptr(), d_mask.data_ptr(), stream=st))
 print(f"two-level fast (unified walk): {ms:.3f} ms  {n/ms/1e3:.1f} Mrays/s  hit rate {d_mask.float().mean().item():.3f}")
 m_u = d_mask.cpu().numpy().copy(); h_u = d_hits.cpu().numpy().copy()
-ms1 = timed(lambda: sc.TraverseDevice(d_rays.data_ptr(), n, d_hits.data_ptr(), d_mask.data_ptr(), flags=(1 << 8), stream=st))
-print(f"two-level fast (phase kernel, variant 1): {ms1:.3f} ms  {n/ms1/1e3:.1f} Mrays/s; identical output: {np.array_equal(m_u, d_mask.cpu().numpy()) and h_u.tobytes() == d_hits.cpu().numpy().tobytes()}")
 sc.TraverseDevice(d_rays.data_ptr(), n, d_hits.data_ptr(), d_mask.data_ptr(), stream=st)
 torch.cuda.synchronize()
 ms_c = timed(lambda: sc.TraverseDevice(d_rays.data_ptr(), n, d_hits.data_ptr(), d_mask.data_ptr(), flags=api.TRAVERSE_CONFORMANCE, stream=st), reps=3)

@@ -19,7 +19,7 @@ lo, hi = sc.GetBoundingBox()
 inc = S.incoherent_rays(lo, hi + np.float32([0, 3, 0]), 4 << 20, seed=4, axis_parallel_fraction=0.0)
 inc["min_t"] = 0.0
 st = torch.cuda.current_stream().cuda_stream
-names = {0: "default <7,16,8>", 1: "phase kernel", 2: "<6,16,8>", 3: "<8,16,8>", 4: "<5,16,8>", 5: "<7,8,8>",
+names = {0: "default <8,16,8>", 2: "<6,16,8>", 3: "<8,16,8>", 4: "<5,16,8>", 5: "<7,8,8>",
          6: "<7,24,8>", 7: "<7,16,4>", 8: "<7,16,12>", 9: "<7,16,16>"}
 for label, rays in (("primary 4K", prim), ("incoherent 4Mi", inc)):
     d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 36)).cuda()
