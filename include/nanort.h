@@ -511,7 +511,7 @@ class BVHAccel<float> {
 };
 
 // ---- BVHAccel<double> ----------------------------------------------------------------------------
-// The fp64 instantiation (nrt_build_f64 / nrt_traverse_f64): same members as above minus Dump / Load.  The tree's
+// The fp64 instantiation (nrt_build_f64 / nrt_adopt_f64 / nrt_traverse_f64): same members as above.  The tree's
 // topology comes from the production builder, every node box is exact in double, Traverse computes in double in the
 // reference's visiting order -- t / u / v carry the reference's bits for the reported primitive.
 static_assert(sizeof(Ray<double>) == 72, "nanort::Ray<double> layout");
@@ -548,13 +548,39 @@ class BVHAccel<double> {
   }
 
   BVHBuildStatistics GetStatistics() const { return stats_; }
-  bool IsValid() const { return handle_ != NULL; }
+  bool IsValid() const { return handle_ != NULL || !nodes_.empty(); }
+
+  /// Raw dump / load in the reference's format (nanort.h:2164-2276); a loaded tree reaches the device at the first
+  /// Traverse, which brings the geometry pointers.
+  bool Dump(FILE *fp) const {
+    Mirror();
+    size_t n = nodes_.size(), m = indices_.size();
+    if (fwrite(&n, sizeof(size_t), 1, fp) != 1) return false;
+    if (n && fwrite(nodes_.data(), sizeof(BVHNode<double>), n, fp) != n) return false;
+    if (fwrite(&m, sizeof(size_t), 1, fp) != 1) return false;
+    if (m && fwrite(indices_.data(), sizeof(unsigned int), m, fp) != m) return false;
+    return true;
+  }
+  bool Load(FILE *fp) {
+    handle_.reset();
+    nodes_.clear();
+    indices_.clear();
+    mirrors_ = false;
+    size_t n = 0, m = 0;
+    if (fread(&n, sizeof(size_t), 1, fp) != 1 || n == 0) return false;
+    nodes_.resize(n);
+    if (fread(nodes_.data(), sizeof(BVHNode<double>), n, fp) != n) return false;
+    if (fread(&m, sizeof(size_t), 1, fp) != 1) return false;
+    indices_.resize(m);
+    if (m && fread(indices_.data(), sizeof(unsigned int), m, fp) != m) return false;
+    mirrors_ = true;
+    return true;
+  }
 
   template <class I, class H>
   bool Traverse(const Ray<double> &ray, const I &intersector, H *isect,
                 const BVHTraceOptions &options = BVHTraceOptions()) const {
-    (void)intersector;
-    if (!handle_) return false;
+    if (!Ready(intersector)) return false;
     TriangleIntersection<double> rec;
     unsigned char hit = 0;
     if (nrt_traverse_f64(handle_.get(), &ray, 1, &rec, &hit, &options, NANORT_B200_INVERSE_FLAG) != NRT_OK) {
@@ -574,8 +600,7 @@ class BVHAccel<double> {
   template <class I>
   size_t TraverseBatch(const Ray<double> *rays, size_t n, const I &intersector, TriangleIntersection<double> *hits,
                        unsigned char *hit_mask, const BVHTraceOptions &options = BVHTraceOptions()) const {
-    (void)intersector;
-    if (!handle_) return static_cast<size_t>(-1);
+    if (!Ready(intersector)) return static_cast<size_t>(-1);
     std::vector<unsigned char> tmp;
     if (!hit_mask) {
       tmp.resize(n);
@@ -600,15 +625,35 @@ class BVHAccel<double> {
   }
 
   void BoundingBox(double bmin[3], double bmax[3]) const {
-    if (!handle_) {
+    if (handle_) {
+      nrt_bounding_box_f64(handle_.get(), bmin, bmax);
+    } else if (!nodes_.empty()) {
+      for (int k = 0; k < 3; k++) {
+        bmin[k] = nodes_[0].bmin[k];
+        bmax[k] = nodes_[0].bmax[k];
+      }
+    } else {
       bmin[0] = bmin[1] = bmin[2] = std::numeric_limits<double>::max();
       bmax[0] = bmax[1] = bmax[2] = -std::numeric_limits<double>::max();
-      return;
     }
-    nrt_bounding_box_f64(handle_.get(), bmin, bmax);
   }
 
  private:
+  template <class I>
+  bool Ready(const I &isec) const {
+    if (handle_) return true;
+    if (nodes_.empty()) return false;
+    nrt_accel_f64 *h = NULL;  // a Load()ed tree: adopt it now that the intersector supplies the geometry
+    if (nrt_adopt_f64(nodes_.data(), nodes_.size(), indices_.data(), indices_.size(), isec.GetVertices(),
+                      isec.GetVertexStrideBytes(), 0, isec.GetFaces(), static_cast<uint32_t>(indices_.size()), &h) !=
+        NRT_OK) {
+      fprintf(stderr, "nanort_b200: adopting the loaded fp64 tree failed: %s\n", nrt_last_error());
+      return false;
+    }
+    handle_ = std::shared_ptr<nrt_accel_f64>(h, nrt_free_f64);
+    nrt_stats_f64(h, &stats_);
+    return true;
+  }
   void Mirror() const {
     if (mirrors_ || !handle_) return;
     const void *pn = NULL;

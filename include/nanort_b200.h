@@ -282,6 +282,11 @@ int nrt_scene_traverse_device(const nrt_scene *s, const void *d_rays_36B, size_t
 typedef struct nrt_accel_f64 nrt_accel_f64;
 int nrt_build_f64(const double *verts, size_t stride_bytes, size_t n_verts_or_0, const uint32_t *faces,
                   uint32_t n_prims, const void *build_opts_32B, nrt_accel_f64 **out);
+/* BVHAccel<double>::Load (nanort.h:2252-2275) + the geometry the first Traverse brings: an existing BVHNode<double>
+ * array, e.g. one dumped by CPU nanort, validated and walked in the reference's order */
+int nrt_adopt_f64(const void *nodes_64B, size_t n_nodes, const uint32_t *indices, size_t n_indices, const double *verts,
+                  size_t stride_bytes, size_t n_verts_or_0, const uint32_t *faces, uint32_t n_prims,
+                  nrt_accel_f64 **out);
 void nrt_free_f64(nrt_accel_f64 *a);
 int nrt_stats_f64(const nrt_accel_f64 *a, void *stats_16B);
 int nrt_bounding_box_f64(const nrt_accel_f64 *a, double bmin[3], double bmax[3]);

@@ -53,7 +53,7 @@ EXPORTS = [
     "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device", "nrt_render_path_device",
     "nrt_scene_commit", "nrt_scene_free", "nrt_scene_bounding_box", "nrt_scene_nodes", "nrt_scene_instance_state",
     "nrt_scene_traverse", "nrt_scene_traverse_device",
-    "nrt_build_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
+    "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
 ]
 
 
@@ -150,6 +150,7 @@ def lib():
     L.nrt_scene_traverse.argtypes = [vp, vp, sz, vp, vp, u32]
     L.nrt_scene_traverse_device.argtypes = [vp, vp, sz, vp, vp, u32, vp]
     L.nrt_build_f64.argtypes = [vp, sz, sz, vp, u32, vp, C.POINTER(vp)]
+    L.nrt_adopt_f64.argtypes = [vp, sz, vp, sz, vp, sz, sz, vp, u32, C.POINTER(vp)]
     L.nrt_free_f64.argtypes = [vp]
     L.nrt_free_f64.restype = None
     L.nrt_stats_f64.argtypes = [vp, vp]
@@ -482,6 +483,22 @@ class BVHAccelF64:
         n_verts = vertices.size * 8 // vertex_stride_bytes
         _check(lib().nrt_build_f64(_p(vertices), vertex_stride_bytes, n_verts, _p(faces), int(num_primitives),
                                    _p(options), C.byref(h)))
+        self._h = h
+        return True
+
+    def Adopt(self, nodes, indices, vertices, faces):
+        """Traverse an existing BVHNode<double> array (e.g. the CPU reference's), nrt_adopt_f64."""
+        self.free()
+        nodes = np.ascontiguousarray(nodes)
+        assert nodes.dtype.itemsize == 64
+        indices = np.ascontiguousarray(indices, np.uint32)
+        vertices = np.ascontiguousarray(vertices, np.float64)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        if self._device is not None:
+            _check(lib().nrt_set_device(int(self._device)))
+        h = C.c_void_p()
+        _check(lib().nrt_adopt_f64(_p(nodes), len(nodes), _p(indices), len(indices), _p(vertices), 24,
+                                   vertices.size // 3, _p(faces), faces.size // 3, C.byref(h)))
         self._h = h
         return True
 

@@ -444,6 +444,100 @@ fail:
   return rc;
 }
 
+int nrt_adopt_f64(const void *nodes_64B, size_t n_nodes, const uint32_t *indices, size_t n_indices, const double *verts,
+                  size_t stride_bytes, size_t n_verts, const uint32_t *faces, uint32_t n_prims, nrt_accel_f64 **out) {
+  if (!out) {
+    set_error("nrt_adopt_f64: out is NULL");
+    return NRT_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (!nodes_64B || !indices || !verts || !faces || n_nodes == 0 || n_prims == 0 || n_indices != n_prims ||
+      stride_bytes < 24) {
+    set_error("nrt_adopt_f64: bad arguments");
+    return NRT_ERR_INVALID;
+  }
+  const Node64 *hn = static_cast<const Node64 *>(nodes_64B);
+  BuildStats16 st = {0, 0, 0, 0.0f};
+  {  // an adopted tree is foreign data: validate child / leaf ranges once on the host, take the statistics
+    std::vector<uint32_t> depth(n_nodes, 0), stack(1, 0u);
+    while (!stack.empty()) {
+      const uint32_t i = stack.back();
+      stack.pop_back();
+      const Node64 &nd = hn[i];
+      st.max_tree_depth = std::max(st.max_tree_depth, depth[i]);
+      if (nd.flag == 0) {
+        st.num_branch_nodes++;
+        if (nd.data[0] >= n_nodes || nd.data[1] >= n_nodes || nd.data[0] <= i || nd.data[1] <= i || nd.axis < 0 ||
+            nd.axis > 2) {
+          set_error("nrt_adopt_f64: branch node with invalid children / axis");
+          return NRT_ERR_INVALID;
+        }
+        depth[nd.data[0]] = depth[nd.data[1]] = depth[i] + 1;
+        stack.push_back(nd.data[0]);
+        stack.push_back(nd.data[1]);
+      } else {
+        st.num_leaf_nodes++;
+        if ((size_t)nd.data[1] + nd.data[0] > n_indices) {
+          set_error("nrt_adopt_f64: leaf range outside indices");
+          return NRT_ERR_INVALID;
+        }
+      }
+    }
+  }
+  if (st.max_tree_depth > 500) {
+    set_error("nrt_adopt_f64: tree deeper than 500 levels (512-entry traversal stack, as the reference's)");
+    return NRT_ERR_INVALID;
+  }
+  for (size_t i = 0; i < n_indices; i++)
+    if (indices[i] >= n_prims) {
+      set_error("nrt_adopt_f64: index outside primitives");
+      return NRT_ERR_INVALID;
+    }
+  int device = 0;
+  int rc = select_device(&device);
+  if (rc != NRT_OK) return rc;
+  if (n_verts == 0) {
+    uint32_t m = 0;
+    for (size_t k = 0; k < (size_t)n_prims * 3; k++) m = std::max(m, faces[k]);
+    n_verts = (size_t)m + 1;
+  }
+  AccelF64 *a = new (std::nothrow) AccelF64();
+  if (!a) return NRT_ERR_NOMEM;
+  a->device = device;
+  a->n_prims = n_prims;
+  a->n_verts = n_verts;
+  a->n_nodes = n_nodes;
+  a->stats = st;
+  std::vector<double> packed(3 * n_verts);
+  for (size_t i = 0; i < n_verts; i++) {
+    const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(verts) + i * stride_bytes);
+    packed[3 * i] = p[0], packed[3 * i + 1] = p[1], packed[3 * i + 2] = p[2];
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_verts, sizeof(double) * 3 * n_verts);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_faces, sizeof(uint32_t) * 3 * (size_t)n_prims);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_nodes, sizeof(Node64) * n_nodes);
+  if (e == cudaSuccess) e = cudaMalloc(&a->d_indices, sizeof(uint32_t) * n_indices);
+  if (e == cudaSuccess) e = cudaMemcpy(a->d_verts, packed.data(), sizeof(double) * 3 * n_verts, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(a->d_nodes, hn, sizeof(Node64) * n_nodes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(a->d_indices, indices, sizeof(uint32_t) * n_indices, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    rc = cuda_fail(e, "nrt_adopt_f64 upload", __FILE__, __LINE__);
+    destroy_f64(a);
+    return rc;
+  }
+  for (int k = 0; k < 3; k++) {
+    a->root_bmin[k] = hn[0].bmin[k];
+    a->root_bmax[k] = hn[0].bmax[k];
+  }
+  a->h_nodes.assign(hn, hn + n_nodes);
+  a->h_indices.assign(indices, indices + n_indices);
+  a->mirrors_valid = true;
+  *out = reinterpret_cast<nrt_accel_f64 *>(a);
+  return NRT_OK;
+}
+
 void nrt_free_f64(nrt_accel_f64 *a) { destroy_f64(reinterpret_cast<AccelF64 *>(a)); }
 
 int nrt_stats_f64(const nrt_accel_f64 *h, void *stats_16B) {

@@ -122,3 +122,33 @@ def test_f64_hits_match_the_reference(cpp11):
     ah2, am2 = adopted.traverse(rays[:8000], topts=o, threads=4)
     assert np.array_equal(am2, gm2) and ah2[am2 == 1].tobytes() == gh2[gm2 == 1].tobytes()
     assert gm2.sum() < gm[:8000].sum()
+
+
+@pytest.mark.parametrize("cpp11", [True, False])
+def test_f64_adopted_reference_tree_is_bit_exact(cpp11):
+    """BVHAccel<double>::Load path (nrt_adopt_f64): the CPU reference's own double tree walked on the GPU gives the
+    reference's records bit for bit -- hit flag, prim_id (ties included), t, u, v."""
+    from nanort_b200 import api
+    from oracle import orc
+
+    if not orc.Reference.available(cpp11):
+        pytest.skip("oracle/_ref not built")
+    ref = orc.ReferenceF64(cpp11)
+    v64, f = _scene64(seed=9)
+    rays = _rays64(v64, 40000, seed=10)
+    racc = ref.build(v64, f)
+    rh, rm = racc.traverse(rays, threads=8)
+    acc = api.BVHAccelF64()
+    assert acc.Adopt(racc.nodes(), racc.indices(), v64, f)
+    gh, gm = acc.Traverse(rays, flags=0 if cpp11 else api.TRAVERSE_CPP03_INVERSE)
+    assert rm.sum() > 3000 and np.array_equal(rm, gm)
+    hit = rm == 1
+    for k in ("t", "u", "v", "prim_id"):
+        assert rh[k][hit].tobytes() == gh[k][hit].tobytes(), k
+    a, b = acc.BoundingBox()
+    ra, rb = racc.bounding_box()
+    assert np.array_equal(a, ra) and np.array_equal(b, rb)
+    with pytest.raises(api.NanortB200Error):  # foreign data is validated
+        bad = racc.nodes().copy()
+        bad["data"][np.nonzero(bad["flag"] == 0)[0][0], 0] = len(bad) + 3
+        api.BVHAccelF64().Adopt(bad, racc.indices(), v64, f)
