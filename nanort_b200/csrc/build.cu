@@ -445,11 +445,11 @@ __global__ void __launch_bounds__(kSubWarps * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sub = blockIdx.x * kSubWarps + warp;
   if (sub >= n_subtrees) return;
-  const size_t per_warp = sizeof(WarpSub) + (size_t)3 * B * kBinWords * 4 + (size_t)2 * B * 4;
+  const size_t per_warp = sizeof(WarpSub) + (size_t)B * kBinWords * 4 + (size_t)2 * B * 4;
   unsigned char *mine = smem_raw + (size_t)warp * per_warp;
   WarpSub &S = *reinterpret_cast<WarpSub *>(mine);
-  uint32_t *sbin = reinterpret_cast<uint32_t *>(mine + sizeof(WarpSub));      // 3*B*kBinWords
-  float *sweep = reinterpret_cast<float *>(sbin + (size_t)3 * B * kBinWords);  // 2*B floats
+  uint32_t *sbin = reinterpret_cast<uint32_t *>(mine + sizeof(WarpSub));  // B*kBinWords: one axis at a time
+  float *sweep = reinterpret_cast<float *>(sbin + (size_t)B * kBinWords);  // 2*B floats
   const uint32_t root = subtrees[sub];
   const BNode rootn = pool[root];
   const uint32_t base = rootn.l, total = rootn.r - rootn.l;
@@ -473,28 +473,29 @@ __global__ void __launch_bounds__(kSubWarps * 32)
     const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
                          inv_extent(nd.bmin[2], nd.bmax[2], B)};
     // ---- bins (nodes with more than 32 primitives)
-    for (int i = lane; !small && i < 3 * B * kBinWords; i += 32) {
-      const int w = i & (kBinWords - 1);
-      sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
-    }
-    __syncwarp();
-    for (uint32_t i = lane; !small && i < n; i += 32) {
-      const uint32_t q = S.ids[lo + i];
-      const float4 l4 = S.plo[q], h4 = S.phi[q];
-      const float c3[3] = {l4.w, h4.w, S.pcz[q]};
-      const uint32_t kl[3] = {fkey(l4.x), fkey(l4.y), fkey(l4.z)}, kh[3] = {fkey(h4.x), fkey(h4.y), fkey(h4.z)};
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        uint32_t *w = sbin + ((size_t)a * B + bin_of(c3[a], nd.bmin[a], iv[a], B)) * kBinWords;
-        atomicAdd(w, 1u);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          atomicMin(w + 1 + k, kl[k]);
-          atomicMax(w + 4 + k, kh[k]);
-        }
+    // nodes with more than 32 primitives (3 of the 31 splits of a full subtree) bin ONE axis at a time into a single
+    // B-bin array -- a third of the shared memory, i.e. half again as many resident warps for the whole kernel
+    auto bin_axis = [&](int a) {
+      for (int i = lane; i < B * kBinWords; i += 32) {
+        const int w = i & (kBinWords - 1);
+        sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
       }
-    }
-    __syncwarp();
+      __syncwarp();
+      for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t q = S.ids[lo + i];
+        const float4 l4 = S.plo[q], h4 = S.phi[q];
+        const float c = a == 0 ? l4.w : (a == 1 ? h4.w : S.pcz[q]);
+        uint32_t *w = sbin + (size_t)bin_of(c, nd.bmin[a], iv[a], B) * kBinWords;
+        atomicAdd(w, 1u);
+        atomicMin(w + 1, fkey(l4.x));
+        atomicMin(w + 2, fkey(l4.y));
+        atomicMin(w + 3, fkey(l4.z));
+        atomicMax(w + 4, fkey(h4.x));
+        atomicMax(w + 5, fkey(h4.y));
+        atomicMax(w + 6, fkey(h4.z));
+      }
+      __syncwarp();
+    };
     // ---- sweep the three axes, pick the split
     float cost[3];
     int cut[3];
@@ -581,15 +582,19 @@ __global__ void __launch_bounds__(kSubWarps * 32)
         }
       }
     } else {
-      for (int a = 0; a < 3; a++) sweep_axis(sbin + (size_t)a * B * kBinWords, B, sweep, sweep + B, cost[a], cut[a]);
+      for (int a = 0; a < 3; a++) {
+        bin_axis(a);
+        sweep_axis(sbin, B, sweep, sweep + B, cost[a], cut[a]);
+      }
       if (cost[0] > cost[1]) ax = 1;
       if (cost[ax] > cost[2]) ax = 2;
+      if (ax != 2 && cost[ax] < FLT_MAX) bin_axis(ax);  // the child boxes come from the chosen axis' bins
     }
     const bool median = !(cost[ax] < FLT_MAX);
     if (!median) {
       if (!small) {
-        range_union(sbin + (size_t)ax * B * kBinWords, 0, cut[ax], lb, nl);
-        range_union(sbin + (size_t)ax * B * kBinWords, cut[ax], B, rb, nr);
+        range_union(sbin, 0, cut[ax], lb, nl);
+        range_union(sbin, cut[ax], B, rb, nr);
       }
     } else {
       nl = n >> 1;
@@ -792,7 +797,7 @@ int build_on_device(Accel *a, cudaStream_t s) {
   int cur = 0, which = 0;
   uint32_t n_active = 0;
   uint32_t n_nodes = 0;
-  const size_t sub_smem = kSubWarps * (sizeof(WarpSub) + (size_t)3 * B * kBinWords * 4 + (size_t)2 * B * 4);
+  const size_t sub_smem = kSubWarps * (sizeof(WarpSub) + (size_t)B * kBinWords * 4 + (size_t)2 * B * 4);
 
   BUILD_CUDA(cudaEventCreate(&ev0));
   BUILD_CUDA(cudaEventCreate(&ev1));
