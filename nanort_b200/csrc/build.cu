@@ -822,6 +822,7 @@ int build_on_device(Accel *a, cudaStream_t s) {
   BUILD_CUDA(cudaMalloc(&d_scene, sizeof(uint32_t) * 8));
   BUILD_CUDA(cudaMalloc(&d_pool, sizeof(BNode) * 2 * (size_t)n));
   BUILD_CUDA(cudaMalloc(&d_ctr, sizeof(BuildCounters)));
+  BUILD_CUDA(cudaMemsetAsync(d_ctr, 0, sizeof(BuildCounters), s));  // incl. the padding the host reads back
   {
     const uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
     BUILD_CUDA(cudaMemcpyAsync(d_scene, init, sizeof(init), cudaMemcpyHostToDevice, s));

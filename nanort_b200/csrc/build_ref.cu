@@ -539,6 +539,7 @@ int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s) {
   RB_CUDA(cudaMalloc(&d_small, sizeof(uint32_t) * 8));
   RB_CUDA(cudaMalloc(&d_pool, sizeof(BNode) * max_nodes));
   RB_CUDA(cudaMalloc(&d_ctr, sizeof(RefCounters)));
+  RB_CUDA(cudaMemsetAsync(d_ctr, 0, sizeof(RefCounters), s));  // incl. the padding the host reads back
   RB_CUDA(cudaMalloc(&a->d_nodes, sizeof(Node40) * max_nodes));
   RB_CUDA(cudaMalloc(&a->d_indices, sizeof(uint32_t) * (size_t)n));
 

@@ -1,0 +1,46 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck):
+production + conformance build, both traversal kernels, the AO and path passes, a two-level scene, the fp64 accel."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from nanort_b200 import api, scenes as S
+
+v, f = S.make_scene("sphere_grid", nx=2, nz=2)
+acc = api.BVHAccel(); acc.Build(len(f), v, f)
+ref = api.BVHAccel(); ref.Build(len(f), v, f, flags=api.BUILD_REFERENCE_TREE)
+cam = S.scene_camera("sphere_grid", 96, 64)
+rays = np.concatenate([S.primary_rays(cam, 96, 64, spp=1, seed=7), S.incoherent_rays(v.min(axis=0), v.max(axis=0), 4096, seed=8)])
+for a in (acc, ref):
+    for fl in (api.TRAVERSE_FAST, api.TRAVERSE_CONFORMANCE):
+        h, m = a.Traverse(rays, flags=fl)
+print("traverse ok", int(m.sum()))
+p = api.AoParams()
+for i in range(12): p.cam[i] = float(cam[i])
+p.width, p.height, p.spp, p.sample0, p.seed = 96, 64, 2, 0, 1
+p.tile_w, p.tile_h, p.shard, p.n_shards = 64, 8, 0, 1
+p.ray_min_t, p.ray_max_t, p.ao_min_t, p.ao_max_t = 1e-3, 1e30, 1e-3, 2.0
+accum = torch.zeros(96 * 64, dtype=torch.float32, device="cuda")
+r = acc.RenderAO(p, accum.data_ptr())
+print("ao ok", r.primary_rays, r.ao_rays)
+insts = S.instances_mixed(7)
+accels, sc = {}, api.Scene()
+for iv, jf, x in insts:
+    key = (iv.ctypes.data, jf.ctypes.data)
+    if key not in accels:
+        accels[key] = api.BVHAccel(); accels[key].Build(len(jf), iv, jf)
+    sc.AddNode(accels[key], x)
+sc.Commit()
+srays = S.incoherent_rays(np.float32([-8, -4, -8]), np.float32([8, 4, 8]), 4096, seed=3)
+srays["min_t"] = 0.0
+for fl in (api.TRAVERSE_FAST, api.TRAVERSE_CONFORMANCE):
+    sh, sm = sc.Traverse(srays, flags=fl)
+print("scene ok", int(sm.sum()))
+a64 = api.BVHAccelF64(); a64.Build(len(f), v.astype(np.float64), f)
+r64 = np.zeros(2048, api.RAY64_DTYPE)
+r64["org"], r64["dir"], r64["min_t"], r64["max_t"] = rays["org"][:2048], rays["dir"][:2048], 0.0, 1e30
+h64, m64 = a64.Traverse(r64)
+print("f64 ok", int(m64.sum()))
+big_v, big_f = S.make_scene("terrain", n=96)
+big = api.BVHAccel(); big.Build(len(big_f), big_v, big_f)
+print("terrain build ok", big.GetStatistics()["num_leaf_nodes"])
