@@ -69,5 +69,5 @@ def build_config():
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("all", "path"): path_config()
+    if which in ("all", "path"): path_config(int(sys.argv[2]) if len(sys.argv) > 2 else 8)
     if which in ("all", "build"): build_config()
