@@ -27,6 +27,8 @@
 // (leaves to the left, depth, right turns) and the 40-byte nodes are emitted in one pass.
 #include <float.h>
 
+#include <utility>
+
 #include "build_common.cuh"
 #include "common.cuh"
 #include "radix_sort.cuh"
@@ -855,15 +857,25 @@ int build_on_device(Accel *a, cudaStream_t s) {
     float3 smin = make_float3(lo[0], lo[1], lo[2]);
     float3 sinv = make_float3(hi[0] > lo[0] ? 1024.0f / (hi[0] - lo[0]) : 0.0f, hi[1] > lo[1] ? 1024.0f / (hi[1] - lo[1]) : 0.0f,
                               hi[2] > lo[2] ? 1024.0f / (hi[2] - lo[2]) : 0.0f);
-    uint32_t *keys = d_flags, *keys_tmp = d_scan, *vals = d_order, *vals_tmp = d_nodeof[1];
-    morton_kernel<<<grid_n, 256, 0, s>>>(d_plo_u, d_phi_u, d_pcz_u, n, smin, sinv, keys, vals);
-    BUILD_CUDA(cudaGetLastError());
-    BUILD_CHECK(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 32, d_table, d_scratch, s));
-    if (vals != d_order) {  // odd number of passes: keep the result in d_order
-      BUILD_CUDA(cudaMemcpyAsync(d_order, vals, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    if (n > (uint32_t)kSubtree) {
+      uint32_t *keys = d_flags, *keys_tmp = d_scan, *vals = d_order, *vals_tmp = d_nodeof[1];
+      morton_kernel<<<grid_n, 256, 0, s>>>(d_plo_u, d_phi_u, d_pcz_u, n, smin, sinv, keys, vals);
+      BUILD_CUDA(cudaGetLastError());
+      BUILD_CHECK(radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, 32, d_table, d_scratch, s));
+      if (vals != d_order) {  // odd number of passes: keep the result in d_order
+        BUILD_CUDA(cudaMemcpyAsync(d_order, vals, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+      }
+      gather_prims_kernel<<<grid_n, 256, 0, s>>>(d_order, d_plo_u, d_phi_u, d_pcz_u, n, d_plo, d_phi, d_pcz);
+      BUILD_CUDA(cudaGetLastError());
+    } else {
+      // the whole scene is one phase-B subtree (a Cornell box, the top level of a small two-level scene): the order
+      // of the records does not matter there, so the 18 launches of the sort are skipped
+      iota_kernel<<<grid_n, 256, 0, s>>>(d_order, d_flags, n);
+      BUILD_CUDA(cudaGetLastError());
+      std::swap(d_plo, d_plo_u);
+      std::swap(d_phi, d_phi_u);
+      std::swap(d_pcz, d_pcz_u);
     }
-    gather_prims_kernel<<<grid_n, 256, 0, s>>>(d_order, d_plo_u, d_phi_u, d_pcz_u, n, d_plo, d_phi, d_pcz);
-    BUILD_CUDA(cudaGetLastError());
   }
   iota_kernel<<<grid_n, 256, 0, s>>>(d_idx[0], d_nodeof[0], n);
   init_build_kernel<<<1, 1, 0, s>>>(d_pool, d_ctr, d_scene, n, min_leaf, opt.max_tree_depth,
