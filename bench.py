@@ -269,6 +269,8 @@ def main():
         ref = CpuReference(verts, faces)
         # every step traces the same bounded sample; the whole run (W + K steps) is kept to about 2.5 minutes
         per_step = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+        if os.environ.get("NRT_BENCH_REF_STEP_S"):  # tests shrink the sample (tests/test_bench_contract.py)
+            per_step = float(os.environ["NRT_BENCH_REF_STEP_S"])
         ref.calibrate_standalone(S, verts, faces, cam, 0.25 * diag, target_s=per_step)
         for _ in range(args.warmup):
             ref.step()
