@@ -12,6 +12,9 @@
  * operation individually rounded: compile with -ffp-contract=off and without
  * -ffast-math (oracle/Makefile does).
  *
+ * The same source compiled with -DORC_DOUBLE (oracle/liborc64.so) is the restatement of BVHAccel<double>; it is
+ * pinned the same way against the reference's double instantiation (tests/test_oracle_f64.py).
+ *
  * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this port
  * bit-for-bit (nodes, indices, statistics, hit flag, prim_id and the raw bits
  * of t/u/v) against the unmodified reference compiled into
@@ -45,30 +48,51 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* ---- precision: the same restatement serves BVHAccel<float> (liborc.so) and, compiled with -DORC_DOUBLE,
+ * BVHAccel<double> (liborc64.so).  The reference is a template over T; the only T-specific pieces are the far-plane
+ * widening constant of IntersectRayAABB (nanort.h:2284-2325 float, 2327-2370 double) and numeric_limits<T>. */
+#ifdef ORC_DOUBLE
+typedef double real;
+#define RC(x) x
+#define R_MAX DBL_MAX
+#define R_EPS DBL_EPSILON
+#define R_FABS fabs
+#define R_COPYSIGN copysign
+#define R_MAXMULT 1.0000000000000004
+#else
+typedef float real;
+#define RC(x) x##f
+#define R_MAX FLT_MAX
+#define R_EPS FLT_EPSILON
+#define R_FABS fabsf
+#define R_COPYSIGN copysignf
+#define R_MAXMULT 1.00000024f
+#endif
+
 /* ---- value types, byte-compatible with the reference ---- */
 typedef struct {
-  float bmin[3];
-  float bmax[3];
+  real bmin[3];
+  real bmax[3];
   int32_t flag; /* 1 leaf, 0 branch */
   int32_t axis;
   uint32_t data[2]; /* leaf {count, first}; branch {left, right} */
 } orc_node; /* 40 B */
 
 typedef struct {
-  float org[3];
-  float dir[3];
-  float min_t;
-  float max_t;
+  real org[3];
+  real dir[3];
+  real min_t;
+  real max_t;
   uint32_t type;
 } orc_ray; /* 36 B */
 
 typedef struct {
-  float u, v, t;
+  real u, v, t;
   uint32_t prim_id;
 } orc_hit; /* 16 B */
 
 typedef struct {
-  float cost_t_aabb;
+  real cost_t_aabb;
   uint32_t min_leaf_primitives;
   uint32_t max_tree_depth;
   uint32_t bin_size;
@@ -97,7 +121,7 @@ typedef struct {
 
 void orc_default_build_options(orc_build_options *o) {
   memset(o, 0, sizeof(*o));
-  o->cost_t_aabb = 0.2f;
+  o->cost_t_aabb = RC(0.2);
   o->min_leaf_primitives = 4;
   o->max_tree_depth = 256;
   o->bin_size = 64;
@@ -123,8 +147,8 @@ void orc_sizes(uint32_t out[5]) {
 }
 
 /* std::min / std::max argument-order semantics (matters for -0.0 and NaN) */
-static inline float stdmin(float a, float b) { return (b < a) ? b : a; }
-static inline float stdmax(float a, float b) { return (a < b) ? b : a; }
+static inline real stdmin(real a, real b) { return (b < a) ? b : a; }
+static inline real stdmax(real a, real b) { return (a < b) ? b : a; }
 
 /* ------------------------------------------------------------------ geometry */
 typedef struct {
@@ -133,14 +157,14 @@ typedef struct {
   const uint32_t *faces;
   /* box primitives (the two-level scene's top-level build): boxes[6*i] = bmin.xyz bmax.xyz; when set, the
    * accessors below follow NodeBBoxGeometry / NodeBBoxPred (examples/nanosg/nanosg.h:511-573) instead */
-  const float *boxes;
+  const real *boxes;
 } orc_mesh;
 
-static inline const float *vtx(const orc_mesh *m, uint32_t i) {
-  return (const float *)(m->verts + (size_t)i * m->stride);
+static inline const real *vtx(const orc_mesh *m, uint32_t i) {
+  return (const real *)(m->verts + (size_t)i * m->stride);
 }
 
-static void orc_prim_bbox(const orc_mesh *m, uint32_t prim, float bmin[3], float bmax[3]) {
+static void orc_prim_bbox(const orc_mesh *m, uint32_t prim, real bmin[3], real bmax[3]) {
   if (m->boxes) {
     for (int k = 0; k < 3; k++) {
       bmin[k] = m->boxes[6 * (size_t)prim + k];
@@ -148,7 +172,7 @@ static void orc_prim_bbox(const orc_mesh *m, uint32_t prim, float bmin[3], float
     }
     return;
   }
-  const float *p = vtx(m, m->faces[3 * (size_t)prim]);
+  const real *p = vtx(m, m->faces[3 * (size_t)prim]);
   for (int k = 0; k < 3; k++) bmin[k] = bmax[k] = p[k];
   for (int c = 1; c < 3; c++) {
     p = vtx(m, m->faces[3 * (size_t)prim + c]);
@@ -159,17 +183,17 @@ static void orc_prim_bbox(const orc_mesh *m, uint32_t prim, float bmin[3], float
   }
 }
 
-static void orc_prim_bbox_center(const orc_mesh *m, uint32_t prim, float bmin[3], float bmax[3],
-                                 float ctr[3]) {
+static void orc_prim_bbox_center(const orc_mesh *m, uint32_t prim, real bmin[3], real bmax[3],
+                                 real ctr[3]) {
   if (m->boxes) {
     orc_prim_bbox(m, prim, bmin, bmax);
-    for (int k = 0; k < 3; k++) ctr[k] = (bmax[k] + bmin[k]) / 2.0f;
+    for (int k = 0; k < 3; k++) ctr[k] = (bmax[k] + bmin[k]) / RC(2.0);
     return;
   }
-  const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
-  const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
-  const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
-  const float third = 1.0f / 3.0f;
+  const real *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
+  const real *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
+  const real *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
+  const real third = RC(1.0) / RC(3.0);
   for (int k = 0; k < 3; k++) {
     bmin[k] = stdmin(p0[k], stdmin(p1[k], p2[k]));
     bmax[k] = stdmax(p0[k], stdmax(p1[k], p2[k]));
@@ -178,10 +202,10 @@ static void orc_prim_bbox_center(const orc_mesh *m, uint32_t prim, float bmin[3]
 }
 
 static void orc_range_bbox(const orc_mesh *m, const uint32_t *idx, uint32_t l, uint32_t r,
-                           float bmin[3], float bmax[3]) {
+                           real bmin[3], real bmax[3]) {
   orc_prim_bbox(m, idx[l], bmin, bmax);
   for (uint32_t i = l + 1; i < r; i++) {
-    float a[3], b[3];
+    real a[3], b[3];
     orc_prim_bbox(m, idx[i], a, b);
     for (int k = 0; k < 3; k++) {
       bmin[k] = stdmin(bmin[k], a[k]);
@@ -192,42 +216,42 @@ static void orc_range_bbox(const orc_mesh *m, const uint32_t *idx, uint32_t l, u
 
 /* ------------------------------------------------------------------ SAH bins */
 typedef struct {
-  float bmin[3], bmax[3];
+  real bmin[3], bmax[3];
   size_t count;
-  float cost;
+  real cost;
 } orc_bin;
 
-static inline float orc_area(const float lo[3], const float hi[3]) {
-  float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-  return 2.0f * ((dx * dy + dy * dz) + dz * dx);
+static inline real orc_area(const real lo[3], const real hi[3]) {
+  real dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  return RC(2.0) * ((dx * dy + dy * dz) + dz * dx);
 }
 
 static void orc_bins_clear(orc_bin *bins, uint32_t B) {
   for (uint32_t i = 0; i < 3 * B; i++) {
     for (int k = 0; k < 3; k++) {
-      bins[i].bmin[k] = FLT_MAX;
-      bins[i].bmax[k] = -FLT_MAX;
+      bins[i].bmin[k] = R_MAX;
+      bins[i].bmax[k] = -R_MAX;
     }
     bins[i].count = 0;
-    bins[i].cost = 0.0f;
+    bins[i].cost = RC(0.0);
   }
 }
 
-static void orc_fill_bins(orc_bin *bins, uint32_t B, uint32_t guard, const float nmin[3],
-                          const float nmax[3], const orc_mesh *m, const uint32_t *idx, uint32_t l,
+static void orc_fill_bins(orc_bin *bins, uint32_t B, uint32_t guard, const real nmin[3],
+                          const real nmax[3], const orc_mesh *m, const uint32_t *idx, uint32_t l,
                           uint32_t r) {
-  float inv[3];
-  const float fB = (float)B;
+  real inv[3];
+  const real fB = (real)B;
   for (int k = 0; k < 3; k++) {
-    float sz = nmax[k] - nmin[k];
-    inv[k] = (sz > 0.0f) ? fB / sz : 0.0f;
+    real sz = nmax[k] - nmin[k];
+    inv[k] = (sz > RC(0.0)) ? fB / sz : RC(0.0);
   }
   orc_bins_clear(bins, B);
   for (uint32_t i = l; i < r; i++) {
-    float lo[3], hi[3], c[3];
+    real lo[3], hi[3], c[3];
     orc_prim_bbox_center(m, idx[i], lo, hi, c);
     for (int j = 0; j < 3; j++) {
-      float q = (c[j] - nmin[j]) * inv[j];
+      real q = (c[j] - nmin[j]) * inv[j];
       int qi = (int)q;
       if (qi < 0) qi = 0;
       uint32_t b = (uint32_t)qi;
@@ -248,14 +272,14 @@ static void orc_fill_bins(orc_bin *bins, uint32_t B, uint32_t guard, const float
   }
 }
 
-static void orc_find_cut(orc_bin *bins, uint32_t B, const float nmin[3], const float nmax[3],
-                         float cut_pos[3], int *best_axis) {
-  float best[3];
+static void orc_find_cut(orc_bin *bins, uint32_t B, const real nmin[3], const real nmax[3],
+                         real cut_pos[3], int *best_axis) {
+  real best[3];
   for (int j = 0; j < 3; j++) {
     orc_bin *ax = bins + (size_t)j * B;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    real lo[3] = {R_MAX, R_MAX, R_MAX}, hi[3] = {-R_MAX, -R_MAX, -R_MAX};
     size_t cnt = 0;
-    best[j] = FLT_MAX;
+    best[j] = R_MAX;
     /* right-to-left: cost of the right-hand side starting at bin i */
     for (size_t i = B - 1; i > 0; i--) {
       for (int k = 0; k < 3; k++) {
@@ -263,11 +287,11 @@ static void orc_find_cut(orc_bin *bins, uint32_t B, const float nmin[3], const f
         hi[k] = stdmax(ax[i].bmax[k], hi[k]);
       }
       cnt += ax[i].count;
-      ax[i].cost = (float)cnt * orc_area(lo, hi);
+      ax[i].cost = (real)cnt * orc_area(lo, hi);
     }
     for (int k = 0; k < 3; k++) {
-      lo[k] = FLT_MAX;
-      hi[k] = -FLT_MAX;
+      lo[k] = R_MAX;
+      hi[k] = -R_MAX;
     }
     cnt = 0;
     size_t arg = 1;
@@ -277,13 +301,13 @@ static void orc_find_cut(orc_bin *bins, uint32_t B, const float nmin[3], const f
         hi[k] = stdmax(ax[i].bmax[k], hi[k]);
       }
       cnt += ax[i].count;
-      float c = (float)cnt * orc_area(lo, hi) + ax[i + 1].cost;
+      real c = (real)cnt * orc_area(lo, hi) + ax[i + 1].cost;
       if (c < best[j]) {
         best[j] = c;
         arg = i + 1;
       }
     }
-    cut_pos[j] = (float)arg * ((nmax[j] - nmin[j]) / (float)B) + nmin[j];
+    cut_pos[j] = (real)arg * ((nmax[j] - nmin[j]) / (real)B) + nmin[j];
   }
   int a = 0;
   if (best[0] > best[1]) a = 1;
@@ -291,22 +315,22 @@ static void orc_find_cut(orc_bin *bins, uint32_t B, const float nmin[3], const f
   *best_axis = a;
 }
 
-static inline int orc_pred(const orc_mesh *m, uint32_t prim, int axis, float pos) {
+static inline int orc_pred(const orc_mesh *m, uint32_t prim, int axis, real pos) {
   if (m->boxes) {
-    const float *b = m->boxes + 6 * (size_t)prim;
-    return (b[axis] + b[3 + axis]) / 2.0f < pos;
+    const real *b = m->boxes + 6 * (size_t)prim;
+    return (b[axis] + b[3 + axis]) / RC(2.0) < pos;
   }
-  const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
-  const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
-  const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
-  float s = (p0[axis] + p1[axis]) + p2[axis];
-  return s < pos * 3.0f;
+  const real *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
+  const real *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
+  const real *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
+  real s = (p0[axis] + p1[axis]) + p2[axis];
+  return s < pos * RC(3.0);
 }
 
 /* two-pointer in-place partition: element order after the call is the one
  * libstdc++'s std::partition (bidirectional iterators) leaves behind */
 static uint32_t orc_partition(uint32_t *idx, uint32_t l, uint32_t r, const orc_mesh *m, int axis,
-                              float pos) {
+                              real pos) {
   uint32_t first = l, last = r;
   for (;;) {
     for (;;) {
@@ -361,9 +385,9 @@ typedef struct {
 } build_ctx;
 
 /* chooses the split of [l,r): returns mid and the axis label the node gets */
-static uint32_t orc_split(build_ctx *c, uint32_t l, uint32_t r, const float bmin[3],
-                          const float bmax[3], int *axis_out) {
-  float cut[3] = {0.0f, 0.0f, 0.0f};
+static uint32_t orc_split(build_ctx *c, uint32_t l, uint32_t r, const real bmin[3],
+                          const real bmax[3], int *axis_out) {
+  real cut[3] = {RC(0.0), RC(0.0), RC(0.0)};
   int first_axis = 0;
   uint32_t n = r - l;
   orc_fill_bins(c->bins, c->opt.bin_size, c->guard, bmin, bmax, &c->mesh, c->idx, l, r);
@@ -383,7 +407,7 @@ static uint32_t orc_split(build_ctx *c, uint32_t l, uint32_t r, const float bmin
   return mid;
 }
 
-static void set_box(orc_node *nd, const float bmin[3], const float bmax[3]) {
+static void set_box(orc_node *nd, const real bmin[3], const real bmax[3]) {
   for (int k = 0; k < 3; k++) {
     nd->bmin[k] = bmin[k];
     nd->bmax[k] = bmax[k];
@@ -394,7 +418,7 @@ static uint32_t orc_build_rec(build_ctx *c, orc_stats *st, node_vec *out, uint32
                               uint32_t depth) {
   uint32_t self = (uint32_t)out->n;
   if (st->max_tree_depth < depth) st->max_tree_depth = depth;
-  float bmin[3], bmax[3];
+  real bmin[3], bmax[3];
   orc_range_bbox(&c->mesh, c->idx, l, r, bmin, bmax);
   uint32_t n = r - l;
   orc_node nd;
@@ -427,7 +451,7 @@ static uint32_t orc_build_shallow_rec(build_ctx *c, orc_stats *st, node_vec *out
                                       uint32_t r, uint32_t depth, uint32_t max_shallow) {
   uint32_t self = (uint32_t)out->n;
   if (st->max_tree_depth < depth) st->max_tree_depth = depth;
-  float bmin[3], bmax[3];
+  real bmin[3], bmax[3];
   orc_range_bbox(&c->mesh, c->idx, l, r, bmin, bmax);
   uint32_t n = r - l;
   orc_node nd;
@@ -527,7 +551,7 @@ static size_t orc_build_core(const orc_mesh *mesh, uint32_t n_prims, const orc_b
   return out.n;
 }
 
-size_t orc_build(const float *verts, size_t stride, const uint32_t *faces, uint32_t n_prims,
+size_t orc_build(const real *verts, size_t stride, const uint32_t *faces, uint32_t n_prims,
                  const orc_build_options *opts, uint32_t mode, orc_node **nodes_out,
                  uint32_t *indices_out, orc_stats *stats_out) {
   orc_mesh m = {(const unsigned char *)verts, stride, faces, NULL};
@@ -536,7 +560,7 @@ size_t orc_build(const float *verts, size_t stride, const uint32_t *faces, uint3
 
 /* the same Build over axis-aligned boxes as primitives (Scene::Commit's top-level build with
  * NodeBBoxGeometry / NodeBBoxPred, examples/nanosg/nanosg.h:722-737) */
-size_t orc_build_boxes(const float *boxes6, uint32_t n_prims, const orc_build_options *opts, uint32_t mode,
+size_t orc_build_boxes(const real *boxes6, uint32_t n_prims, const orc_build_options *opts, uint32_t mode,
                        orc_node **nodes_out, uint32_t *indices_out, orc_stats *stats_out) {
   orc_mesh m = {NULL, 0, NULL, boxes6};
   return orc_build_core(&m, n_prims, opts, mode, nodes_out, indices_out, stats_out);
@@ -552,48 +576,48 @@ typedef struct {
 } orc_counters;
 
 typedef struct {
-  float org[3];
-  float inv[3];
+  real org[3];
+  real inv[3];
   int sign[3];
   int kx, ky, kz;
-  float Sx, Sy, Sz;
-  float t_min;
+  real Sx, Sy, Sz;
+  real t_min;
   orc_trace_options opt;
   /* running best */
-  float t, u, v;
+  real t, u, v;
   uint32_t prim;
 } ray_state;
 
-static inline float orc_safe_inverse(float d, int cpp11) {
-  if (fabsf(d) < FLT_EPSILON) {
-    float sgn;
+static inline real orc_safe_inverse(real d, int cpp11) {
+  if (R_FABS(d) < R_EPS) {
+    real sgn;
     if (cpp11)
-      sgn = copysignf(1.0f, d); /* -0.0f -> -inf */
+      sgn = R_COPYSIGN(RC(1.0), d); /* -0.0 -> -inf */
     else
-      sgn = (d < 0.0f) ? -1.0f : 1.0f; /* -0.0f -> +inf */
+      sgn = (d < RC(0.0)) ? -RC(1.0) : RC(1.0); /* -0.0 -> +inf */
     return INFINITY * sgn;
   }
-  return 1.0f / d;
+  return RC(1.0) / d;
 }
 
 static void orc_prepare(ray_state *s, const orc_ray *ray, const orc_trace_options *opt, int cpp11) {
   for (int k = 0; k < 3; k++) {
     s->org[k] = ray->org[k];
-    s->sign[k] = ray->dir[k] < 0.0f ? 1 : 0;
+    s->sign[k] = ray->dir[k] < RC(0.0) ? 1 : 0;
     s->inv[k] = orc_safe_inverse(ray->dir[k], cpp11);
   }
   int kz = 0;
-  float m = fabsf(ray->dir[0]);
-  if (m < fabsf(ray->dir[1])) {
+  real m = R_FABS(ray->dir[0]);
+  if (m < R_FABS(ray->dir[1])) {
     kz = 1;
-    m = fabsf(ray->dir[1]);
+    m = R_FABS(ray->dir[1]);
   }
-  if (m < fabsf(ray->dir[2])) {
+  if (m < R_FABS(ray->dir[2])) {
     kz = 2;
   }
   int kx = kz + 1 == 3 ? 0 : kz + 1;
   int ky = kx + 1 == 3 ? 0 : kx + 1;
-  if (ray->dir[kz] < 0.0f) {
+  if (ray->dir[kz] < RC(0.0)) {
     int t = kx;
     kx = ky;
     ky = t;
@@ -603,63 +627,63 @@ static void orc_prepare(ray_state *s, const orc_ray *ray, const orc_trace_option
   s->kz = kz;
   s->Sx = ray->dir[kx] / ray->dir[kz];
   s->Sy = ray->dir[ky] / ray->dir[kz];
-  s->Sz = 1.0f / ray->dir[kz];
+  s->Sz = RC(1.0) / ray->dir[kz];
   s->t_min = ray->min_t;
   s->opt = *opt;
-  s->u = 0.0f;
-  s->v = 0.0f;
+  s->u = RC(0.0);
+  s->v = RC(0.0);
 }
 
 /* (a > b) ? a : b and (a < b) ? a : b, the reference's safemax / safemin */
-static inline float smax(float a, float b) { return (a > b) ? a : b; }
-static inline float smin(float a, float b) { return (a < b) ? a : b; }
+static inline real smax(real a, real b) { return (a > b) ? a : b; }
+static inline real smin(real a, real b) { return (a < b) ? a : b; }
 
-static inline int orc_slab(const ray_state *s, const orc_node *nd, float min_t, float max_t) {
-  float tn[3], tf[3];
+static inline int orc_slab(const ray_state *s, const orc_node *nd, real min_t, real max_t) {
+  real tn[3], tf[3];
   for (int k = 0; k < 3; k++) {
-    float nearp = s->sign[k] ? nd->bmax[k] : nd->bmin[k];
-    float farp = s->sign[k] ? nd->bmin[k] : nd->bmax[k];
+    real nearp = s->sign[k] ? nd->bmax[k] : nd->bmin[k];
+    real farp = s->sign[k] ? nd->bmin[k] : nd->bmax[k];
     tn[k] = (nearp - s->org[k]) * s->inv[k];
-    tf[k] = ((farp - s->org[k]) * s->inv[k]) * 1.00000024f;
+    tf[k] = ((farp - s->org[k]) * s->inv[k]) * R_MAXMULT;
   }
-  float tmin = smax(tn[2], smax(tn[1], smax(tn[0], min_t)));
-  float tmax = smin(tf[2], smin(tf[1], smin(tf[0], max_t)));
+  real tmin = smax(tn[2], smax(tn[1], smax(tn[0], min_t)));
+  real tmax = smin(tf[2], smin(tf[1], smin(tf[0], max_t)));
   return tmin <= tmax;
 }
 
-static inline int orc_tri(ray_state *s, const orc_mesh *m, uint32_t prim, float *t_inout) {
+static inline int orc_tri(ray_state *s, const orc_mesh *m, uint32_t prim, real *t_inout) {
   if (prim < s->opt.prim_ids_range[0] || prim >= s->opt.prim_ids_range[1]) return 0;
   if (prim == s->opt.skip_prim_id) return 0;
-  const float *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
-  const float *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
-  const float *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
-  float A[3], B[3], C[3];
+  const real *p0 = vtx(m, m->faces[3 * (size_t)prim + 0]);
+  const real *p1 = vtx(m, m->faces[3 * (size_t)prim + 1]);
+  const real *p2 = vtx(m, m->faces[3 * (size_t)prim + 2]);
+  real A[3], B[3], C[3];
   for (int k = 0; k < 3; k++) {
     A[k] = p0[k] - s->org[k];
     B[k] = p1[k] - s->org[k];
     C[k] = p2[k] - s->org[k];
   }
   const int kx = s->kx, ky = s->ky, kz = s->kz;
-  const float Ax = A[kx] - s->Sx * A[kz], Ay = A[ky] - s->Sy * A[kz];
-  const float Bx = B[kx] - s->Sx * B[kz], By = B[ky] - s->Sy * B[kz];
-  const float Cx = C[kx] - s->Sx * C[kz], Cy = C[ky] - s->Sy * C[kz];
-  float U = Cx * By - Cy * Bx;
-  float V = Ax * Cy - Ay * Cx;
-  float W = Bx * Ay - By * Ax;
-  if (U == 0.0f || V == 0.0f || W == 0.0f) {
-    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
-    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
-    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  const real Ax = A[kx] - s->Sx * A[kz], Ay = A[ky] - s->Sy * A[kz];
+  const real Bx = B[kx] - s->Sx * B[kz], By = B[ky] - s->Sy * B[kz];
+  const real Cx = C[kx] - s->Sx * C[kz], Cy = C[ky] - s->Sy * C[kz];
+  real U = Cx * By - Cy * Bx;
+  real V = Ax * Cy - Ay * Cx;
+  real W = Bx * Ay - By * Ax;
+  if (U == RC(0.0) || V == RC(0.0) || W == RC(0.0)) {
+    U = (real)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (real)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (real)((double)Bx * (double)Ay - (double)By * (double)Ax);
   }
-  if (U < 0.0f || V < 0.0f || W < 0.0f) {
-    if (s->opt.cull_back_face || U > 0.0f || V > 0.0f || W > 0.0f) return 0;
+  if (U < RC(0.0) || V < RC(0.0) || W < RC(0.0)) {
+    if (s->opt.cull_back_face || U > RC(0.0) || V > RC(0.0) || W > RC(0.0)) return 0;
   }
-  float det = (U + V) + W;
-  if (det == 0.0f) return 0;
-  const float Az = s->Sz * A[kz], Bz = s->Sz * B[kz], Cz = s->Sz * C[kz];
-  const float D = (U * Az + V * Bz) + W * Cz;
-  const float rcp = 1.0f / det;
-  const float tt = D * rcp;
+  real det = (U + V) + W;
+  if (det == RC(0.0)) return 0;
+  const real Az = s->Sz * A[kz], Bz = s->Sz * B[kz], Cz = s->Sz * C[kz];
+  const real D = (U * Az + V * Bz) + W * Cz;
+  const real rcp = RC(1.0) / det;
+  const real tt = D * rcp;
   if (tt > *t_inout) return 0;
   if (tt < s->t_min) return 0;
   *t_inout = tt;
@@ -671,7 +695,7 @@ static inline int orc_tri(ray_state *s, const orc_mesh *m, uint32_t prim, float 
 #define ORC_STACK 512
 
 /* returns 1 on hit (hit written), 0 on miss (hit untouched) */
-int orc_traverse_one(const orc_node *nodes, const uint32_t *indices, const float *verts,
+int orc_traverse_one(const orc_node *nodes, const uint32_t *indices, const real *verts,
                      size_t stride, const uint32_t *faces, const orc_ray *ray,
                      const orc_trace_options *topt, int cpp11, orc_hit *hit, orc_counters *ctr) {
   orc_mesh m = {(const unsigned char *)verts, stride, faces, NULL};
@@ -681,7 +705,7 @@ int orc_traverse_one(const orc_node *nodes, const uint32_t *indices, const float
     topt = &dflt;
   }
   ray_state s;
-  float hit_t = ray->max_t;
+  real hit_t = ray->max_t;
   s.t = hit_t;
   s.prim = 0xFFFFFFFFu;
   orc_prepare(&s, ray, topt, cpp11);
@@ -700,11 +724,11 @@ int orc_traverse_one(const orc_node *nodes, const uint32_t *indices, const float
       stack[++sp] = nd->data[nearc];
       if (ctr && (uint32_t)sp > ctr->max_stack) ctr->max_stack = (uint32_t)sp;
     } else {
-      float t = s.t;
+      real t = s.t;
       int any = 0;
       for (uint32_t i = 0; i < nd->data[0]; i++) {
         uint32_t prim = indices[nd->data[1] + i];
-        float lt = t;
+        real lt = t;
         if (ctr) ctr->prims_tested++;
         if (orc_tri(&s, &m, prim, &lt)) {
           t = lt;
@@ -729,7 +753,7 @@ int orc_traverse_one(const orc_node *nodes, const uint32_t *indices, const float
 typedef struct {
   const orc_node *nodes;
   const uint32_t *indices;
-  const float *verts;
+  const real *verts;
   size_t stride;
   const uint32_t *faces;
   const orc_ray *rays;
@@ -766,7 +790,7 @@ static void *batch_worker(void *arg) {
 }
 
 /* hits[i] is written only where mask[i] == 1 (reference semantics, nanort.h:1205-1213) */
-size_t orc_traverse_batch(const orc_node *nodes, const uint32_t *indices, const float *verts,
+size_t orc_traverse_batch(const orc_node *nodes, const uint32_t *indices, const real *verts,
                           size_t stride, const uint32_t *faces, const orc_ray *rays, size_t n_rays,
                           orc_hit *hits, uint8_t *mask, const orc_trace_options *topt, int cpp11,
                           int n_threads, orc_counters *ctr_out) {
@@ -818,7 +842,7 @@ size_t orc_traverse_batch(const orc_node *nodes, const uint32_t *indices, const 
 /* Re-tests ONE primitive for ONE ray with the reference arithmetic; used by the
  * parity checker to classify exact-t ties: returns 1 and the
  * (t,u,v) this primitive alone would report with t_inout = max_t. */
-int orc_test_prim(const float *verts, size_t stride, const uint32_t *faces, const orc_ray *ray,
+int orc_test_prim(const real *verts, size_t stride, const uint32_t *faces, const orc_ray *ray,
                   const orc_trace_options *topt, int cpp11, uint32_t prim, orc_hit *out) {
   orc_mesh m = {(const unsigned char *)verts, stride, faces, NULL};
   orc_trace_options dflt;
@@ -828,7 +852,7 @@ int orc_test_prim(const float *verts, size_t stride, const uint32_t *faces, cons
   }
   ray_state s;
   orc_prepare(&s, ray, topt, cpp11);
-  float t = ray->max_t;
+  real t = ray->max_t;
   if (!orc_tri(&s, &m, prim, &t)) return 0;
   out->t = t;
   out->u = s.u;
@@ -837,6 +861,7 @@ int orc_test_prim(const float *verts, size_t stride, const uint32_t *faces, cons
   return 1;
 }
 
+#ifndef ORC_DOUBLE /* the scene-graph example is float only (nanosg::Scene<float, M> in the reference's renderer) */
 /* ====================================================================== two-level scene
  * Restatement of the reference's scene-graph example (examples/nanosg/nanosg.h) for the instancing row:
  *   orc_mat_inverse            Matrix::Inverse (Cramer's rule)          nanosg.h:92-184
@@ -1182,3 +1207,4 @@ size_t orc_sg_traverse_batch(const orc_node *top, const uint32_t *top_idx, const
   for (int t = 0; t < n_threads; t++) total += jobs[t].n_hits;
   return total;
 }
+#endif /* !ORC_DOUBLE */

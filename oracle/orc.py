@@ -430,10 +430,75 @@ NODE64_DTYPE = np.dtype([("bmin", "<f8", (3,)), ("bmax", "<f8", (3,)), ("flag", 
                          ("data", "<u4", (2,))])
 
 
+BUILD_OPT64_DTYPE = np.dtype([("cost_t_aabb", "<f8"), ("min_leaf_primitives", "<u4"), ("max_tree_depth", "<u4"),
+                              ("bin_size", "<u4"), ("shallow_depth", "<u4"),
+                              ("min_primitives_for_parallel_build", "<u4"), ("cache_bbox", "u1"), ("pad", "u1", (3,))])
+assert BUILD_OPT64_DTYPE.itemsize == 32
+
+
+def build_options_f64(**kw):
+    o = np.zeros(1, BUILD_OPT64_DTYPE)
+    o["cost_t_aabb"], o["min_leaf_primitives"], o["max_tree_depth"], o["bin_size"] = 0.2, 4, 256, 64
+    o["shallow_depth"], o["min_primitives_for_parallel_build"] = 4, 8192
+    for k, v in kw.items():
+        o[k] = v
+    return o
+
+
+class Port64:
+    """The C restatement instantiated for double (oracle/liborc64.so = nanort_oracle.c with -DORC_DOUBLE)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "liborc64.so")
+        if not os.path.exists(path):
+            make(force=True)
+        self.lib = L = C.CDLL(path)
+        L.orc_build.restype = C.c_size_t
+        L.orc_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_traverse_batch.restype = C.c_size_t
+        L.orc_traverse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p]
+        L.orc_sizes.argtypes = [C.c_void_p]
+
+    def sizes(self):
+        s = np.zeros(5, np.uint32)
+        self.lib.orc_sizes(_p(s))
+        return [int(x) for x in s]
+
+    def build(self, verts, faces, opts=None, mode=MODE_CPP11):
+        verts = np.ascontiguousarray(verts, np.float64)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        n = len(faces)
+        indices, stats, out = np.zeros(n, np.uint32), np.zeros(3, np.uint32), C.c_void_p()
+        nn = self.lib.orc_build(_p(verts), 24, _p(faces), n, _p(opts) if opts is not None else None, mode,
+                                C.byref(out), _p(indices), _p(stats))
+        if nn == 0:
+            return None
+        nodes = np.frombuffer((C.c_char * (nn * 64)).from_address(out.value), NODE64_DTYPE).copy()
+        self.lib.orc_free(out)
+        return nodes, indices, {"max_tree_depth": int(stats[0]), "num_leaf_nodes": int(stats[1]),
+                                "num_branch_nodes": int(stats[2])}
+
+    def traverse(self, nodes, indices, verts, faces, rays, topts=None, cpp11=True, threads=1):
+        nodes = np.ascontiguousarray(nodes)
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype.itemsize == 72 and nodes.dtype.itemsize == 64
+        verts = np.ascontiguousarray(verts, np.float64)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        indices = np.ascontiguousarray(indices, np.uint32)
+        n = len(rays)
+        hits, mask = np.zeros(n, HIT64_DTYPE), np.zeros(n, np.uint8)
+        self.lib.orc_traverse_batch(_p(nodes), _p(indices), _p(verts), 24, _p(faces), _p(rays), n, _p(hits), _p(mask),
+                                    _p(topts) if topts is not None else None, 1 if cpp11 else 0, threads, None)
+        return hits, mask
+
+
 class ReferenceF64:
-    """nanort::BVHAccel<double> of the unmodified reference (oracle/_ref, ref64_* in oracle/ref_shim.cc).  There is
-    no C restatement of the fp64 instantiation: fp64 parity is checked against the reference directly and against
-    the committed golden vectors (tests/golden/regression30.npz)."""
+    """nanort::BVHAccel<double> of the unmodified reference (oracle/_ref, ref64_* in oracle/ref_shim.cc); Port64 is
+    pinned to it (tests/test_oracle_f64.py)."""
 
     def __init__(self, cpp11=True):
         name = "libnanort_ref.so" if cpp11 else "libnanort_ref03.so"

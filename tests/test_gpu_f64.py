@@ -152,3 +152,32 @@ def test_f64_adopted_reference_tree_is_bit_exact(cpp11):
         bad = racc.nodes().copy()
         bad["data"][np.nonzero(bad["flag"] == 0)[0][0], 0] = len(bad) + 3
         api.BVHAccelF64().Adopt(bad, racc.indices(), v64, f)
+
+
+@pytest.mark.parametrize("cpp11", [True, False])
+def test_f64_against_the_c_restatement(cpp11):
+    """The same checks with the oracle proper (oracle/liborc64.so, pinned to the reference by tests/test_oracle_f64.py):
+    the port walking the GPU's BVHNode<double> array must reproduce the GPU's records bit for bit, and the GPU walking
+    the port's own (reference-identical) tree must reproduce the port's."""
+    from nanort_b200 import api
+    from oracle import orc
+
+    port = orc.Port64()
+    v64, f = _scene64(seed=13)
+    rays = _rays64(v64, 30000, seed=14)
+    flags = 0 if cpp11 else api.TRAVERSE_CPP03_INVERSE
+    acc = api.BVHAccelF64()
+    acc.Build(len(f), v64, f)
+    gh, gm = acc.Traverse(rays, flags=flags)
+    ph, pm = port.traverse(acc.GetNodes(), acc.GetIndices(), v64, f, rays, cpp11=cpp11, threads=8)
+    assert pm.sum() > 2000 and np.array_equal(pm, gm)
+    for k in ("t", "u", "v", "prim_id"):
+        assert ph[k][pm == 1].tobytes() == gh[k][gm == 1].tobytes(), k
+    nodes, idx, _ = port.build(v64, f, None, orc.MODE_CPP11 if cpp11 else 0)
+    adopted = api.BVHAccelF64()
+    adopted.Adopt(nodes, idx, v64, f)
+    ah, am = adopted.Traverse(rays, flags=flags)
+    qh, qm = port.traverse(nodes, idx, v64, f, rays, cpp11=cpp11, threads=8)
+    assert np.array_equal(qm, am)
+    for k in ("t", "u", "v", "prim_id"):
+        assert qh[k][qm == 1].tobytes() == ah[k][am == 1].tobytes(), k
