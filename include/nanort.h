@@ -29,14 +29,37 @@
 
 #include <stddef.h>
 #include <stdint.h>
-#include <stdio.h>
-#include <string.h>
 
+// the reference header's own include set (nanort.h:36-49, 67-73): callers such as examples/path_tracer/main.cc rely on
+// it transitively (std::atomic / std::thread under NANORT_USE_CPP11_FEATURE, assert, std::string ...)
+#include <algorithm>
+#include <cassert>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
+#include <mutex>
+#include <queue>
+#include <string>
 #include <type_traits>
 #include <vector>
+
+// constants of the reference (nanort.h:62-65)
+#define kNANORT_MAX_STACK_DEPTH (512)
+#define kNANORT_MIN_PRIMITIVES_FOR_PARALLEL_BUILD (1024 * 8)
+#define kNANORT_SHALLOW_DEPTH (4)
+
+#ifdef NANORT_USE_CPP11_FEATURE
+#include <atomic>
+#include <thread>
+#define kNANORT_MAX_THREADS (256)
+#ifndef NANORT_ENABLE_PARALLEL_BUILD
+#define NANORT_ENABLE_PARALLEL_BUILD
+#endif
+#endif
 
 #include "nanort_b200.h"
 
@@ -77,7 +100,7 @@ template <typename T = float>
 class real3 {
  public:
   real3() { v[0] = v[1] = v[2] = T(0); }
-  explicit real3(T s) { v[0] = v[1] = v[2] = s; }
+  real3(T s) { v[0] = v[1] = v[2] = s; }  // implicit, as nanort.h:325
   real3(T x, T y, T z) {
     v[0] = x;
     v[1] = y;
@@ -124,9 +147,41 @@ inline T vlength(const real3<T> &a) {
   return std::sqrt(vdot(a, a));
 }
 template <typename T>
-inline real3<T> vnormalize(const real3<T> &a) {
-  T l = vlength(a);
-  return l > T(0) ? a * (T(1) / l) : a;
+inline real3<T> vneg(const real3<T> &a) {  // nanort.h:377-380
+  return real3<T>(-a[0], -a[1], -a[2]);
+}
+template <typename T>
+inline real3<T> vnormalize(const real3<T> &a) {  // nanort.h:387-398: unchanged below epsilon, else scaled by 1 / length
+  real3<T> r = a;
+  const T l = vlength(a);
+  if (std::fabs(l) > std::numeric_limits<T>::epsilon()) {
+    const T inv = T(1) / l;
+    r[0] *= inv;
+    r[1] *= inv;
+    r[2] *= inv;
+  }
+  return r;
+}
+// nanort.h:414-465: 1 / v with +-inf for |v| < epsilon; the sign convention follows NANORT_USE_CPP11_FEATURE
+template <typename T>
+inline real3<T> vsafe_inverse(const real3<T> v) {
+  real3<T> r;
+  for (int k = 0; k < 3; k++) {
+    if (std::fabs(v[k]) < std::numeric_limits<T>::epsilon()) {
+#ifdef NANORT_USE_CPP11_FEATURE
+      r[k] = std::numeric_limits<T>::infinity() * std::copysign(T(1), v[k]);
+#else
+      r[k] = std::numeric_limits<T>::infinity() * (v[k] < T(0) ? T(-1) : T(1));
+#endif
+    } else {
+      r[k] = T(1) / v[k];
+    }
+  }
+  return r;
+}
+template <typename real>
+inline const real *get_vertex_addr(const real *p, const size_t idx, const size_t stride_bytes) {  // nanort.h:467-472
+  return reinterpret_cast<const real *>(reinterpret_cast<const unsigned char *>(p) + idx * stride_bytes);
 }
 
 // ---- value types ----------------------------------------------------------------------------
@@ -207,8 +262,68 @@ static_assert(sizeof(BVHBuildOptions<float>) == 28, "nanort::BVHBuildOptions<flo
 static_assert(sizeof(BVHBuildStatistics) == 16, "nanort::BVHBuildStatistics layout");
 static_assert(sizeof(BVHTraceOptions) == 16, "nanort::BVHTraceOptions layout");
 
+// ---- node-traversal records of the two-level API -- :629-694
+template <typename T>
+class BBox {
+ public:
+  real3<T> bmin;
+  real3<T> bmax;
+  BBox() {
+    bmin[0] = bmin[1] = bmin[2] = std::numeric_limits<T>::max();
+    bmax[0] = bmax[1] = bmax[2] = -std::numeric_limits<T>::max();
+  }
+};
+
+template <typename T>
+class NodeHit {
+ public:
+  NodeHit()
+      : t_min(std::numeric_limits<T>::max()), t_max(-std::numeric_limits<T>::max()),
+        node_id(static_cast<unsigned int>(-1)) {}
+  T t_min;
+  T t_max;
+  unsigned int node_id;
+};
+
+template <typename T>
+class NodeHitComparator {
+ public:
+  inline bool operator()(const NodeHit<T> &a, const NodeHit<T> &b) { return a.t_min < b.t_min; }
+};
+
+template <class H>
+class IntersectComparator {  // :552-557
+ public:
+  bool operator()(const H &a, const H &b) const { return a.t < b.t; }
+};
+
+// nanort.h:286-319: the reference's fixed-capacity vector (a std::vector over a stack arena).  Same surface
+// (operator->, operator[], container()); storage is a std::vector reserved to the capacity.
+template <typename T, size_t stack_capacity>
+class StackVector {
+ public:
+  typedef std::vector<T> ContainerType;
+  StackVector() { container_.reserve(stack_capacity); }
+  ContainerType &container() { return container_; }
+  const ContainerType &container() const { return container_; }
+  ContainerType *operator->() { return &container_; }
+  const ContainerType *operator->() const { return &container_; }
+  T &operator[](size_t i) { return container_[i]; }
+  const T &operator[](size_t i) const { return container_[i]; }
+
+ private:
+  ContainerType container_;
+};
+
 // ---- built-in triangle classes ----------------------------------------------------------------
 namespace detail {
+// a mutex that does not make its owner non-copyable (copies of a BVHAccel share the device tree, not the lock)
+struct CopyableMutex {
+  std::mutex m;
+  CopyableMutex() {}
+  CopyableMutex(const CopyableMutex &) {}
+  CopyableMutex &operator=(const CopyableMutex &) { return *this; }
+};
 template <typename T>
 inline const T *vertex_at(const T *base, size_t i, size_t stride_bytes) {
   return reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(base) + i * stride_bytes);
@@ -303,11 +418,34 @@ class TriangleIntersector {
   const unsigned int *GetFaces() const { return faces_; }
   size_t GetVertexStrideBytes() const { return vertex_stride_bytes_; }
 
+  /// Closest distance found by the last Traverse made with this object (nanort.h:1159; callers such as
+  /// examples/par_msquare/main.cc:501 read it instead of the hit record).
+  T GetT() const { return t_; }
+  /// BVHAccel::Traverse stores the device's result here (what Update + PostTraversal do in the reference, :1153-1213)
+  void SetResult(T t, T u, T v, unsigned int prim_id) const {
+    t_ = t;
+    u_ = u;
+    v_ = v;
+    prim_id_ = prim_id;
+  }
+
  private:
   const T *vertices_;
   const unsigned int *faces_;
   const size_t vertex_stride_bytes_;
+  mutable T t_ = T(0), u_ = T(0), v_ = T(0);
+  mutable unsigned int prim_id_ = static_cast<unsigned int>(-1);
 };
+
+namespace detail {
+// writes the result into intersectors that can take it (the built-in one); user types without SetResult are left alone
+template <class I, class T>
+inline auto set_result(const I &isec, T t, T u, T v, unsigned int prim, int) -> decltype(isec.SetResult(t, u, v, prim), void()) {
+  isec.SetResult(t, u, v, prim);
+}
+template <class I, class T>
+inline void set_result(const I &, T, T, T, unsigned int, long) {}
+}  // namespace detail
 
 // ---- BVHAccel ------------------------------------------------------------------------------------
 template <typename T>
@@ -365,6 +503,7 @@ class BVHAccel<float> {
       fprintf(stderr, "nanort_b200: Traverse failed: %s\n", nrt_last_error());
       return false;
     }
+    detail::set_result(intersector, rec.t, rec.u, rec.v, rec.prim_id, 0);
     if (hit && isect) {  // *isect stays untouched on a miss, as in the reference
       isect->t = rec.t;
       isect->u = rec.u;
@@ -470,8 +609,11 @@ class BVHAccel<float> {
   const nrt_accel *NativeHandle() const { return handle_.get(); }
 
  private:
+  // The reference's Traverse may run on many threads at once (examples/path_tracer/main.cc:787-799): the lazy adopt of
+  // a Load()ed tree and the lazy host mirror are serialised.
   template <class I>
   bool Ready(const I &isec) const {
+    std::lock_guard<std::mutex> lock(mu_.m);
     if (handle_) return true;
     if (nodes_.empty()) return false;
     // a Load()ed tree: adopt it now that the intersector supplies the geometry
@@ -490,6 +632,7 @@ class BVHAccel<float> {
     return true;
   }
   void Mirror() const {
+    std::lock_guard<std::mutex> lock(mu_.m);
     if (mirrors_ || !handle_) return;
     const void *pn = NULL;
     const uint32_t *pi = NULL;
@@ -505,6 +648,7 @@ class BVHAccel<float> {
   mutable std::vector<BVHNode<float> > nodes_;
   mutable std::vector<unsigned int> indices_;
   mutable bool mirrors_ = false;
+  mutable detail::CopyableMutex mu_;
   BVHBuildOptions<float> options_;
   mutable BVHBuildStatistics stats_;
   unsigned int n_prims_;
@@ -587,6 +731,7 @@ class BVHAccel<double> {
       fprintf(stderr, "nanort_b200: Traverse<double> failed: %s\n", nrt_last_error());
       return false;
     }
+    detail::set_result(intersector, rec.t, rec.u, rec.v, rec.prim_id, 0);
     if (hit && isect) {
       isect->t = rec.t;
       isect->u = rec.u;
@@ -641,6 +786,7 @@ class BVHAccel<double> {
  private:
   template <class I>
   bool Ready(const I &isec) const {
+    std::lock_guard<std::mutex> lock(mu_.m);
     if (handle_) return true;
     if (nodes_.empty()) return false;
     nrt_accel_f64 *h = NULL;  // a Load()ed tree: adopt it now that the intersector supplies the geometry
@@ -655,6 +801,7 @@ class BVHAccel<double> {
     return true;
   }
   void Mirror() const {
+    std::lock_guard<std::mutex> lock(mu_.m);
     if (mirrors_ || !handle_) return;
     const void *pn = NULL;
     const uint32_t *pi = NULL;
@@ -669,6 +816,7 @@ class BVHAccel<double> {
   mutable std::vector<BVHNode<double> > nodes_;
   mutable std::vector<unsigned int> indices_;
   mutable bool mirrors_;
+  mutable detail::CopyableMutex mu_;
   mutable BVHBuildStatistics stats_;
 };
 

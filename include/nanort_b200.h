@@ -44,6 +44,10 @@ extern "C" {
 /* nrt_ao_params.flags only: run the AO stages as stand-alone kernels instead of fused into the traversal
  * kernel's retire step (A/B and equivalence tests; results are identical) */
 #define NRT_AO_UNFUSED 0x10000u
+/* nrt_ao_params.flags: d_accum is a tile-major buffer of THIS shard's tiles (tile k of the shard at float offset
+ * k * tile_w * tile_h, rows of tile_w floats) instead of the width x height image -- what nrt_render_ao_sharded
+ * accumulates into so that the framebuffer all-gather needs no pack step */
+#define NRT_AO_PACKED_TILES 0x20000u
 
 typedef struct nrt_accel nrt_accel; /* opaque: device-resident BVH + host mirrors */
 
@@ -129,6 +133,13 @@ int nrt_traverse_count_device(const nrt_accel *a, const void *d_rays_36B, size_t
                               const void *trace_opts_16B, uint32_t flags, uint64_t *boxes_tested,
                               uint64_t *prims_tested, void *stream);
 
+/* Measured roofs for benchmark reports (bench.py's roofline block), same process / device / clocks as the traversal:
+ * streaming read bandwidth over `bytes` of device memory with 16-byte loads (<= ~64 MB: L2-resident after the warm-up
+ * pass -> L2 roof; >= 1 GB -> HBM roof), and the pinned host <-> device copy rate (direction 0 = H2D, 1 = D2H).
+ * GB/s, best of `iters`.  Not part of the traversal path. */
+int nrt_probe_read_gbs(size_t bytes, int iters, double *gb_per_s);
+int nrt_probe_copy_gbs(size_t bytes, int iters, int direction, double *gb_per_s);
+
 /* Pinned host memory for ray / hit buffers handed to nrt_traverse (plain memory works too, slower). */
 void *nrt_host_alloc(size_t bytes);
 void nrt_host_free(void *p);
@@ -162,6 +173,8 @@ typedef struct nrt_ao_result {
   float total_ms;       /* device time of the whole pass */
   uint32_t launches;    /* kernels launched by this call */
   uint32_t traverse_launches;
+  float primary_traverse_ms; /* traverse_ms split by launch kind: camera-ray launches ... */
+  float ao_traverse_ms;      /* ... and AO-ray launches */
 } nrt_ao_result;
 
 /* d_accum: DEVICE float[width*height] accumulating sum of visibility (1 = unoccluded, 0.0 for primary
@@ -177,6 +190,28 @@ int nrt_render_ao_device(const nrt_accel *a, const nrt_ao_params *p, float *d_ac
  * very same rays. */
 int nrt_ao_workload_device(const nrt_accel *a, const nrt_ao_params *p, float *d_accum, void *d_primary_rays_36B,
                            void *d_ao_rays_36B, uint64_t *n_primary, uint64_t *n_ao, void *stream);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * One process (or host thread) per GPU.  Rays shard by image tile: tile t belongs to rank t % world; the BVH is
+ * replicated (every rank calls nrt_build on the same arrays: the builder is deterministic); there is no exchange
+ * during traversal and ONE collective per frame, the framebuffer all-gather (ncclAllGather over NVLink, in place, on
+ * the pass's stream).  NCCL is bound at run time (dlopen), so nothing here is needed for single-GPU use.
+ *
+ *   rank 0:            nrt_comm_unique_id(id)           -> ship the 128 bytes to the other ranks (pipe, file, MPI ...)
+ *   every rank:        nrt_set_device(local_gpu); nrt_build(...); nrt_comm_init(id, rank, world, &comm)
+ *   every frame, all:  nrt_render_ao_sharded(accel, comm, &params, d_frame_full, &res, stream)
+ *
+ * nrt_render_ao_sharded = nrt_render_ao_device over this rank's tiles (params.shard / n_shards are overwritten by
+ * the communicator's rank / size) + all-gather + unpack: on return (stream order) d_frame_full, a DEVICE
+ * float[width*height] on EVERY rank, holds the whole frame's visibility sums.  *res counts this rank's rays.
+ * examples/multi_gpu_ao.cc drives it with fork(), without MPI or torchrun. */
+typedef struct nrt_comm nrt_comm;
+int nrt_comm_unique_id(void *id_128B);
+int nrt_comm_init(const void *id_128B, int rank, int world, nrt_comm **out);
+void nrt_comm_free(nrt_comm *c);
+int nrt_comm_rank(const nrt_comm *c, int *rank, int *world);
+int nrt_render_ao_sharded(const nrt_accel *a, nrt_comm *c, const nrt_ao_params *p, float *d_frame_full,
+                          nrt_ao_result *res, void *stream);
 
 /*
  * Device-resident wavefront form of the reference path tracer's pixel -> sample -> bounce loop

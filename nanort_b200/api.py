@@ -54,6 +54,8 @@ EXPORTS = [
     "nrt_scene_commit", "nrt_scene_free", "nrt_scene_bounding_box", "nrt_scene_nodes", "nrt_scene_instance_state",
     "nrt_scene_traverse", "nrt_scene_traverse_device",
     "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
+    "nrt_comm_unique_id", "nrt_comm_init", "nrt_comm_free", "nrt_comm_rank", "nrt_render_ao_sharded",
+    "nrt_probe_read_gbs", "nrt_probe_copy_gbs",
 ]
 
 
@@ -79,6 +81,7 @@ class AoResult(C.Structure):
         ("primary_rays", C.c_uint64), ("ao_rays", C.c_uint64), ("ao_hits", C.c_uint64),
         ("traverse_ms", C.c_float), ("total_ms", C.c_float),
         ("launches", C.c_uint32), ("traverse_launches", C.c_uint32),
+        ("primary_traverse_ms", C.c_float), ("ao_traverse_ms", C.c_float),
     ]
 
 
@@ -157,6 +160,14 @@ def lib():
     L.nrt_bounding_box_f64.argtypes = [vp, vp, vp]
     L.nrt_nodes_f64.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
     L.nrt_traverse_f64.argtypes = [vp, vp, sz, vp, vp, vp, u32]
+    L.nrt_comm_unique_id.argtypes = [vp]
+    L.nrt_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.nrt_comm_free.argtypes = [vp]
+    L.nrt_comm_free.restype = None
+    L.nrt_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.nrt_render_ao_sharded.argtypes = [vp, vp, C.POINTER(AoParams), vp, C.POINTER(AoResult), vp]
+    L.nrt_probe_read_gbs.argtypes = [sz, C.c_int, C.POINTER(C.c_double)]
+    L.nrt_probe_copy_gbs.argtypes = [sz, C.c_int, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -192,6 +203,65 @@ def BVHTraceOptions(**kw):
     for k, v in kw.items():
         o[k] = v
     return o
+
+
+AO_UNFUSED = 0x10000
+AO_PACKED_TILES = 0x20000
+
+
+def probe_read_gbs(nbytes, iters=10, device=None):
+    """Measured streaming-read bandwidth (GB/s) over nbytes of device memory: L2 roof for <= 64 MB, HBM for >= 1 GB."""
+    if device is not None:
+        _check(lib().nrt_set_device(int(device)))
+    v = C.c_double(0.0)
+    _check(lib().nrt_probe_read_gbs(int(nbytes), int(iters), C.byref(v)))
+    return v.value
+
+
+def probe_copy_gbs(nbytes, direction, iters=5, device=None):
+    """Measured pinned host<->device copy rate (GB/s); direction 0 = H2D, 1 = D2H."""
+    if device is not None:
+        _check(lib().nrt_set_device(int(device)))
+    v = C.c_double(0.0)
+    _check(lib().nrt_probe_copy_gbs(int(nbytes), int(iters), int(direction), C.byref(v)))
+    return v.value
+
+
+class Comm:
+    """Multi-GPU communicator of the C-ABI (nrt_comm_*): one per process / GPU, NCCL underneath (bound at run time)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().nrt_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int | None = None):
+        assert len(unique_id) == 128
+        if device is not None:
+            _check(lib().nrt_set_device(int(device)))
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(lib().nrt_comm_init(C.cast(buf, C.c_void_p), int(rank), int(world), C.byref(h)))
+        self._h, self.rank, self.world = h, rank, world
+
+    def free(self):
+        if self._h:
+            lib().nrt_comm_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def RenderAO(self, accel, params: AoParams, d_frame_full_ptr, stream=None, want_result=True):
+        """nrt_render_ao_sharded: this rank's tiles + framebuffer all-gather; every rank's d_frame_full holds the frame."""
+        res = AoResult()
+        _check(lib().nrt_render_ao_sharded(accel._h, self._h, C.byref(params), C.c_void_p(d_frame_full_ptr),
+                                           C.byref(res) if want_result else None, C.c_void_p(stream) if stream else None))
+        return res if want_result else None
 
 
 class PinnedArray:

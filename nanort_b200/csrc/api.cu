@@ -40,13 +40,15 @@ int select_device(int *device_out) {
 
 static void destroy(Accel *a) {
   if (!a) return;
-  cudaSetDevice(a->device);
+  DeviceGuard dg(a->device);
   cudaFree(a->d_nodes);
   cudaFree(a->d_indices);
   cudaFree(a->d_verts);
   cudaFree(a->d_faces);
   cudaFree(a->d_wide);
   cudaFree(a->d_tris);
+  cudaFree(a->d_pair);
+  cudaFree(a->d_tris_cm);
   cudaFree(a->d_wave);
   cudaFree(a->d_counters);
   for (int i = 0; i < 3; i++) {
@@ -59,8 +61,12 @@ static void destroy(Accel *a) {
 }
 
 // Uploads geometry as tightly packed float3 vertices + faces.
+// Stream-ordered on a->streams[0], the (non-blocking) stream every build / layout kernel of this accel runs on: a
+// synchronous cudaMemcpy from pageable memory on the NULL stream may return before its DMA has finished, and
+// non-blocking streams do not order after the NULL stream.
 static int upload_geometry(Accel *a, const float *verts, size_t stride, size_t n_verts, const uint32_t *faces,
                            uint32_t n_prims) {
+  cudaStream_t s = a->streams[0];
   if (n_verts == 0) {
     uint32_t m = 0;
     const size_t cnt = (size_t)n_prims * 3;
@@ -72,12 +78,105 @@ static int upload_geometry(Accel *a, const float *verts, size_t stride, size_t n
   NRT_CUDA(cudaMalloc(&a->d_verts, sizeof(float) * 3 * n_verts));
   NRT_CUDA(cudaMalloc(&a->d_faces, sizeof(uint32_t) * 3 * (size_t)n_prims));
   if (stride == 12) {
-    NRT_CUDA(cudaMemcpy(a->d_verts, verts, sizeof(float) * 3 * n_verts, cudaMemcpyHostToDevice));
+    NRT_CUDA(cudaMemcpyAsync(a->d_verts, verts, sizeof(float) * 3 * n_verts, cudaMemcpyHostToDevice, s));
   } else {
-    NRT_CUDA(cudaMemcpy2D(a->d_verts, 12, verts, stride, 12, n_verts, cudaMemcpyHostToDevice));
+    NRT_CUDA(cudaMemcpy2DAsync(a->d_verts, 12, verts, stride, 12, n_verts, cudaMemcpyHostToDevice, s));
   }
-  NRT_CUDA(cudaMemcpy(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice));
+  NRT_CUDA(cudaMemcpyAsync(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice, s));
+  NRT_CUDA(cudaStreamSynchronize(s));  // the caller's buffers are borrowed only for the duration of the call
   return NRT_OK;
+}
+
+}  // namespace nrt
+
+// Structure check of a nanort-layout tree that did not come from our builders (nrt_adopt, BVHAccel::Load).  Accepts
+// exactly what the reference's Build can emit and the kernels rely on:
+//   * every node is reached exactly once from node 0 (a tree, not a DAG: a shared child would also make this walk
+//     exponential), children lie behind their parent, axis in 0..2, flag in {0, 1};
+//   * the non-empty leaves' ranges [first, first + count) partition [0, n_indices) exactly -- the private layout marks
+//     the LAST triangle of a leaf, so overlapping leaves would end early at a foreign mark and skip primitives;
+//   * indices address existing primitives; depth <= 500 (512-entry traversal stacks, kNANORT_MAX_STACK_DEPTH).
+// Leaves with count == 0 are legal (min_leaf_primitives == 0 produces them); the layout gives them an inverted box.
+template <class NodeT>
+static bool validate_foreign_tree_t(const NodeT *hn, size_t n_nodes, const uint32_t *indices, size_t n_indices,
+                                    uint32_t n_prims, nrt::BuildStats16 *stats, std::string *why) {
+  *stats = nrt::BuildStats16{0, 0, 0, 0.0f};
+  std::vector<uint8_t> seen(n_nodes, 0);
+  std::vector<std::pair<uint32_t, uint32_t> > stack;  // (node, depth)
+  std::vector<std::pair<uint32_t, uint32_t> > ranges;
+  stack.push_back(std::make_pair(0u, 0u));
+  seen[0] = 1;
+  while (!stack.empty()) {
+    const uint32_t i = stack.back().first, d = stack.back().second;
+    stack.pop_back();
+    const NodeT &nd = hn[i];
+    stats->max_tree_depth = std::max(stats->max_tree_depth, d);
+    if (d > 500) {
+      *why = "tree deeper than 500 levels (512-entry traversal stack, as the reference's)";
+      return false;
+    }
+    if (nd.flag == 0) {
+      stats->num_branch_nodes++;
+      const uint32_t c0 = nd.data[0], c1 = nd.data[1];
+      if (c0 >= n_nodes || c1 >= n_nodes || c0 <= i || c1 <= i || c0 == c1 || nd.axis < 0 || nd.axis > 2) {
+        *why = "branch node with invalid children / axis";
+        return false;
+      }
+      if (seen[c0] || seen[c1]) {
+        *why = "node reachable twice (the array is not a tree)";
+        return false;
+      }
+      seen[c0] = seen[c1] = 1;
+      stack.push_back(std::make_pair(c0, d + 1));
+      stack.push_back(std::make_pair(c1, d + 1));
+    } else if (nd.flag == 1) {
+      stats->num_leaf_nodes++;
+      if ((size_t)nd.data[1] + nd.data[0] > n_indices) {
+        *why = "leaf range outside indices";
+        return false;
+      }
+      if (nd.data[0] > 0) ranges.push_back(std::make_pair(nd.data[1], nd.data[0]));
+    } else {
+      *why = "node flag is neither 0 (branch) nor 1 (leaf)";
+      return false;
+    }
+  }
+  std::sort(ranges.begin(), ranges.end());
+  size_t next = 0;
+  for (size_t k = 0; k < ranges.size(); k++) {
+    if (ranges[k].first != next) {
+      *why = "leaf ranges do not partition indices (gap or overlap)";
+      return false;
+    }
+    next += ranges[k].second;
+  }
+  if (next != n_indices) {
+    *why = "leaf ranges do not cover indices";
+    return false;
+  }
+  for (size_t i = 0; i < n_indices; i++) {
+    if (indices[i] >= n_prims) {
+      *why = "index outside primitives";
+      return false;
+    }
+  }
+  return true;
+}
+
+namespace nrt {
+bool validate_foreign_tree(const Node40 *hn, size_t n_nodes, const uint32_t *indices, size_t n_indices,
+                           uint32_t n_prims, BuildStats16 *stats, std::string *why) {
+  return validate_foreign_tree_t(hn, n_nodes, indices, n_indices, n_prims, stats, why);
+}
+bool validate_foreign_tree64(const void *nodes_64B, size_t n_nodes, const uint32_t *indices, size_t n_indices,
+                             uint32_t n_prims, BuildStats16 *stats, std::string *why) {
+  struct Node64 {
+    double bmin[3], bmax[3];
+    int32_t flag, axis;
+    uint32_t data[2];
+  };
+  static_assert(sizeof(Node64) == 64, "BVHNode<double> layout");
+  return validate_foreign_tree_t(static_cast<const Node64 *>(nodes_64B), n_nodes, indices, n_indices, n_prims, stats, why);
 }
 
 static int common_init(Accel *a) {
@@ -152,6 +251,7 @@ int nrt_build_ex(const float *verts, size_t stride_bytes, size_t n_verts, const 
     g_err = "nrt_build: bad geometry pointers / stride";
     return NRT_ERR_INVALID;
   }
+  DeviceGuard dg_caller;  // select_device makes the chosen device current; the caller gets its own back
   int rc = select_device(nullptr);
   if (rc != NRT_OK) return rc;
   Accel *a = new (std::nothrow) Accel();
@@ -197,52 +297,18 @@ int nrt_adopt(const void *nodes_40B, size_t n_nodes, const uint32_t *indices, si
     g_err = "nrt_adopt: bad arguments";
     return NRT_ERR_INVALID;
   }
+  DeviceGuard dg_caller;  // select_device makes the chosen device current; the caller gets its own back
   int rc = select_device(nullptr);
   if (rc != NRT_OK) return rc;
   Accel *a = new (std::nothrow) Accel();
   if (!a) return NRT_ERR_NOMEM;
   a->options = default_build_options();
   const Node40 *hn = static_cast<const Node40 *>(nodes_40B);
-  // validate child / leaf ranges once on the host (an adopted tree is foreign data) and take statistics
-  a->stats = BuildStats16{0, 0, 0, 0.0f};
+  // An adopted tree is foreign data (a dump file): validate it once on the host before any kernel trusts it.
   {
-    std::vector<uint32_t> depth(n_nodes, 0);
-    std::vector<uint32_t> stack;
-    stack.push_back(0);
-    while (!stack.empty()) {
-      uint32_t i = stack.back();
-      stack.pop_back();
-      const Node40 &nd = hn[i];
-      a->stats.max_tree_depth = std::max(a->stats.max_tree_depth, depth[i]);
-      if (nd.flag == 0) {
-        a->stats.num_branch_nodes++;
-        if (nd.data[0] >= n_nodes || nd.data[1] >= n_nodes || nd.data[0] <= i || nd.data[1] <= i ||
-            nd.axis < 0 || nd.axis > 2) {
-          g_err = "nrt_adopt: branch node with invalid children / axis";
-          delete a;
-          return NRT_ERR_INVALID;
-        }
-        depth[nd.data[0]] = depth[nd.data[1]] = depth[i] + 1;
-        stack.push_back(nd.data[0]);
-        stack.push_back(nd.data[1]);
-      } else {
-        a->stats.num_leaf_nodes++;
-        if ((size_t)nd.data[1] + nd.data[0] > n_indices) {
-          g_err = "nrt_adopt: leaf range outside indices";
-          delete a;
-          return NRT_ERR_INVALID;
-        }
-      }
-    }
-  }
-  if (a->stats.max_tree_depth > 500) {
-    g_err = "nrt_adopt: tree deeper than 500 levels (512-entry traversal stack, as the reference's)";
-    delete a;
-    return NRT_ERR_INVALID;
-  }
-  for (size_t i = 0; i < n_indices; i++) {
-    if (indices[i] >= n_prims) {
-      g_err = "nrt_adopt: index outside primitives";
+    std::string why;
+    if (!validate_foreign_tree(hn, n_nodes, indices, n_indices, n_prims, &a->stats, &why)) {
+      g_err = "nrt_adopt: " + why;
       delete a;
       return NRT_ERR_INVALID;
     }
@@ -253,8 +319,11 @@ int nrt_adopt(const void *nodes_40B, size_t n_nodes, const uint32_t *indices, si
     a->n_nodes = n_nodes;
     cudaError_t e = cudaMalloc(&a->d_nodes, sizeof(Node40) * n_nodes);
     if (e == cudaSuccess) e = cudaMalloc(&a->d_indices, sizeof(uint32_t) * n_indices);
-    if (e == cudaSuccess) e = cudaMemcpy(a->d_nodes, hn, sizeof(Node40) * n_nodes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(a->d_indices, indices, sizeof(uint32_t) * n_indices, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(a->d_nodes, hn, sizeof(Node40) * n_nodes, cudaMemcpyHostToDevice, a->streams[0]);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(a->d_indices, indices, sizeof(uint32_t) * n_indices, cudaMemcpyHostToDevice, a->streams[0]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(a->streams[0]);
     if (e != cudaSuccess) rc = cuda_fail(e, "nrt_adopt upload", __FILE__, __LINE__);
   }
   if (rc == NRT_OK) rc = derive_private_layout(a, a->streams[0]);
@@ -304,7 +373,7 @@ int nrt_nodes(nrt_accel *h, const void **nodes_40B, size_t *n_nodes, const uint3
   }
   Accel *a = reinterpret_cast<Accel *>(h);
   if (!a->mirrors_valid) {
-    NRT_CUDA(cudaSetDevice(a->device));
+    NRT_DEVICE(a->device);
     a->h_nodes.resize(a->n_nodes);
     a->h_indices.resize(a->n_prims);
     NRT_CUDA(cudaMemcpy(a->h_nodes.data(), a->d_nodes, sizeof(Node40) * a->n_nodes, cudaMemcpyDeviceToHost));
@@ -327,7 +396,7 @@ int nrt_traverse_device(const nrt_accel *h, const void *d_rays_36B, size_t n_ray
   const Accel *a = reinterpret_cast<const Accel *>(h);
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
-  NRT_CUDA(cudaSetDevice(a->device));
+  NRT_DEVICE(a->device);
   return launch_traverse(a, static_cast<const Ray36 *>(d_rays_36B), n_rays, static_cast<Hit16 *>(d_hits_16B),
                          d_hit_mask, opt, flags, static_cast<cudaStream_t>(stream));
 }
@@ -341,7 +410,8 @@ int nrt_traverse_count_device(const nrt_accel *h, const void *d_rays_36B, size_t
   const Accel *a = reinterpret_cast<const Accel *>(h);
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
-  NRT_CUDA(cudaSetDevice(a->device));
+  NRT_DEVICE(a->device);
+  std::lock_guard<std::mutex> lock(const_cast<Accel *>(a)->host_mu);  // d_counters[8..9] is per-accel scratch
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint64_t *d_counts = a->d_counters + 8;
   int rc = launch_traverse_count(a, static_cast<const Ray36 *>(d_rays_36B), n_rays, opt, flags, d_counts, s);
@@ -367,7 +437,7 @@ int nrt_traverse(const nrt_accel *h, const void *rays_36B, size_t n_rays, void *
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
   std::lock_guard<std::mutex> lock(a->host_mu);
-  NRT_CUDA(cudaSetDevice(a->device));
+  NRT_DEVICE(a->device);
   const size_t kChunk = (size_t)1 << 20;  // 1 Mi rays = 36 MiB up, 17 MiB down per chunk
   size_t chunk = std::min(n_rays, kChunk);
   int rc = ensure_staging(a, std::max(chunk, a->stage_rays));
@@ -377,24 +447,32 @@ int nrt_traverse(const nrt_accel *h, const void *rays_36B, size_t n_rays, void *
   char *dst = static_cast<char *>(hits_16B);
   size_t done = 0;
   int slot = 0;
-  while (done < n_rays) {
+  cudaError_t e = cudaSuccess;
+  while (done < n_rays && rc == NRT_OK && e == cudaSuccess) {
     size_t m = std::min(chunk, n_rays - done);
     cudaStream_t s = a->streams[slot];
     // the slot's previous chunk (3 iterations ago) must have drained before its buffers are reused
-    NRT_CUDA(cudaStreamSynchronize(s));
-    NRT_CUDA(cudaMemcpyAsync(a->d_stage_rays[slot], src + done * sizeof(Ray36), m * sizeof(Ray36),
-                             cudaMemcpyHostToDevice, s));
+    e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(a->d_stage_rays[slot], src + done * sizeof(Ray36), m * sizeof(Ray36), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) break;
     rc = launch_traverse(a, static_cast<const Ray36 *>(a->d_stage_rays[slot]), m,
                          static_cast<Hit16 *>(a->d_stage_hits[slot]),
                          hit_mask ? static_cast<uint8_t *>(a->d_stage_mask[slot]) : nullptr, opt, flags, s);
-    if (rc != NRT_OK) return rc;
-    NRT_CUDA(cudaMemcpyAsync(dst + done * sizeof(Hit16), a->d_stage_hits[slot], m * sizeof(Hit16),
-                             cudaMemcpyDeviceToHost, s));
-    if (hit_mask) NRT_CUDA(cudaMemcpyAsync(hit_mask + done, a->d_stage_mask[slot], m, cudaMemcpyDeviceToHost, s));
+    if (rc != NRT_OK) break;
+    e = cudaMemcpyAsync(dst + done * sizeof(Hit16), a->d_stage_hits[slot], m * sizeof(Hit16), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && hit_mask)
+      e = cudaMemcpyAsync(hit_mask + done, a->d_stage_mask[slot], m, cudaMemcpyDeviceToHost, s);
     done += m;
     slot = (slot + 1) % 3;
   }
-  for (int i = 0; i < 3; i++) NRT_CUDA(cudaStreamSynchronize(a->streams[i]));
+  // success or not, nothing may still be writing into the caller's buffers when this call returns
+  for (int i = 0; i < 3; i++) {
+    const cudaError_t es = cudaStreamSynchronize(a->streams[i]);
+    if (e == cudaSuccess) e = es;
+  }
+  if (rc != NRT_OK) return rc;
+  NRT_CUDA(e);
   return NRT_OK;
 }
 

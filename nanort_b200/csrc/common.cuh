@@ -85,6 +85,28 @@ struct PackedTri {
 };
 static_assert(sizeof(PackedTri) == 48, "PackedTri");
 
+// ---- round-2 traversal layout (traverse_fast3_kernel) ------------------------------------------------------
+// PairNode, 128 bytes = one L1 line, one per BRANCH node, both child boxes.  Every axis owns one 32-byte sector that
+// holds the four planes of that axis in BOTH orders,
+//   sector x = { lo0 lo1 hi0 hi1 | hi0 hi1 lo0 lo1 }     (y, z alike)
+// so a ray loads ONE aligned float4 per axis at byte offset (dir_sign ? 16 : 0) and finds {near0 near1 far0 far1}
+// in fixed registers: the reference's `ray_dir_sign ? bmax : bmin` selection (nanort.h:2291-2302) becomes address
+// arithmetic done once per ray instead of 12 selects per visited pair.  Sector 3 = {ref0, ref1, axis, 0, ...}.
+struct PairNode {
+  float4 x[2], y[2], z[2];
+  int4 r, pad;
+};
+static_assert(sizeof(PairNode) == 128, "PairNode");
+
+// TriCM, 48 bytes, component-major packed triangle in leaf order:
+//   X = {a.x b.x c.x w}  Y = {a.y b.y c.y w}  Z = {a.z b.z c.z w},  w = prim_id | last_in_leaf << 31 (in all three)
+// The watertight test permutes the components by the ray's (kx, ky, kz) (nanort.h:1073-1081); with this layout the
+// permutation is again an address: the ray loads the float4 at byte offset 16 * k and needs no selects.
+struct TriCM {
+  float4 X, Y, Z;
+};
+static_assert(sizeof(TriCM) == 48, "TriCM");
+
 // ---- accel object ----------------------------------------------------------------
 struct Accel {
   int device = 0;
@@ -105,6 +127,8 @@ struct Accel {
   // device: private traversal layout
   WideNode *d_wide = nullptr;
   PackedTri *d_tris = nullptr;
+  PairNode *d_pair = nullptr;  // same indices and refs as d_wide
+  TriCM *d_tris_cm = nullptr;  // same slots as d_tris
   // host mirrors (lazy)
   std::vector<Node40> h_nodes;
   std::vector<uint32_t> h_indices;
@@ -138,6 +162,36 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     cudaError_t _e = (expr);                                               \
     if (_e != cudaSuccess) return nrt::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
+
+// Every entry point makes the accel's device current for its own duration only and puts the caller's device back:
+// a host that drives several GPUs from one thread (or torch, whose current_device() is cudaGetDevice) must not find
+// its current device switched by a library call -- nrt_free from a garbage collector included.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  DeviceGuard() {  // only remembers the caller's device (for entry points that select one themselves)
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      prev = -1;
+      cudaGetLastError();
+    }
+  }
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      prev = -1;
+      cudaGetLastError();
+    }
+    if (prev != device) err = cudaSetDevice(device);
+    if (prev == device) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define NRT_DEVICE(dev)            \
+  nrt::DeviceGuard _nrt_dg((dev)); \
+  NRT_CUDA(_nrt_dg.err)
 
 inline TraceOptions16 default_trace_options() {
   TraceOptions16 o;
@@ -179,6 +233,11 @@ int build_on_device(Accel *a, cudaStream_t s);
 int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s);
 
 int device_sm_count(int device);
+// api.cu: structure check of a foreign nanort-layout tree (see there); fills the statistics
+bool validate_foreign_tree(const Node40 *nodes, size_t n_nodes, const uint32_t *indices, size_t n_indices,
+                           uint32_t n_prims, BuildStats16 *stats, std::string *why);
+bool validate_foreign_tree64(const void *nodes_64B, size_t n_nodes, const uint32_t *indices, size_t n_indices,
+                             uint32_t n_prims, BuildStats16 *stats, std::string *why);
 // api.cu: makes the calling thread's selected device current (nrt_set_device); NRT_ERR_CUDA without a usable device
 int select_device(int *device_out);
 

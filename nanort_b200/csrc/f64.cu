@@ -70,7 +70,7 @@ struct AccelF64 {
 
 void destroy_f64(AccelF64 *a) {
   if (!a) return;
-  cudaSetDevice(a->device);
+  DeviceGuard dg(a->device);
   cudaFree(a->d_nodes);
   cudaFree(a->d_indices);
   cudaFree(a->d_faces);
@@ -361,6 +361,7 @@ int nrt_build_f64(const double *verts, size_t stride_bytes, size_t n_verts, cons
     return NRT_ERR_INVALID;
   }
   int device = 0;
+  DeviceGuard dg_caller;  // select_device makes the chosen device current; the caller gets its own back
   int rc = select_device(&device);
   if (rc != NRT_OK) return rc;
   if (n_verts == 0) {
@@ -389,8 +390,10 @@ int nrt_build_f64(const double *verts, size_t stride_bytes, size_t n_verts, cons
     F64_CUDA(cudaMalloc(&a->d_verts, sizeof(double) * 3 * n_verts));
     F64_CUDA(cudaMalloc(&a->d_faces, sizeof(uint32_t) * 3 * (size_t)n_prims));
     F64_CUDA(cudaMalloc(&t->d_verts, sizeof(float) * 3 * n_verts));
-    F64_CUDA(cudaMemcpy(a->d_verts, packed.data(), sizeof(double) * 3 * n_verts, cudaMemcpyHostToDevice));
-    F64_CUDA(cudaMemcpy(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice));
+    // stream-ordered with the kernels that consume them (a->stream is non-blocking, see api.cu:upload_geometry)
+    F64_CUDA(cudaMemcpyAsync(a->d_verts, packed.data(), sizeof(double) * 3 * n_verts, cudaMemcpyHostToDevice, a->stream));
+    F64_CUDA(cudaMemcpyAsync(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice, a->stream));
+    F64_CUDA(cudaStreamSynchronize(a->stream));
   }
   t->d_faces = a->d_faces;  // shared, freed with `a`
   t->options = default_build_options();
@@ -458,42 +461,15 @@ int nrt_adopt_f64(const void *nodes_64B, size_t n_nodes, const uint32_t *indices
   }
   const Node64 *hn = static_cast<const Node64 *>(nodes_64B);
   BuildStats16 st = {0, 0, 0, 0.0f};
-  {  // an adopted tree is foreign data: validate child / leaf ranges once on the host, take the statistics
-    std::vector<uint32_t> depth(n_nodes, 0), stack(1, 0u);
-    while (!stack.empty()) {
-      const uint32_t i = stack.back();
-      stack.pop_back();
-      const Node64 &nd = hn[i];
-      st.max_tree_depth = std::max(st.max_tree_depth, depth[i]);
-      if (nd.flag == 0) {
-        st.num_branch_nodes++;
-        if (nd.data[0] >= n_nodes || nd.data[1] >= n_nodes || nd.data[0] <= i || nd.data[1] <= i || nd.axis < 0 ||
-            nd.axis > 2) {
-          set_error("nrt_adopt_f64: branch node with invalid children / axis");
-          return NRT_ERR_INVALID;
-        }
-        depth[nd.data[0]] = depth[nd.data[1]] = depth[i] + 1;
-        stack.push_back(nd.data[0]);
-        stack.push_back(nd.data[1]);
-      } else {
-        st.num_leaf_nodes++;
-        if ((size_t)nd.data[1] + nd.data[0] > n_indices) {
-          set_error("nrt_adopt_f64: leaf range outside indices");
-          return NRT_ERR_INVALID;
-        }
-      }
-    }
-  }
-  if (st.max_tree_depth > 500) {
-    set_error("nrt_adopt_f64: tree deeper than 500 levels (512-entry traversal stack, as the reference's)");
-    return NRT_ERR_INVALID;
-  }
-  for (size_t i = 0; i < n_indices; i++)
-    if (indices[i] >= n_prims) {
-      set_error("nrt_adopt_f64: index outside primitives");
+  {  // an adopted tree is foreign data: the same structure check as nrt_adopt (api.cu:validate_foreign_tree)
+    std::string why;
+    if (!validate_foreign_tree64(nodes_64B, n_nodes, indices, n_indices, n_prims, &st, &why)) {
+      set_error("nrt_adopt_f64: " + why);
       return NRT_ERR_INVALID;
     }
+  }
   int device = 0;
+  DeviceGuard dg_caller;  // select_device makes the chosen device current; the caller gets its own back
   int rc = select_device(&device);
   if (rc != NRT_OK) return rc;
   if (n_verts == 0) {
@@ -518,10 +494,14 @@ int nrt_adopt_f64(const void *nodes_64B, size_t n_nodes, const uint32_t *indices
   if (e == cudaSuccess) e = cudaMalloc(&a->d_faces, sizeof(uint32_t) * 3 * (size_t)n_prims);
   if (e == cudaSuccess) e = cudaMalloc(&a->d_nodes, sizeof(Node64) * n_nodes);
   if (e == cudaSuccess) e = cudaMalloc(&a->d_indices, sizeof(uint32_t) * n_indices);
-  if (e == cudaSuccess) e = cudaMemcpy(a->d_verts, packed.data(), sizeof(double) * 3 * n_verts, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(a->d_nodes, hn, sizeof(Node64) * n_nodes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(a->d_indices, indices, sizeof(uint32_t) * n_indices, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(a->d_verts, packed.data(), sizeof(double) * 3 * n_verts, cudaMemcpyHostToDevice, a->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice, a->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(a->d_nodes, hn, sizeof(Node64) * n_nodes, cudaMemcpyHostToDevice, a->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(a->d_indices, indices, sizeof(uint32_t) * n_indices, cudaMemcpyHostToDevice, a->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(a->stream);
   if (e != cudaSuccess) {
     rc = cuda_fail(e, "nrt_adopt_f64 upload", __FILE__, __LINE__);
     destroy_f64(a);
@@ -571,7 +551,7 @@ int nrt_nodes_f64(nrt_accel_f64 *h, const void **nodes_64B, size_t *n_nodes, con
   AccelF64 *a = reinterpret_cast<AccelF64 *>(h);
   std::lock_guard<std::mutex> lock(a->mu);
   if (!a->mirrors_valid) {
-    NRT_CUDA(cudaSetDevice(a->device));
+    NRT_DEVICE(a->device);
     a->h_nodes.resize(a->n_nodes);
     a->h_indices.resize(a->n_prims);
     NRT_CUDA(cudaMemcpy(a->h_nodes.data(), a->d_nodes, sizeof(Node64) * a->n_nodes, cudaMemcpyDeviceToHost));
@@ -596,7 +576,7 @@ int nrt_traverse_f64(const nrt_accel_f64 *h, const void *rays_72B, size_t n_rays
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
   std::lock_guard<std::mutex> lock(a->mu);  // Traverse is const and thread-safe in the reference; staging is shared
-  NRT_CUDA(cudaSetDevice(a->device));
+  NRT_DEVICE(a->device);
   const size_t chunk = std::min(n_rays, (size_t)1 << 20);
   if (a->stage < chunk) {
     cudaFree(a->d_rays);

@@ -51,6 +51,13 @@ __device__ __forceinline__ int child_ref(const Node40 &c, uint32_t cidx, const u
   return ~(int)c.data[1];
 }
 
+__device__ __forceinline__ void invert_box(Node40 &c) {
+  for (int k = 0; k < 3; k++) {
+    c.bmin[k] = 3.402823466e38f;
+    c.bmax[k] = -3.402823466e38f;
+  }
+}
+
 __global__ void wide_nodes_kernel(const Node40 *__restrict__ nodes, uint32_t n, const uint32_t *__restrict__ widx,
                                   WideNode *__restrict__ wide, PackedTri *__restrict__ tris) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,6 +82,10 @@ __global__ void wide_nodes_kernel(const Node40 *__restrict__ nodes, uint32_t n, 
     return;
   }
   Node40 c0 = nodes[nd.data[0]], c1 = nodes[nd.data[1]];
+  // a child leaf without primitives (reference trees built with min_leaf_primitives == 0 contain them) carries an
+  // inverted box: it can never pass the slab test, so no kernel ever has to follow an empty reference
+  if (c0.flag != 0 && c0.data[0] == 0) invert_box(c0);
+  if (c1.flag != 0 && c1.data[0] == 0) invert_box(c1);
   WideNode w;
   w.q0 = make_float4(c0.bmin[0], c0.bmin[1], c0.bmin[2], c0.bmax[0]);
   w.q1 = make_float4(c0.bmax[1], c0.bmax[2], c1.bmin[0], c1.bmin[1]);
@@ -127,20 +138,57 @@ __global__ void remap_wide_kernel(const WideNode *__restrict__ in, const uint32_
   out[new_idx[i]] = w;
 }
 
+// ---- round-2 layout: PairNode (sign-addressed planes) and TriCM (component-major triangles), derived from the
+// final WideNode / PackedTri arrays so that indices, refs and slots are shared by every kernel
+__global__ void pair_from_wide_kernel(const WideNode *__restrict__ wide, uint32_t n, PairNode *__restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const WideNode w = wide[i];
+  // WideNode: q0 = c0.lo.xyz, c0.hi.x | q1 = c0.hi.yz, c1.lo.xy | q2 = c1.lo.z, c1.hi.xyz
+  const float lo0x = w.q0.x, lo0y = w.q0.y, lo0z = w.q0.z, hi0x = w.q0.w, hi0y = w.q1.x, hi0z = w.q1.y;
+  const float lo1x = w.q1.z, lo1y = w.q1.w, lo1z = w.q2.x, hi1x = w.q2.y, hi1y = w.q2.z, hi1z = w.q2.w;
+  PairNode p;
+  p.x[0] = make_float4(lo0x, lo1x, hi0x, hi1x);
+  p.x[1] = make_float4(hi0x, hi1x, lo0x, lo1x);
+  p.y[0] = make_float4(lo0y, lo1y, hi0y, hi1y);
+  p.y[1] = make_float4(hi0y, hi1y, lo0y, lo1y);
+  p.z[0] = make_float4(lo0z, lo1z, hi0z, hi1z);
+  p.z[1] = make_float4(hi0z, hi1z, lo0z, lo1z);
+  p.r = w.q3;
+  p.pad = make_int4(0, 0, 0, 0);
+  out[i] = p;
+}
+
+__global__ void tris_cm_kernel(const PackedTri *__restrict__ in, uint32_t n, TriCM *__restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PackedTri t = in[i];
+  const uint32_t w = (__float_as_uint(t.a.w) & 0x7FFFFFFFu) | (__float_as_uint(t.b.w) != 0u ? 0x80000000u : 0u);
+  const float wf = __uint_as_float(w);
+  TriCM o;
+  o.X = make_float4(t.a.x, t.b.x, t.c.x, wf);
+  o.Y = make_float4(t.a.y, t.b.y, t.c.y, wf);
+  o.Z = make_float4(t.a.z, t.b.z, t.c.z, wf);
+  out[i] = o;
+}
+
 static int reorder_top_treelet(Accel *a, cudaStream_t s) {
   const uint32_t n = (uint32_t)a->n_wide;
   uint32_t *d_new = nullptr, *d_not = nullptr, *d_rank = nullptr, *d_ntop = nullptr;
   WideNode *d_out = nullptr;
-  NRT_CUDA(cudaMalloc(&d_new, sizeof(uint32_t) * (size_t)n));
-  NRT_CUDA(cudaMalloc(&d_not, sizeof(uint32_t) * (size_t)n));
-  NRT_CUDA(cudaMalloc(&d_rank, sizeof(uint32_t) * (size_t)n));
-  NRT_CUDA(cudaMalloc(&d_ntop, sizeof(uint32_t)));
-  NRT_CUDA(cudaMalloc(&d_out, sizeof(WideNode) * (size_t)n));
-  fill_u32_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_not, n, 1u);
-  bfs_top_kernel<<<1, 32, 0, s>>>(a->d_wide, n, d_new, d_not, d_ntop);
-  NRT_CUDA(cudaGetLastError());
+  cudaError_t ea = cudaMalloc(&d_new, sizeof(uint32_t) * (size_t)n);
+  if (ea == cudaSuccess) ea = cudaMalloc(&d_not, sizeof(uint32_t) * (size_t)n);
+  if (ea == cudaSuccess) ea = cudaMalloc(&d_rank, sizeof(uint32_t) * (size_t)n);
+  if (ea == cudaSuccess) ea = cudaMalloc(&d_ntop, sizeof(uint32_t));
+  if (ea == cudaSuccess) ea = cudaMalloc(&d_out, sizeof(WideNode) * (size_t)n);
+  if (ea == cudaSuccess) {
+    fill_u32_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_not, n, 1u);
+    bfs_top_kernel<<<1, 32, 0, s>>>(a->d_wide, n, d_new, d_not, d_ntop);
+    ea = cudaGetLastError();
+  }
   uint32_t n_rest = 0;
-  int rc = exclusive_scan_u32(d_not, d_rank, n, &n_rest, s);
+  int rc = ea == cudaSuccess ? exclusive_scan_u32(d_not, d_rank, n, &n_rest, s)
+                             : cuda_fail(ea, "reorder_top_treelet", __FILE__, __LINE__);
   if (rc == NRT_OK) {
     finish_new_idx_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_not, d_rank, d_ntop, n, d_new);
     remap_wide_kernel<<<(n + 255) / 256, 256, 0, s>>>(a->d_wide, d_new, n, d_out);
@@ -168,10 +216,14 @@ static int reorder_top_treelet(Accel *a, cudaStream_t s) {
 int derive_private_layout(Accel *a, cudaStream_t s) {
   const uint32_t n_nodes = (uint32_t)a->n_nodes;
   const uint32_t n_prims = a->n_prims;
-  if (a->d_tris) cudaFree(a->d_tris);
-  if (a->d_wide) cudaFree(a->d_wide);
+  cudaFree(a->d_tris);
+  cudaFree(a->d_wide);
+  cudaFree(a->d_pair);
+  cudaFree(a->d_tris_cm);
   a->d_tris = nullptr;
   a->d_wide = nullptr;
+  a->d_pair = nullptr;
+  a->d_tris_cm = nullptr;
   NRT_CUDA(cudaMalloc(&a->d_tris, sizeof(PackedTri) * (size_t)n_prims));
   if (a->d_prim_boxes)
     pack_boxes_kernel<<<(n_prims + 255) / 256, 256, 0, s>>>(a->d_indices, a->d_prim_boxes, n_prims, a->d_tris);
@@ -180,26 +232,38 @@ int derive_private_layout(Accel *a, cudaStream_t s) {
   NRT_CUDA(cudaGetLastError());
 
   uint32_t *d_flags = nullptr, *d_widx = nullptr;
-  NRT_CUDA(cudaMalloc(&d_flags, sizeof(uint32_t) * (size_t)n_nodes));
-  NRT_CUDA(cudaMalloc(&d_widx, sizeof(uint32_t) * (size_t)n_nodes));
-  branch_flags_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(a->d_nodes, n_nodes, d_flags);
-  NRT_CUDA(cudaGetLastError());
   uint32_t n_branch = 0;
-  int rc = exclusive_scan_u32(d_flags, d_widx, n_nodes, &n_branch, s);
-  if (rc != NRT_OK) {
-    cudaFree(d_flags);
-    cudaFree(d_widx);
-    return rc;
+  int rc = NRT_OK;
+  cudaError_t e = cudaMalloc(&d_flags, sizeof(uint32_t) * (size_t)n_nodes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_widx, sizeof(uint32_t) * (size_t)n_nodes);
+  if (e == cudaSuccess) {
+    branch_flags_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(a->d_nodes, n_nodes, d_flags);
+    e = cudaGetLastError();
   }
-  a->n_wide = n_branch > 0 ? n_branch : 1;
-  a->root_is_leaf = (n_branch == 0);
-  NRT_CUDA(cudaMalloc(&a->d_wide, sizeof(WideNode) * a->n_wide));
-  wide_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(a->d_nodes, n_nodes, d_widx, a->d_wide, a->d_tris);
+  if (e == cudaSuccess) rc = exclusive_scan_u32(d_flags, d_widx, n_nodes, &n_branch, s);
+  if (e == cudaSuccess && rc == NRT_OK) {
+    a->n_wide = n_branch > 0 ? n_branch : 1;
+    a->root_is_leaf = (n_branch == 0);
+    e = cudaMalloc(&a->d_wide, sizeof(WideNode) * a->n_wide);
+  }
+  if (e == cudaSuccess && rc == NRT_OK) {
+    wide_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, s>>>(a->d_nodes, n_nodes, d_widx, a->d_wide, a->d_tris);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_flags);  // every path, error or not
+  cudaFree(d_widx);
+  if (e != cudaSuccess) return cuda_fail(e, "derive_private_layout", __FILE__, __LINE__);
+  if (rc != NRT_OK) return rc;
+  rc = reorder_top_treelet(a, s);
+  if (rc != NRT_OK || a->d_prim_boxes) return rc;  // box accels (top level of a scene) are walked by scene.cu only
+  NRT_CUDA(cudaMalloc(&a->d_pair, sizeof(PairNode) * a->n_wide));
+  NRT_CUDA(cudaMalloc(&a->d_tris_cm, sizeof(TriCM) * (size_t)n_prims));
+  pair_from_wide_kernel<<<((uint32_t)a->n_wide + 255) / 256, 256, 0, s>>>(a->d_wide, (uint32_t)a->n_wide, a->d_pair);
+  tris_cm_kernel<<<(n_prims + 255) / 256, 256, 0, s>>>(a->d_tris, n_prims, a->d_tris_cm);
   NRT_CUDA(cudaGetLastError());
   NRT_CUDA(cudaStreamSynchronize(s));
-  cudaFree(d_flags);
-  cudaFree(d_widx);
-  return reorder_top_treelet(a, s);
+  return NRT_OK;
 }
 
 }  // namespace nrt

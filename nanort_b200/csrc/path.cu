@@ -89,7 +89,8 @@ extern "C" int nrt_render_path_device(const nrt_accel *h, const nrt_path_params 
     set_error("nrt_render_path_device: bad parameters");
     return NRT_ERR_INVALID;
   }
-  NRT_CUDA(cudaSetDevice(a->device));
+  NRT_DEVICE(a->device);
+  std::lock_guard<std::mutex> lock(a->host_mu);  // d_wave / d_counters are per-accel scratch (see render.cu)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint32_t tiles_x = (p.width + p.tile_w - 1) / p.tile_w, tiles_y = (p.height + p.tile_h - 1) / p.tile_h;
   const uint32_t n_tiles = tiles_x * tiles_y;

@@ -10,6 +10,8 @@
 //                     nanort has no any-hit, so AO rays do the same full closest-hit work here)
 // Rays live in SoA queues (two float4 per ray); hits are nanort's 16-byte records.
 #include <algorithm>
+#include <mutex>
+#include <string>
 
 #include "common.cuh"
 #include "wavefront.cuh"
@@ -176,7 +178,10 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
     set_error("nrt_render_ao_device: bad parameters (tiles must be multiples of 8x4 pixels)");
     return NRT_ERR_INVALID;
   }
-  NRT_CUDA(cudaSetDevice(a->device));
+  NRT_DEVICE(a->device);
+  // d_wave and d_counters[2..6] are per-accel scratch: concurrent passes on ONE accel are serialised (passes on
+  // different accels, e.g. one per GPU, run concurrently)
+  std::lock_guard<std::mutex> lock(a->host_mu);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint32_t tiles_x = (p.width + p.tile_w - 1) / p.tile_w, tiles_y = (p.height + p.tile_h - 1) / p.tile_h;
   const uint32_t n_tiles = tiles_x * tiles_y;
@@ -233,26 +238,37 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
   uint32_t launches = 0, trav_launches = 0;
   unsigned long long dumped_ao = 0, valid_primaries_host = 0;
   const bool fused = !dump_primary && !dump_ao && !(p.flags & NRT_AO_UNFUSED);
+  if (!fused && (p.flags & NRT_AO_PACKED_TILES)) {
+    set_error("nrt_render_ao_device: NRT_AO_PACKED_TILES needs the fused pass");
+    return NRT_ERR_INVALID;
+  }
   const uint32_t trav_flags = p.flags & 0xFFFFu;
   int rc = NRT_OK;
   for (unsigned long long s0 = 0; s0 < total_slots && rc == NRT_OK; s0 += cap) {
     const uint32_t count = (uint32_t)std::min<unsigned long long>(cap, total_slots - s0);
     const uint32_t grid = (count + 255) / 256;
-    cudaMemsetAsync(wave_ctr, 0, 2 * sizeof(unsigned long long), s);
+    if (cudaMemsetAsync(wave_ctr, 0, 2 * sizeof(unsigned long long), s) != cudaSuccess) {
+      rc = NRT_ERR_CUDA;
+      break;
+    }
     if (!fused) {
       gen_primary_kernel<<<grid, 256, 0, s>>>(p, s0, count, w, wave_ctr);
       launches++;
     }
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
     if (res) {
-      cudaEventCreate(&t0);
-      cudaEventCreate(&t1);
-      cudaEventCreate(&t2);
-      cudaEventCreate(&t3);
-      ev.push_back(t0);
+      cudaError_t ee = cudaEventCreate(&t0);
+      if (ee == cudaSuccess) ee = cudaEventCreate(&t1);
+      if (ee == cudaSuccess) ee = cudaEventCreate(&t2);
+      if (ee == cudaSuccess) ee = cudaEventCreate(&t3);
+      ev.push_back(t0);  // pushed even on failure: the clean-up loop below destroys whatever was created
       ev.push_back(t1);
       ev.push_back(t2);
       ev.push_back(t3);
+      if (ee != cudaSuccess) {
+        rc = cuda_fail(ee, "cudaEventCreate", __FILE__, __LINE__);
+        break;
+      }
     }
     if (fused) {
       // two traversal launches per wave and nothing else: camera rays are generated at ray fetch, the retire
@@ -303,6 +319,8 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
     }
     if (cudaGetLastError() != cudaSuccess) rc = NRT_ERR_CUDA;
   }
+  if (rc != NRT_OK && cudaGetLastError() != cudaSuccess && std::string(nrt_last_error()).empty())
+    set_error("nrt_render_ao_device: CUDA launch failure");
   if (rc == NRT_OK && res) {
     unsigned long long ht[3] = {0, 0, 0};
     cudaEventRecord(e_end, s);
@@ -314,26 +332,37 @@ static int run_ao_pass(const nrt_accel *h, const nrt_ao_params *pp, float *d_acc
       res->ao_rays = ht[0];
       res->ao_hits = ht[1];
       res->primary_rays = ht[2] + valid_primaries_host;
-      float tms = 0.0f, total = 0.0f;
+      float tms = 0.0f, total = 0.0f, tp = 0.0f, ta = 0.0f;
       for (size_t i = 0; i + 3 < ev.size(); i += 4) {
         float m1 = 0, m2 = 0;
         cudaEventElapsedTime(&m1, ev[i], ev[i + 1]);
         cudaEventElapsedTime(&m2, ev[i + 2], ev[i + 3]);
         tms += m1 + m2;
+        tp += m1;
+        ta += m2;
       }
       cudaEventElapsedTime(&total, e_begin, e_end);
       res->traverse_ms = tms;
+      res->primary_traverse_ms = tp;
+      res->ao_traverse_ms = ta;
       res->total_ms = total;
       res->launches = launches;
       res->traverse_launches = trav_launches;
     }
   }
-  for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ev)
+    if (e) cudaEventDestroy(e);
   if (e_begin) cudaEventDestroy(e_begin);
   if (e_end) cudaEventDestroy(e_end);
   if (n_ao_out) *n_ao_out = dumped_ao;
   return rc;
 }
+
+namespace nrt {
+int run_ao_pass_internal(const nrt_accel *h, const nrt_ao_params *pp, float *d_accum, nrt_ao_result *res, void *stream) {
+  return run_ao_pass(h, pp, d_accum, res, stream, nullptr, nullptr, nullptr);
+}
+}  // namespace nrt
 
 extern "C" int nrt_render_ao_device(const nrt_accel *h, const nrt_ao_params *pp, float *d_accum, nrt_ao_result *res,
                                     void *stream) {

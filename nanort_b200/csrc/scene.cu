@@ -770,7 +770,7 @@ struct Scene {
 
 static void scene_destroy(Scene *s) {
   if (!s) return;
-  cudaSetDevice(s->device);
+  DeviceGuard dg(s->device);
   if (s->top) {
     cudaFree(s->top->d_nodes);
     cudaFree(s->top->d_indices);
@@ -908,7 +908,8 @@ int nrt_scene_commit(const nrt_instance *instances, uint32_t n_instances, uint32
     scene_destroy(sc);
     return code;
   };
-  cudaError_t e = cudaSetDevice(sc->device);
+  DeviceGuard dg(sc->device);
+  cudaError_t e = dg.err;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&sc->d_counters, 32 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(sc->d_counters, 0, 32 * sizeof(unsigned long long));
@@ -987,7 +988,7 @@ int nrt_scene_nodes(nrt_scene *s, const void **nodes_40B, size_t *n_nodes, const
   Accel *a = sc->top;
   std::lock_guard<std::mutex> lock(sc->mu);
   if (!a->mirrors_valid) {
-    NRT_CUDA(cudaSetDevice(sc->device));
+    NRT_DEVICE(sc->device);
     a->h_nodes.resize(a->n_nodes);
     a->h_indices.resize(a->n_prims);
     NRT_CUDA(cudaMemcpy(a->h_nodes.data(), a->d_nodes, sizeof(Node40) * a->n_nodes, cudaMemcpyDeviceToHost));
@@ -1007,7 +1008,7 @@ int nrt_scene_instance_state(const nrt_scene *s, uint32_t instance, float out76[
     set_error("nrt_scene_instance_state: bad argument");
     return NRT_ERR_INVALID;
   }
-  NRT_CUDA(cudaSetDevice(sc->device));
+  NRT_DEVICE(sc->device);
   NRT_CUDA(cudaMemcpy(out76, sc->d_state + 76 * (size_t)instance, sizeof(float) * 76, cudaMemcpyDeviceToHost));
   return NRT_OK;
 }
@@ -1019,7 +1020,7 @@ int nrt_scene_traverse_device(const nrt_scene *s, const void *d_rays_36B, size_t
     return NRT_ERR_INVALID;
   }
   Scene *sc = const_cast<Scene *>(reinterpret_cast<const Scene *>(s));
-  NRT_CUDA(cudaSetDevice(sc->device));
+  NRT_DEVICE(sc->device);
   return scene_launch(sc, static_cast<const Ray36 *>(d_rays_36B), n_rays, static_cast<SceneHit32 *>(d_hits_32B),
                       d_hit_mask, flags, static_cast<cudaStream_t>(stream));
 }
@@ -1032,7 +1033,7 @@ int nrt_scene_traverse(const nrt_scene *s, const void *rays_36B, size_t n_rays, 
   }
   if (n_rays == 0) return NRT_OK;
   Scene *sc = const_cast<Scene *>(reinterpret_cast<const Scene *>(s));
-  NRT_CUDA(cudaSetDevice(sc->device));
+  NRT_DEVICE(sc->device);
   const size_t kChunk = (size_t)1 << 20;
   const size_t chunk = std::min(n_rays, kChunk);
   // one caller at a time on the staging buffers (Scene::Traverse is const and thread-safe in the reference)

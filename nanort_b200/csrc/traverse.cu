@@ -16,14 +16,16 @@
 #include "common.cuh"
 #include "trav_common.cuh"
 #include "wavefront.cuh"
+#include "traverse3.cuh"
 
 namespace nrt {
 
 // ------------------------------------------------------------------ ray loaders
 struct AosRays {
+  static constexpr int kPayloadWords = 0;
   const Ray36 *rays;
   __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy,
-                                       float &dz, float &tmin, float &tmax) const {
+                                       float &dz, float &tmin, float &tmax, uint32_t * = nullptr) const {
     const float *p = reinterpret_cast<const float *>(rays + i);
     ox = __ldcs(p + 0);
     oy = __ldcs(p + 1);
@@ -37,10 +39,11 @@ struct AosRays {
 };
 
 struct SoaRays {
+  static constexpr int kPayloadWords = 0;
   const float4 *org_tmin;
   const float4 *dir_tmax;
   __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy,
-                                       float &dz, float &tmin, float &tmax) const {
+                                       float &dz, float &tmin, float &tmax, uint32_t * = nullptr) const {
     float4 o = __ldcs(org_tmin + i);  // read once: evict-first, keep L1/L2 for the tree
     float4 d = __ldcs(dir_tmax + i);
     ox = o.x;
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
 
     // ---- retire: the epilogue (store the hit / spawn the AO ray / accumulate) runs warp-wide
     const bool retiring = ray_idx >= 0 && cur == kNone && leaf == kNone;
-    if (__any_sync(FULL_MASK, retiring)) epi(retiring, (size_t)ray_idx, best.t, best.u, best.v, best.prim, max_t);
+    if (__any_sync(FULL_MASK, retiring)) epi(retiring, (size_t)ray_idx, best.t, best.u, best.v, best.prim, max_t, nullptr);
     if (retiring) ray_idx = -1;
   }
 
@@ -390,28 +393,124 @@ static cudaError_t launch_fast2(const Accel *a, Rays rays, size_t n, Epi epi, co
   return cudaGetLastError();
 }
 
-// Default policy (chosen from the sweeps in profiles/r01_variant_sweep.md): 128-thread CTAs, 10 per SM (48
-// registers), refill when 16 lanes retired, node phase ends below 8 descending lanes, no TMA treelet, and the
-// whole per-lane stack in thread-local memory (L1-backed) -- the shared-memory short stack measured 2-3 % slower
-// because its carve-out takes L1 capacity away from the tree.
-typedef FastPolicy<128, 10, 16, 8, 0, 0> DefaultPolicy;
+// Round-1 policy, kept as experiment variants 100+ (profiles/r01_variant_sweep.md): 128-thread CTAs, 10 per SM
+// (48 registers), refill when 16 lanes retired, node phase ends below 8 descending lanes, no TMA treelet, whole
+// per-lane stack in thread-local memory.
+typedef FastPolicy<128, 10, 16, 8, 0, 0> OldDefaultPolicy;
+// Round-2 defaults (profiles/r02_variant_sweep.md): 128-thread CTAs, 10 per SM (48 registers), refill when 16 lanes
+// retired, node phase ends below 8 descending lanes.  Coherent launches (camera rays, caller-supplied rays) read the
+// 128-byte PairNode (no selects: they are issue bound); incoherent launches (AO, shadow and bounce rays) and trees
+// whose PairNode array would not stay L2-resident read the 64-byte WideNode (they are bound by the L1 data pipe and
+// by cache capacity, and the ALU pipe has room for the 12 selects).
+typedef Policy3<128, 10, 16, 8, true> DefaultPolicy;
+typedef Policy3<128, 10, 16, 8, false> IncoherentPolicy;
+// PairNode arrays above this size are not used (126 MB L2; the triangles want their share)
+constexpr size_t kPair128MaxBytes = (size_t)96 << 20;
+
+static unsigned long long *next_cursor(const Accel *a, cudaStream_t s, cudaError_t *e) {
+  // ring of 32 cursors: launches in flight on different streams never share one.  More than 32 traversal launches
+  // of ONE accel in flight at once would alias; every entry point of this library keeps at most 3.
+  unsigned long long *cursor =
+      reinterpret_cast<unsigned long long *>(a->d_counters) + 16 + (a->cursor_ring.fetch_add(1) & 31u);
+  *e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s);
+  return cursor;
+}
+
+template <class Rays, int DEPTH, bool COUNT, class P, class Epi>
+static cudaError_t launch_fast3(const Accel *a, Rays rays, size_t n, Epi epi, const TraceOptions16 &opt,
+                                uint32_t flags, unsigned long long *cursor, unsigned long long *d_counts,
+                                const unsigned long long *n_ptr, cudaStream_t s) {
+  const int sms = device_sm_count(a->device);
+  const size_t warps_per_block = P::kBlock / 32;
+  size_t grid = (size_t)sms * P::kMinBlocks;  // persistent: every SM holds its full complement of CTAs
+  const size_t need_blocks = ((n + 31) / 32 + warps_per_block - 1) / warps_per_block;
+  if (grid > need_blocks) grid = need_blocks;
+  if (grid == 0) grid = 1;
+  const void *nodes = P::kPair128 ? static_cast<const void *>(a->d_pair) : static_cast<const void *>(a->d_wide);
+  traverse_fast3_kernel<Rays, DEPTH, COUNT, P, Epi><<<(unsigned)grid, P::kBlock, 0, s>>>(
+      nodes, a->d_tris_cm, rays, n, epi, opt, flags, cursor, d_counts, n_ptr);
+  return cudaGetLastError();
+}
+
+// a child pair pushes at most one entry and descends one level: the stack never holds more entries than the tree
+// has levels.  Two instantiations: 64 entries (every tree the production builder emits) and 512 (the reference's
+// kNANORT_MAX_STACK_DEPTH, for adopted trees; nrt_build / nrt_adopt reject deeper ones).
+static bool needs_deep_stack(const Accel *a) { return a->stats.max_tree_depth + 2 > 64u; }
+
+template <class Rays, bool COUNT, class P, class Epi>
+static int launch_fast3_any(const Accel *a, Rays rays, size_t n, Epi epi, const TraceOptions16 &opt, uint32_t flags,
+                            unsigned long long *d_counts, const unsigned long long *n_ptr, cudaStream_t s);
+
+// the default for coherent launches, with the size cut-off
+template <class Rays, bool COUNT, class Epi>
+static int launch_fast3_coherent(const Accel *a, Rays rays, size_t n, Epi epi, const TraceOptions16 &opt, uint32_t flags,
+                                 unsigned long long *d_counts, const unsigned long long *n_ptr, cudaStream_t s) {
+  if (a->n_wide * sizeof(PairNode) > kPair128MaxBytes)
+    return launch_fast3_any<Rays, COUNT, IncoherentPolicy>(a, rays, n, epi, opt, flags, d_counts, n_ptr, s);
+  return launch_fast3_any<Rays, COUNT, DefaultPolicy>(a, rays, n, epi, opt, flags, d_counts, n_ptr, s);
+}
+
+template <class Rays, bool COUNT, class P, class Epi>
+static int launch_fast3_any(const Accel *a, Rays rays, size_t n, Epi epi, const TraceOptions16 &opt, uint32_t flags,
+                            unsigned long long *d_counts, const unsigned long long *n_ptr, cudaStream_t s) {
+  if (!a->d_pair || !a->d_tris_cm) {
+    set_error("traverse: this accel has no triangle traversal layout");
+    return NRT_ERR_INVALID;
+  }
+  cudaError_t e;
+  unsigned long long *cursor = next_cursor(a, s, &e);
+  NRT_CUDA(e);
+  if (needs_deep_stack(a))
+    e = launch_fast3<Rays, 512, COUNT, P>(a, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, s);
+  else
+    e = launch_fast3<Rays, 64, COUNT, P>(a, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, s);
+  NRT_CUDA(e);
+  return NRT_OK;
+}
 
 template <class Rays, bool COUNT>
 static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
                        const TraceOptions16 &opt, uint32_t flags, unsigned long long *d_counts, cudaStream_t s,
                        const unsigned long long *n_ptr = nullptr) {
-  unsigned long long *cursor =
-      reinterpret_cast<unsigned long long *>(a->d_counters) + 16 + (a->cursor_ring.fetch_add(1) & 31u);
-  NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
-  // wide-node stack depth never exceeds the tree depth
-  const bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
   const uint32_t variant = (flags >> 8) & 0xFFu;  // experiment selector (tools/trav_sweep.py); 0 = default
-  cudaError_t e = cudaSuccess;
   const StoreHitsEpilogue epi{d_hits, d_mask};
+  if (variant == 0 || COUNT) return launch_fast3_coherent<Rays, COUNT>(a, rays, n, epi, opt, flags, d_counts, n_ptr, s);
+  if (variant < 100) {
+#define NRT_VARIANT3(id, ...)                                                                                          \
+  case id:                                                                                                            \
+    return launch_fast3_any<Rays, false, Policy3<__VA_ARGS__> >(a, rays, n, epi, opt, flags, d_counts, n_ptr, s);
+    switch (variant) {
+      NRT_VARIANT3(1, 128, 8, 16, 8)
+      NRT_VARIANT3(2, 128, 9, 16, 8)
+      NRT_VARIANT3(3, 128, 12, 16, 8)
+      NRT_VARIANT3(4, 128, 10, 8, 8)
+      NRT_VARIANT3(5, 128, 10, 24, 8)
+      NRT_VARIANT3(6, 128, 10, 16, 4)
+      NRT_VARIANT3(7, 128, 10, 16, 12)
+      NRT_VARIANT3(8, 128, 10, 16, 0)
+      NRT_VARIANT3(9, 256, 5, 16, 8)
+      NRT_VARIANT3(10, 64, 20, 16, 8)
+      NRT_VARIANT3(11, 128, 7, 16, 8)
+      NRT_VARIANT3(12, 128, 6, 16, 8)
+      NRT_VARIANT3(20, 128, 10, 16, 8, false)
+      NRT_VARIANT3(21, 128, 9, 16, 8, false)
+      NRT_VARIANT3(22, 128, 8, 16, 8, false)
+      NRT_VARIANT3(23, 128, 10, 16, 4, false)
+      NRT_VARIANT3(19, 128, 10, 16, 8, true)  // PairNode regardless of the size cut-off
+      NRT_VARIANT3(30, 128, 10, 16, 8, false, true)  // 2 x LDG.256 per node: measured 5-7 % slower than 4 loads
+      default:
+        set_error("nrt_traverse: unknown kernel variant in flags");
+        return NRT_ERR_INVALID;
+    }
+#undef NRT_VARIANT3
+  }
+  // ---- round-1 kernel (64-byte WideNode + vertex-major PackedTri), kept for A/B runs
+  cudaError_t e;
+  unsigned long long *cursor = next_cursor(a, s, &e);
+  NRT_CUDA(e);
+  const bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
   if (deep) {
-    e = launch_fast2<Rays, 512 - kStackSmem, COUNT, DefaultPolicy>(a, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, s);
-  } else if (variant == 0 || COUNT) {
-    e = launch_fast2<Rays, 48, COUNT, DefaultPolicy>(a, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, s);
+    e = launch_fast2<Rays, 512 - kStackSmem, false, OldDefaultPolicy>(a, rays, n, epi, opt, flags, cursor, d_counts, n_ptr, s);
   } else {
 #define NRT_VARIANT(id, ...)                                                                                        \
   case id:                                                                                                          \
@@ -419,18 +518,11 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
                                                                 n_ptr, s);                                          \
     break;
     switch (variant) {
-      NRT_VARIANT(2, 128, 8, 1, 0)
-      NRT_VARIANT(4, 128, 8, 16, 0)
-      NRT_VARIANT(5, 128, 8, 8, 8)
-      NRT_VARIANT(6, 128, 8, 8, 16)
-      NRT_VARIANT(8, 64, 16, 8, 0)
-      NRT_VARIANT(9, 256, 4, 8, 0)
-      NRT_VARIANT(10, 128, 6, 8, 0)
-      NRT_VARIANT(11, 128, 10, 8, 0)
-      NRT_VARIANT(21, 128, 9, 8, 8)
-      NRT_VARIANT(30, 128, 10, 16, 8, 64)
-      NRT_VARIANT(40, 128, 10, 16, 8, 0, 8)
-      NRT_VARIANT(42, 128, 10, 16, 8, 0, 4)
+      NRT_VARIANT(100, 128, 10, 16, 8, 0, 0)
+      NRT_VARIANT(130, 128, 10, 16, 8, 64)
+      NRT_VARIANT(131, 128, 9, 16, 8, 128)
+      NRT_VARIANT(140, 128, 10, 16, 8, 0, 8)
+      NRT_VARIANT(142, 128, 10, 16, 8, 0, 4)
       default:
         set_error("nrt_traverse: unknown kernel variant in flags");
         return NRT_ERR_INVALID;
@@ -485,17 +577,7 @@ template <class Epi, class P = DefaultPolicy, class Rays = SoaRays>
 static int launch_fused(const Accel *a, Rays rays, size_t n, const unsigned long long *n_ptr, Epi epi,
                         const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   if (n == 0) return NRT_OK;
-  unsigned long long *cursor =
-      reinterpret_cast<unsigned long long *>(a->d_counters) + 16 + (a->cursor_ring.fetch_add(1) & 31u);
-  NRT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
-  const bool deep = a->stats.max_tree_depth + 2 > (uint32_t)(kStackSmem + 48);
-  cudaError_t e;
-  if (deep)
-    e = launch_fast2<Rays, 512 - kStackSmem, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
-  else
-    e = launch_fast2<Rays, 48, false, P>(a, rays, n, epi, opt, flags, cursor, nullptr, n_ptr, s);
-  NRT_CUDA(e);
-  return NRT_OK;
+  return launch_fast3_any<Rays, false, P>(a, rays, n, epi, opt, flags, nullptr, n_ptr, s);
 }
 
 int launch_traverse_primary_fused(const Accel *a, const Wave &w, const nrt_ao_params &p, unsigned long long slot0,
@@ -510,21 +592,22 @@ int launch_traverse_camera_fused(const Accel *a, const Wave &w, const nrt_ao_par
                                  size_t count, float *d_accum, unsigned long long *d_wave_counters,
                                  const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   PrimaryToAoEpilogue<true> epi{p, slot0, w, a->d_verts, a->d_faces, d_accum, d_wave_counters};
-  return launch_fused<PrimaryToAoEpilogue<true>, DefaultPolicy, CameraRays>(a, CameraRays{p, slot0}, count, nullptr, epi,
-                                                                            opt, flags, s);
+  if (count == 0) return NRT_OK;
+  return launch_fast3_coherent<CameraRays, false>(a, CameraRays(p, slot0), count, epi, opt, flags, nullptr, nullptr, s);
 }
 
 int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long long *d_count, size_t capacity,
                              float *d_accum, unsigned long long *d_totals, const TraceOptions16 &opt, uint32_t flags,
                              cudaStream_t s) {
   AoAccumulateEpilogue epi{w.ao_pix, d_accum, d_totals};
-  return launch_fused(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count, epi, opt, flags, s);
+  return launch_fused<AoAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count, epi,
+                                                              opt, flags, s);
 }
 
 int launch_traverse_path_radiance(const Accel *a, const PathShadeEpilogue &epi, const unsigned long long *d_count,
                                   size_t capacity, const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   // the shading block needs more registers than the plain traversal: 8 CTAs/SM (64 registers) instead of 10
-  return launch_fused<PathShadeEpilogue, FastPolicy<128, 8, 16, 8, 0, 0> >(
+  return launch_fused<PathShadeEpilogue, Policy3<128, 8, 16, 8, false> >(
       a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]}, capacity, d_count, epi, opt, flags, s);
 }
 
@@ -532,7 +615,8 @@ int launch_traverse_path_shadow(const Accel *a, const PathQueues &q, const unsig
                                 size_t capacity, float *d_accum, const TraceOptions16 &opt, uint32_t flags,
                                 cudaStream_t s) {
   ShadowAccumulateEpilogue epi{q.sh_contrib_pix, d_accum};
-  return launch_fused(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity, d_count, epi, opt, flags, s);
+  return launch_fused<ShadowAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity, d_count,
+                                                                  epi, opt, flags, s);
 }
 
 int launch_traverse_count(const Accel *a, const Ray36 *d_rays, size_t n, const TraceOptions16 &opt,

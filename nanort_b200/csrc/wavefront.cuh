@@ -38,18 +38,47 @@ __device__ __forceinline__ float rand_ps(uint32_t pix, uint32_t smp, uint32_t di
 // The part of nrt_ao_params / nrt_path_params that maps ray slots to pixels.
 struct TileMap {
   uint32_t width, height, spp, sample0, tile_w, tile_h, shard, n_shards;
+  uint32_t packed;  // accumulate into a tile-major buffer of this shard's tiles (NRT_AO_PACKED_TILES) instead of the image
 };
 __host__ __device__ __forceinline__ TileMap tile_map(const nrt_ao_params &p) {
-  return TileMap{p.width, p.height, p.spp, p.sample0, p.tile_w, p.tile_h, p.shard, p.n_shards};
+  return TileMap{p.width, p.height, p.spp, p.sample0, p.tile_w, p.tile_h, p.shard, p.n_shards,
+                 (p.flags & NRT_AO_PACKED_TILES) ? 1u : 0u};
 }
 __host__ __device__ __forceinline__ TileMap tile_map(const nrt_path_params &p) {
-  return TileMap{p.width, p.height, p.spp, p.sample0, p.tile_w, p.tile_h, p.shard, p.n_shards};
+  return TileMap{p.width, p.height, p.spp, p.sample0, p.tile_w, p.tile_h, p.shard, p.n_shards, 0u};
 }
+
+// Division of a 32-bit value by a run-time constant without a divide (Granlund-Montgomery round-up method, exact for
+// every uint32 x): the slot -> pixel mapping of a camera ray needs four of them, and an integer division costs more
+// instructions than the slab test of a node pair.
+struct FastDiv {
+  uint32_t d, mul, shift;  // shift == 0xFFFFFFFF: d is 1
+  __host__ __device__ FastDiv() : d(1), mul(0), shift(0xFFFFFFFFu) {}
+  __host__ explicit FastDiv(uint32_t dd) : d(dd ? dd : 1), mul(0), shift(0xFFFFFFFFu) {
+    if (d > 1) {
+      uint32_t l = 0;
+      while ((1ull << l) < d) l++;  // ceil(log2 d) >= 1
+      mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1ull);
+      shift = l - 1;
+    }
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t x) const {
+    if (shift == 0xFFFFFFFFu) return x;
+    const uint32_t t = __umulhi(mul, x);
+    return (t + ((x - t) >> 1)) >> shift;
+  }
+  __device__ __forceinline__ void divmod(uint32_t x, uint32_t &q, uint32_t &r) const {
+    q = div(x);
+    r = x - q * d;
+  }
+};
 
 // Slot -> (pixel, sample).  Slots enumerate this shard's tiles; inside a tile the order is sample-major over
 // 8x4 pixel blocks, so the 32 lanes of a warp start as one coherent 8x4 packet.
+// `acc` = where the pixel's samples are accumulated: the pixel itself, or -- tile-major packing for the multi-GPU
+// gather (comm.cu) -- k * tile_pixels + row-major offset inside the tile.
 __device__ __forceinline__ bool slot_to_pixel(const TileMap &p, unsigned long long slot, uint32_t &pix,
-                                              uint32_t &smp) {
+                                              uint32_t &smp, uint32_t &acc) {
   const uint32_t tile_pix = p.tile_w * p.tile_h;
   const unsigned long long per_tile = (unsigned long long)tile_pix * p.spp;
   const uint32_t k = (uint32_t)(slot / per_tile);  // k-th tile of this shard
@@ -66,7 +95,14 @@ __device__ __forceinline__ bool slot_to_pixel(const TileMap &p, unsigned long lo
   const uint32_t x = tx * p.tile_w + lx, y = ty * p.tile_h + ly;
   if (x >= p.width || y >= p.height) return false;
   pix = y * p.width + x;
+  acc = p.packed ? k * tile_pix + ly * p.tile_w + lx : pix;
   return true;
+}
+
+__device__ __forceinline__ bool slot_to_pixel(const TileMap &p, unsigned long long slot, uint32_t &pix,
+                                              uint32_t &smp) {
+  uint32_t acc;
+  return slot_to_pixel(p, slot, pix, smp, acc);
 }
 
 __device__ __forceinline__ bool slot_to_pixel(const nrt_ao_params &p, unsigned long long slot, uint32_t &pix,
@@ -98,26 +134,69 @@ __device__ __forceinline__ void camera_ray(const float *cam, uint32_t width, uin
 }
 
 // Ray "loader" that generates the camera ray of slot (slot0 + i) instead of reading a queue: the primary
-// traversal then needs no generator kernel and no primary ray queue at all.
+// traversal then needs no generator kernel and no primary ray queue at all.  The mapping is slot_to_pixel() with its
+// divisions replaced by multiplications (slot0 is a multiple of the per-tile slot count: waves are whole tiles), and
+// what the retire step needs again -- direction, pixel, sample, accumulation index -- travels as the ray's payload
+// (6 words the kernel parks in thread-local memory) instead of being recomputed.
 struct CameraRays {
+  static constexpr int kPayloadWords = 6;
   nrt_ao_params p;
-  unsigned long long slot0;
+  uint32_t k0;  // slot0 / per_tile: ordinal (within the shard) of the wave's first tile
+  FastDiv per_tile, tile_pix, bw, tiles_x;
+  uint32_t packed;
+  __host__ CameraRays(const nrt_ao_params &pp, unsigned long long slot0) : p(pp) {
+    const uint32_t tp = pp.tile_w * pp.tile_h;
+    per_tile = FastDiv(tp * pp.spp);
+    tile_pix = FastDiv(tp);
+    bw = FastDiv(pp.tile_w / 8);
+    tiles_x = FastDiv((pp.width + pp.tile_w - 1) / pp.tile_w);
+    k0 = (uint32_t)(slot0 / ((unsigned long long)tp * pp.spp));
+    packed = (pp.flags & NRT_AO_PACKED_TILES) ? 1u : 0u;
+  }
   __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy, float &dz,
-                                       float &tmin, float &tmax) const {
-    uint32_t pix, smp;
+                                       float &tmin, float &tmax, uint32_t *payload) const {
+    uint32_t k, rem, smp, q, blk, bx, by, ty, tx;
+    per_tile.divmod((uint32_t)i, k, rem);
+    k += k0;
+    tile_pix.divmod(rem, smp, q);
+    blk = q >> 5;
+    const uint32_t in = q & 31u;
+    bw.divmod(blk, by, bx);
+    const uint32_t lx = bx * 8 + (in & 7), ly = by * 4 + (in >> 3);
+    tiles_x.divmod(k * p.n_shards + p.shard, ty, tx);
+    const uint32_t x = tx * p.tile_w + lx, y = ty * p.tile_h + ly;
     ox = p.cam[0];
     oy = p.cam[1];
     oz = p.cam[2];
-    if (slot_to_pixel(p, slot0 + i, pix, smp)) {
-      camera_ray(p.cam, p.width, p.height, p.seed, pix, smp + p.sample0, dx, dy, dz);
+    if (x < p.width && y < p.height) {
+      const uint32_t pix = y * p.width + x;
+      smp += p.sample0;
+      // camera_ray() with the pixel coordinates at hand (same arithmetic, same rays bit for bit)
+      const float jx = rand_ps(pix, smp, 0, p.seed), jy = rand_ps(pix, smp, 1, p.seed);
+      const float sx = ((float)x + jx) / (float)p.width - 0.5f;
+      const float sy = 0.5f - ((float)y + jy) / (float)p.height;
+      dx = p.cam[3] * sx + p.cam[6] * sy + p.cam[9];
+      dy = p.cam[4] * sx + p.cam[7] * sy + p.cam[10];
+      dz = p.cam[5] * sx + p.cam[8] * sy + p.cam[11];
+      const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+      dx *= inv;
+      dy *= inv;
+      dz *= inv;
       tmin = p.ray_min_t;
       tmax = p.ray_max_t;
+      payload[0] = __float_as_uint(dx);
+      payload[1] = __float_as_uint(dy);
+      payload[2] = __float_as_uint(dz);
+      payload[3] = pix;
+      payload[4] = smp;
+      payload[5] = packed ? k * tile_pix.d + ly * p.tile_w + lx : pix;
     } else {  // slot outside the image: retires at the root as a miss
       dx = 0.0f;
       dy = 0.0f;
       dz = -1.0f;
       tmin = 0.0f;
       tmax = -1.0f;
+      payload[3] = 0xFFFFFFFFu;
     }
   }
 };
@@ -164,7 +243,7 @@ struct StoreHitsEpilogue {
   Hit16 *hits;
   uint8_t *mask;
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
-                                             float max_t) const {
+                                             float max_t, const uint32_t *) const {
     if (retiring && hits) {
       const bool hit = t < max_t;  // a hit exactly at max_t is a miss (nanort.h:2552)
       float4 r = hit ? make_float4(u, v, t, __uint_as_float(prim)) : make_float4(0.0f, 0.0f, max_t, __uint_as_float(0xFFFFFFFFu));
@@ -186,27 +265,27 @@ struct PrimaryToAoEpilogue {
   float *accum;
   unsigned long long *counters;  // [0] AO rays of this wave
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
-                                             float max_t) const {
+                                             float max_t, const uint32_t *payload) const {
     (void)u;
     (void)v;
     bool make = false;
     float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4;
-    uint32_t pix = 0xFFFFFFFFu;
+    uint32_t pix = 0xFFFFFFFFu, acc = 0;
     if (retiring) {
       uint32_t smp = 0;
       float4 ro, rd;
-      if (GEN) {
-        if (slot_to_pixel(p, slot0 + ray_idx, pix, smp)) {
-          smp += p.sample0;
-          float dx, dy, dz;
-          camera_ray(p.cam, p.width, p.height, p.seed, pix, smp, dx, dy, dz);
+      if (GEN) {  // the camera ray's payload (CameraRays::load): direction, pixel, sample, accumulation index
+        pix = payload[3];
+        if (pix != 0xFFFFFFFFu) {
+          smp = payload[4];
+          acc = payload[5];
           ro = make_float4(p.cam[0], p.cam[1], p.cam[2], p.ray_min_t);
-          rd = make_float4(dx, dy, dz, p.ray_max_t);
-        } else {
-          pix = 0xFFFFFFFFu;
+          rd = make_float4(__uint_as_float(payload[0]), __uint_as_float(payload[1]), __uint_as_float(payload[2]),
+                           p.ray_max_t);
         }
       } else {
         pix = w.pix[ray_idx];
+        acc = pix;  // the unfused path does not pack (run_ao_pass rejects the combination)
         if (pix != 0xFFFFFFFFu) {
           smp = slot_sample(p, slot0 + ray_idx);
           ro = w.org_tmin[ray_idx];
@@ -218,7 +297,7 @@ struct PrimaryToAoEpilogue {
           make_ao_ray(p, pix, smp, ro, rd, t, prim, verts, faces, o4, d4);
           make = true;
         } else {
-          atomicAdd(accum + pix, 1.0f);
+          atomicAdd(accum + acc, 1.0f);
         }
       }
     }
@@ -232,7 +311,7 @@ struct PrimaryToAoEpilogue {
       const unsigned long long j = base + __popc(m & ((1u << lane) - 1u));
       w.ao_org_tmin[j] = o4;
       w.ao_dir_tmax[j] = d4;
-      w.ao_pix[j] = pix;
+      w.ao_pix[j] = acc;  // the AO retire step only needs the accumulation index
     }
   }
 };
@@ -243,7 +322,7 @@ struct AoAccumulateEpilogue {
   float *accum;
   unsigned long long *totals;  // [1] occluded AO rays
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
-                                             float max_t) const {
+                                             float max_t, const uint32_t *) const {
     (void)u;
     (void)v;
     (void)prim;
@@ -307,7 +386,7 @@ struct PathShadeEpilogue {
   float *accum;                  // rgb
   unsigned long long *counters;  // [0] continuation rays, [1] shadow rays of this bounce
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
-                                             float max_t) const {
+                                             float max_t, const uint32_t *) const {
     bool cont = false, shadow = false;
     float4 co = make_float4(0, 0, 0, 0), cd = co, so = co, sd = co, sc = co;
     uint32_t pid = 0;
@@ -511,7 +590,7 @@ struct ShadowAccumulateEpilogue {
   const float4 *contrib_pix;
   float *accum;
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
-                                             float max_t) const {
+                                             float max_t, const uint32_t *) const {
     (void)u;
     (void)v;
     (void)prim;

@@ -80,3 +80,38 @@ def slot_pixels(width, height, tile_w, tile_h, shard, n_shards, spp):
     pix = np.where((x < width) & (y < height), y * width + x, -1)
     smp = np.broadcast_to(np.arange(spp, dtype=np.int64)[None, :, None], pix.shape)
     return pix.reshape(-1), smp.reshape(-1)
+
+
+# ---- host model of the C-ABI multi-GPU path (csrc/comm.cu: nrt_render_ao_sharded) --------------------------------
+# A rank accumulates into a TILE-MAJOR buffer of its own tiles (NRT_AO_PACKED_TILES, csrc/wavefront.cuh): its k-th
+# tile (image tile k * world + rank) occupies floats [k * tile_w * tile_h, (k + 1) * tile_w * tile_h), rows of tile_w.
+# All ranks' buffers have the same size (ceil(n_tiles / world) tiles), so ONE equal-count all-gather moves them, and the
+# unpack (comm.cu:unpack_tiles_kernel) reads pixel (x, y) from rank (tile % world), tile slot (tile // world).
+def packed_slot_floats(width, height, tile_w, tile_h, world):
+    tiles_x = (width + tile_w - 1) // tile_w
+    tiles_y = (height + tile_h - 1) // tile_h
+    return ((tiles_x * tiles_y + world - 1) // world) * tile_w * tile_h
+
+
+def pack_own_tiles(frame, width, height, tile_w, tile_h, shard, n_shards):
+    """What the device pass leaves in a rank's slot: `frame` (row-major, only this rank's pixels are read) tile-major."""
+    out = np.zeros(packed_slot_floats(width, height, tile_w, tile_h, n_shards), dtype=frame.dtype)
+    tiles, tiles_x = shard_tiles(width, height, tile_w, tile_h, shard, n_shards)
+    img = frame.reshape(height, width)
+    for k, t in enumerate(tiles):
+        x0, y0 = int(t % tiles_x) * tile_w, int(t // tiles_x) * tile_h
+        blk = img[y0:y0 + tile_h, x0:x0 + tile_w]
+        dst = out[k * tile_w * tile_h:(k + 1) * tile_w * tile_h].reshape(tile_h, tile_w)
+        dst[: blk.shape[0], : blk.shape[1]] = blk
+    return out
+
+
+def unpack_gathered(gathered, width, height, tile_w, tile_h, world):
+    """comm.cu:unpack_tiles_kernel on the host: gathered = world slots of packed_slot_floats() floats each."""
+    slot = packed_slot_floats(width, height, tile_w, tile_h, world)
+    tiles_x = (width + tile_w - 1) // tile_w
+    y, x = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    tx, ty = x // tile_w, y // tile_h
+    tile = ty * tiles_x + tx
+    src = (tile % world) * slot + (tile // world) * tile_w * tile_h + (y - ty * tile_h) * tile_w + (x - tx * tile_w)
+    return np.asarray(gathered).reshape(-1)[src.reshape(-1)]

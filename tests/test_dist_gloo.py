@@ -43,3 +43,30 @@ def test_two_rank_gather_equals_single_rank_frame(tmp_path):
     want = np.arange(W * H, dtype=np.float32) * 0.5 + 1.0
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"r{r}.npy"), want)
+
+
+def _worker_packed(rank, world, port, W, H, tw, th, out_dir):
+    """The C-ABI path's data movement (csrc/comm.cu) on the host: tile-major slot per rank, ONE equal-count all_gather
+    (gloo here, ncclAllGather there), unpack to the row-major frame."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nanort_b200 import dist as nd
+
+    full = np.arange(W * H, dtype=np.float32) * 0.25 + 3.0
+    mine = torch.as_tensor(nd.pack_own_tiles(full, W, H, tw, th, rank, world))
+    slot = nd.packed_slot_floats(W, H, tw, th, world)
+    assert len(mine) == slot
+    gathered = torch.zeros(slot * world)
+    dist.all_gather_into_tensor(gathered, mine)
+    np.save(os.path.join(out_dir, f"p{rank}.npy"), nd.unpack_gathered(gathered.numpy(), W, H, tw, th, world))
+    dist.destroy_process_group()
+
+
+def test_two_rank_packed_tile_gather_equals_single_rank_frame(tmp_path):
+    W, H, tw, th = 200, 100, 64, 8  # partial tiles on both edges, odd tile count
+    port = _free_port()
+    mp.spawn(_worker_packed, args=(2, port, W, H, tw, th, str(tmp_path)), nprocs=2, join=True)
+    want = np.arange(W * H, dtype=np.float32) * 0.25 + 3.0
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"p{r}.npy"), want)

@@ -115,3 +115,31 @@ def test_f64_drop_in_prints_the_reference_output():
     with gzip.open(os.path.join(ROOT, "tests", "golden", "f64_check_ref.txt.gz"), "rt") as f:
         want = f.read().strip().splitlines()
     assert len(want) > 1500 and got == want
+
+
+def test_reference_objrender_program_renders_the_reference_image(tmp_path):
+    """The reference's OWN example program (examples/objrender/main.cc, unmodified; one BVHAccel::Traverse per pixel),
+    compiled once against the reference header and once against include/nanort.h (examples/Makefile, target `ref`),
+    must write byte-identical images; the run also gives the rays/s of the literal per-ray drop-in."""
+    import time
+
+    exe_b, exe_r = os.path.join(BIN, "ref_objrender_b200"), os.path.join(BIN, "ref_objrender_ref")
+    obj = os.path.join(BIN, "assets", "cornellbox_suzanne.obj")
+    if not (os.path.exists(exe_b) and os.path.exists(exe_r) and os.path.exists(obj)):
+        pytest.skip("reference example binaries were not built (authoring container without /root/reference)")
+    imgs = {}
+    for tag, exe in (("b200", exe_b), ("ref", exe_r)):
+        d = tmp_path / tag
+        d.mkdir()
+        for f in ("cornellbox_suzanne.obj", "cornellbox_suzanne.mtl"):
+            os.symlink(os.path.join(BIN, "assets", f), d / f)
+        t0 = time.time()
+        out = subprocess.run([exe, "cornellbox_suzanne.obj"], cwd=d, check=True, capture_output=True, text=True,
+                             timeout=600).stdout
+        dt = time.time() - t0
+        imgs[tag] = (open(d / "render.exr", "rb").read(), open(d / "render.png", "rb").read())
+        render = [ln for ln in out.splitlines() if ln.startswith("Render ")]
+        print(f"objrender[{tag}]: wall {dt:.2f} s, {render[-1] if render else ''} "
+              f"({512 * 512 / max(float(render[-1].split()[1]), 1e-9) / 1e6 if render else 0:.3f} Mrays/s per-ray Traverse)")
+    assert imgs["b200"][0] == imgs["ref"][0], "render.exr differs from the reference program's"
+    assert imgs["b200"][1] == imgs["ref"][1], "render.png differs from the reference program's"
