@@ -447,6 +447,44 @@ template <class I, class T>
 inline void set_result(const I &, T, T, T, unsigned int, long) {}
 }  // namespace detail
 
+// ---- user-defined primitives ------------------------------------------------------------------------
+// The reference lets a caller hand ANY Prim / Pred / Intersector classes to BVHAccel (nanort.h:698-860).  Host functors
+// cannot run inside a CUDA kernel, so on the device the concept maps to primitive KINDS (include/nanort_b200.h,
+// nrt_build_prims).  Build() picks the kind from the Prim class:
+//   * TriangleMesh<T>                                  -> triangles (the hot path)
+//   * a class with members `vertices_` and `radiuss_`  -> spheres: the SphereGeometry of the reference's
+//     examples/particle_primitive/main.cc:105-145 -- that example compiles unmodified; other sphere-like classes opt in
+//     by specialising nanort::DeviceSpheres<Prim> below
+//   * anything else                                    -> its bounding boxes: p.BoundingBox() is evaluated on the HOST for
+//     every primitive and the tree is built over those boxes; such an accel answers ListNodeIntersections (the
+//     node-level query of the two-level API, nanort.h:2607-2692) -- Traverse() needs a kind the device knows.
+template <class Prim, class Enable = void>
+struct DeviceSpheres {
+  static const bool value = false;
+};
+template <class Prim>
+struct DeviceSpheres<Prim, decltype((void)std::declval<const Prim &>().vertices_, (void)std::declval<const Prim &>().radiuss_, void())> {
+  static const bool value = true;
+  static const float *centers(const Prim &p) { return p.vertices_; }
+  static const float *radii(const Prim &p) { return p.radiuss_; }
+  static size_t center_stride_bytes(const Prim &) { return 3 * sizeof(float); }
+};
+
+namespace detail {
+struct triangle_tag {};
+struct sphere_tag {};
+struct boxes_tag {};
+template <class Prim>
+struct prim_tag {
+  typedef typename std::conditional<std::is_same<Prim, TriangleMesh<float> >::value, triangle_tag,
+                                    typename std::conditional<DeviceSpheres<Prim>::value, sphere_tag, boxes_tag>::type>::type type;
+};
+template <class I>
+struct is_triangle_intersector : std::false_type {};
+template <class H>
+struct is_triangle_intersector<TriangleIntersector<float, H> > : std::true_type {};
+}  // namespace detail
+
 // ---- BVHAccel ------------------------------------------------------------------------------------
 template <typename T>
 class BVHAccel {
@@ -465,9 +503,7 @@ class BVHAccel<float> {
   template <class Prim, class Pred>
   bool Build(const unsigned int num_primitives, const Prim &p, const Pred &pred,
              const BVHBuildOptions<float> &options = BVHBuildOptions<float>()) {
-    static_assert(std::is_same<Prim, TriangleMesh<float> >::value && std::is_same<Pred, TriangleSAHPred<float> >::value,
-                  "nanort_b200: Build runs on the GPU for TriangleMesh<float> + TriangleSAHPred<float> only");
-    (void)pred;
+    (void)pred;  // the SAH partition runs on the device over the primitives' boxes / centroids
     handle_.reset();
     nodes_.clear();
     indices_.clear();
@@ -475,10 +511,10 @@ class BVHAccel<float> {
     stats_ = BVHBuildStatistics();
     options_ = options;
     n_prims_ = 0;
+    kind_ = 0;
     if (num_primitives == 0) return false;
     nrt_accel *h = NULL;
-    int rc = nrt_build_ex(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), num_primitives, &options,
-                          NANORT_B200_BUILD_FLAGS, &h);
+    const int rc = BuildKind(num_primitives, p, options, &h, typename detail::prim_tag<Prim>::type());
     if (rc != NRT_OK) {
       fprintf(stderr, "nanort_b200: Build failed: %s\n", nrt_last_error());
       return false;
@@ -496,7 +532,7 @@ class BVHAccel<float> {
   template <class I, class H>
   bool Traverse(const Ray<float> &ray, const I &intersector, H *isect,
                 const BVHTraceOptions &options = BVHTraceOptions()) const {
-    if (!Ready(intersector)) return false;
+    if (!ReadyFor(intersector, detail::is_triangle_intersector<I>())) return false;
     TriangleIntersection<float> rec;
     unsigned char hit = 0;
     if (nrt_traverse(handle_.get(), &ray, 1, &rec, &hit, &options, NANORT_B200_TRAVERSE_FLAGS) != NRT_OK) {
@@ -533,6 +569,37 @@ class BVHAccel<float> {
     size_t c = 0;
     for (size_t i = 0; i < n; i++) c += hit_mask[i] ? 1 : 0;
     return c;
+  }
+
+  /// nanort.h:2607-2692: the (at most max_intersections) nearest primitive BOXES the ray pierces, nearest first.  The
+  /// accel must have been built from a box-like Prim (see "user-defined primitives" above); the box test is the one of
+  /// the reference's NodeBBoxIntersector (examples/nanosg/nanosg.h:562-640) -- `intersector` only names the kind.
+  template <class I>
+  bool ListNodeIntersections(const Ray<float> &ray, int max_intersections, const I &intersector,
+                             StackVector<NodeHit<float>, 128> *hits) const {
+    (void)intersector;
+    (*hits)->clear();
+    if (!handle_ || kind_ != (int)NRT_PRIM_BOXES) {
+      fprintf(stderr, "nanort_b200: ListNodeIntersections needs an accel built over boxes\n");
+      return false;
+    }
+    if (max_intersections > 64) max_intersections = 64;
+    struct Rec {
+      float t_min, t_max;
+      unsigned int node_id;
+    } recs[64];
+    uint32_t count = 0;
+    if (nrt_list_node_intersections(handle_.get(), &ray, 1, max_intersections, recs, &count, NANORT_B200_INVERSE_FLAG) != NRT_OK) {
+      fprintf(stderr, "nanort_b200: ListNodeIntersections failed: %s\n", nrt_last_error());
+      return false;
+    }
+    (*hits)->resize(count);
+    for (uint32_t k = 0; k < count; k++) {
+      (*hits)[k].t_min = recs[k].t_min;
+      (*hits)[k].t_max = recs[k].t_max;
+      (*hits)[k].node_id = recs[k].node_id;
+    }
+    return count > 0;
   }
 
   const std::vector<BVHNode<float> > &GetNodes() const {
@@ -609,6 +676,46 @@ class BVHAccel<float> {
   const nrt_accel *NativeHandle() const { return handle_.get(); }
 
  private:
+  template <class Prim>
+  int BuildKind(unsigned int n, const Prim &p, const BVHBuildOptions<float> &options, nrt_accel **h, detail::triangle_tag) {
+    kind_ = 0;
+    return nrt_build_ex(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), n, &options, NANORT_B200_BUILD_FLAGS, h);
+  }
+  template <class Prim>
+  int BuildKind(unsigned int n, const Prim &p, const BVHBuildOptions<float> &options, nrt_accel **h, detail::sphere_tag) {
+    kind_ = (int)NRT_PRIM_SPHERES;
+    return nrt_build_prims(NRT_PRIM_SPHERES, DeviceSpheres<Prim>::centers(p), DeviceSpheres<Prim>::center_stride_bytes(p),
+                           DeviceSpheres<Prim>::radii(p), n, &options, h);
+  }
+  template <class Prim>
+  int BuildKind(unsigned int n, const Prim &p, const BVHBuildOptions<float> &options, nrt_accel **h, detail::boxes_tag) {
+    kind_ = (int)NRT_PRIM_BOXES;
+    std::vector<float> boxes(6 * static_cast<size_t>(n));  // the user's Prim::BoundingBox, evaluated on the host
+    for (unsigned int i = 0; i < n; i++) {
+      real3<float> bmin, bmax;
+      p.BoundingBox(&bmin, &bmax, i);
+      for (int k = 0; k < 3; k++) {
+        boxes[6 * static_cast<size_t>(i) + k] = bmin[k];
+        boxes[6 * static_cast<size_t>(i) + 3 + k] = bmax[k];
+      }
+    }
+    return nrt_build_prims(NRT_PRIM_BOXES, boxes.data(), 24, NULL, n, &options, h);
+  }
+  template <class I>
+  bool ReadyFor(const I &isec, std::true_type) const {
+    if (kind_ != 0) {
+      fprintf(stderr, "nanort_b200: a TriangleIntersector was handed to an accel built over another primitive kind\n");
+      return false;
+    }
+    return Ready(isec);
+  }
+  template <class I>
+  bool ReadyFor(const I &, std::false_type) const {
+    if (handle_ && kind_ == (int)NRT_PRIM_SPHERES) return true;
+    fprintf(stderr, "nanort_b200: Traverse with a user-defined intersector needs an accel of a kind the device knows "
+                    "(spheres: see DeviceSpheres in nanort.h); this accel has kind %d\n", kind_);
+    return false;
+  }
   // The reference's Traverse may run on many threads at once (examples/path_tracer/main.cc:787-799): the lazy adopt of
   // a Load()ed tree and the lazy host mirror are serialised.
   template <class I>
@@ -652,6 +759,7 @@ class BVHAccel<float> {
   BVHBuildOptions<float> options_;
   mutable BVHBuildStatistics stats_;
   unsigned int n_prims_;
+  int kind_ = 0;  // 0 triangles, NRT_PRIM_SPHERES, NRT_PRIM_BOXES
 };
 
 // ---- BVHAccel<double> ----------------------------------------------------------------------------

@@ -101,6 +101,29 @@ void nrt_free(nrt_accel *a);
 int nrt_stats(const nrt_accel *a, void *stats_16B);
 /* BVHAccel::BoundingBox (nanort.h:792-804). */
 int nrt_bounding_box(const nrt_accel *a, float bmin[3], float bmax[3]);
+/* ------------------------------------------------------------------ non-triangle primitives
+ * nanort's Prim / Pred / Intersector concept (nanort.h:698-860, 1014-1229) on the device: host functors cannot run in a
+ * kernel, so the hook is a set of primitive KINDS, each the device restatement of one of the reference's own models:
+ *   NRT_PRIM_SPHERES  examples/particle_primitive/main.cc:80-291 (SpherePred, SphereGeometry, SphereIntersector):
+ *                     data = centers (float3, stride_bytes apart), aux = radii.  The accel then works with
+ *                     nrt_traverse / nrt_traverse_device / nrt_nodes / nrt_stats / nrt_bounding_box; hit records are
+ *                     {u, v, t, prim_id} as SphereIntersector::PostTraversal fills them (NOTE the model's own
+ *                     behaviour, kept: no ray.min_t test inside Intersect, only prim_ids_range of the trace options).
+ *   NRT_PRIM_BOXES    the node-level primitive of the two-level API (NodeBBoxGeometry / NodeBBoxIntersector,
+ *                     examples/nanosg/nanosg.h:447-640): data = {bmin.xyz, bmax.xyz} per box, stride 24, aux NULL;
+ *                     query with nrt_list_node_intersections.
+ * The tree is built by the production builder over the primitives' boxes (their Prim::BoundingBox). */
+#define NRT_PRIM_SPHERES 1u
+#define NRT_PRIM_BOXES 2u
+int nrt_build_prims(uint32_t kind, const float *data, size_t stride_bytes, const float *aux, uint32_t n_prims,
+                    const void *build_opts_28B, nrt_accel **out);
+/* BVHAccel::ListNodeIntersections (nanort.h:2607-2692) for n rays over a NRT_PRIM_BOXES accel: per ray the (at most
+ * max_intersections <= 64) nearest boxes the ray pierces, nearest first, as records {float t_min, float t_max,
+ * uint32 node_id} at hits_12B[ray * max_intersections + k], k < counts[ray].  Host pointers.
+ * flags: NRT_TRAVERSE_CPP03_INVERSE. */
+int nrt_list_node_intersections(const nrt_accel *a, const void *rays_36B, size_t n_rays, int max_intersections,
+                                void *hits_12B, uint32_t *counts, uint32_t flags);
+
 /* BVHAccel::GetNodes / GetIndices (nanort.h:786-787): host mirror in nanort layout, downloaded on
  * first use and owned by the accel. */
 int nrt_nodes(nrt_accel *a, const void **nodes_40B, size_t *n_nodes, const uint32_t **indices,
@@ -254,6 +277,20 @@ typedef struct nrt_path_result {
 /* d_accum_rgb: DEVICE float[3*width*height], sum over samples of the path radiance (divide by spp). */
 int nrt_render_path_device(const nrt_accel *a, const nrt_path_params *p, float *d_accum_rgb, nrt_path_result *res,
                            void *stream);
+
+
+/* One bounce of that loop on caller-owned DEVICE queues (what nrt_render_path_device repeats max_bounces times): the
+ * n_rays radiance rays {org.xyz,min_t | dir.xyz,max_t} with their path ids (= primary slot of the path under the tile
+ * map of *p, which gives pixel and sample) are traversed and shaded as bounce `bounce` (main.cc:856-976); continuation
+ * rays go to d_out_*, shadow rays {ray, contribution.rgb | pixel} to d_sh_*, d_weight[path id] = {throughput.rgb,
+ * do_emission} is read and updated, emission goes to d_accum_rgb; unless skip_shadow_pass the shadow rays are then
+ * traversed and the unoccluded contributions added to d_accum_rgb (main.cc:940-947, 675-701).  Output queues need
+ * room for n_rays entries.  Synchronises the stream to return the two counts. */
+int nrt_path_bounce_device(const nrt_accel *a, const nrt_path_params *p, uint32_t bounce, uint64_t n_rays,
+                           const void *d_org_tmin, const void *d_dir_tmax, const uint32_t *d_path_id, void *d_weight,
+                           void *d_out_org_tmin, void *d_out_dir_tmax, uint32_t *d_out_path_id, void *d_sh_org_tmin,
+                           void *d_sh_dir_tmax, void *d_sh_contrib_pix, float *d_accum_rgb, uint64_t *n_continue,
+                           uint64_t *n_shadow, int skip_shadow_pass, void *stream);
 
 
 /* ------------------------------------------------------------------ two-level scene (instancing)

@@ -54,6 +54,7 @@ EXPORTS = [
     "nrt_scene_commit", "nrt_scene_free", "nrt_scene_bounding_box", "nrt_scene_nodes", "nrt_scene_instance_state",
     "nrt_scene_traverse", "nrt_scene_traverse_device",
     "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
+    "nrt_path_bounce_device", "nrt_build_prims", "nrt_list_node_intersections",
     "nrt_comm_unique_id", "nrt_comm_init", "nrt_comm_free", "nrt_comm_rank", "nrt_render_ao_sharded",
     "nrt_probe_read_gbs", "nrt_probe_copy_gbs",
 ]
@@ -160,6 +161,10 @@ def lib():
     L.nrt_bounding_box_f64.argtypes = [vp, vp, vp]
     L.nrt_nodes_f64.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
     L.nrt_traverse_f64.argtypes = [vp, vp, sz, vp, vp, vp, u32]
+    L.nrt_path_bounce_device.argtypes = [vp, C.POINTER(PathParams), u32, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                         vp, u64p, u64p, C.c_int, vp]
+    L.nrt_build_prims.argtypes = [u32, vp, sz, vp, u32, vp, C.POINTER(vp)]
+    L.nrt_list_node_intersections.argtypes = [vp, vp, sz, C.c_int, vp, vp, u32]
     L.nrt_comm_unique_id.argtypes = [vp]
     L.nrt_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
     L.nrt_comm_free.argtypes = [vp]
@@ -262,6 +267,11 @@ class Comm:
         _check(lib().nrt_render_ao_sharded(accel._h, self._h, C.byref(params), C.c_void_p(d_frame_full_ptr),
                                            C.byref(res) if want_result else None, C.c_void_p(stream) if stream else None))
         return res if want_result else None
+
+
+PRIM_SPHERES = 1
+PRIM_BOXES = 2
+NODE_HIT_DTYPE = np.dtype([("t_min", np.float32), ("t_max", np.float32), ("node_id", np.uint32)])
 
 
 class PinnedArray:
@@ -419,6 +429,61 @@ class BVHAccel:
                                             C.byref(res) if want_result else None,
                                             C.c_void_p(stream) if stream else None))
         return res
+
+    def BuildSpheres(self, centers, radii, options=None):
+        """BVHAccel::Build(n, SphereGeometry(centers, radii), SpherePred(centers), options) of the reference's
+        particle_primitive model (nrt_build_prims, NRT_PRIM_SPHERES).  Traverse() then returns sphere hit records."""
+        self.free()
+        self._set_device()
+        centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        radii = np.ascontiguousarray(radii, np.float32)
+        assert len(radii) == len(centers)
+        h = C.c_void_p()
+        rc = lib().nrt_build_prims(PRIM_SPHERES, _p(centers), 12, _p(radii), len(radii), _p(options), C.byref(h))
+        if rc != 0:
+            if len(radii) == 0:
+                return False
+            _check(rc)
+        self._h = h
+        self._keep = (centers, radii)
+        return True
+
+    def BuildBoxes(self, boxes6, options=None):
+        """A tree over axis-aligned boxes {bmin, bmax} (the node-level primitive of the two-level API); query with
+        ListNodeIntersections()."""
+        self.free()
+        self._set_device()
+        boxes6 = np.ascontiguousarray(boxes6, np.float32).reshape(-1, 6)
+        h = C.c_void_p()
+        rc = lib().nrt_build_prims(PRIM_BOXES, _p(boxes6), 24, None, len(boxes6), _p(options), C.byref(h))
+        if rc != 0:
+            if len(boxes6) == 0:
+                return False
+            _check(rc)
+        self._h = h
+        return True
+
+    def ListNodeIntersections(self, rays, max_intersections=64, flags=0):
+        """BVHAccel::ListNodeIntersections for every ray: (hits[n, max], counts[n]); hits[i, :counts[i]] nearest first."""
+        rays = np.ascontiguousarray(rays)
+        n = len(rays)
+        hits = np.zeros((n, max_intersections), NODE_HIT_DTYPE)
+        counts = np.zeros(n, np.uint32)
+        _check(lib().nrt_list_node_intersections(self._h, _p(rays), n, int(max_intersections), _p(hits), _p(counts), int(flags)))
+        return hits, counts
+
+    def PathBounce(self, params: PathParams, bounce, n_rays, d_org_tmin, d_dir_tmax, d_path_id, d_weight, d_out_org_tmin,
+                   d_out_dir_tmax, d_out_path_id, d_sh_org_tmin, d_sh_dir_tmax, d_sh_contrib_pix, d_accum_rgb,
+                   skip_shadow_pass=False, stream=None):
+        """nrt_path_bounce_device: one bounce on caller-owned device queues; returns (n_continue, n_shadow)."""
+        nc, ns = C.c_uint64(0), C.c_uint64(0)
+        vp = C.c_void_p
+        _check(lib().nrt_path_bounce_device(self._h, C.byref(params), int(bounce), int(n_rays), vp(d_org_tmin), vp(d_dir_tmax),
+                                            vp(d_path_id), vp(d_weight), vp(d_out_org_tmin), vp(d_out_dir_tmax),
+                                            vp(d_out_path_id), vp(d_sh_org_tmin), vp(d_sh_dir_tmax), vp(d_sh_contrib_pix),
+                                            vp(d_accum_rgb), C.byref(nc), C.byref(ns), 1 if skip_shadow_pass else 0,
+                                            vp(stream) if stream else None))
+        return int(nc.value), int(ns.value)
 
     def RenderAO(self, params: AoParams, d_accum_ptr, stream=None, want_result=True):
         res = AoResult()

@@ -49,6 +49,8 @@ static void destroy(Accel *a) {
   cudaFree(a->d_tris);
   cudaFree(a->d_pair);
   cudaFree(a->d_tris_cm);
+  cudaFree(a->d_prim_boxes);
+  cudaFree(a->d_prim_data);
   cudaFree(a->d_wave);
   cudaFree(a->d_counters);
   for (int i = 0; i < 3; i++) {

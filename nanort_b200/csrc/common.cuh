@@ -124,6 +124,9 @@ struct Accel {
   // when set, the primitives of this accel are n_prims axis-aligned boxes (6 floats each: bmin, bmax) instead of
   // triangles -- the top-level tree of a two-level scene; such an accel has no private traversal layout
   float *d_prim_boxes = nullptr;
+  // 0 = triangles; NRT_PRIM_SPHERES / NRT_PRIM_BOXES: primitives of another kind built through their boxes (prims.cu)
+  int prim_kind = 0;
+  void *d_prim_data = nullptr;  // spheres: float4 {center.xyz, radius} per primitive
   // device: private traversal layout
   WideNode *d_wide = nullptr;
   PackedTri *d_tris = nullptr;
@@ -231,6 +234,10 @@ int derive_private_layout(Accel *a, cudaStream_t s);
 int build_on_device(Accel *a, cudaStream_t s);
 // build_ref.cu
 int build_reference_tree_on_device(Accel *a, bool cpp11_order, cudaStream_t s);
+
+// prims.cu
+int launch_traverse_prims(const Accel *a, const Ray36 *d_rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
+                          const TraceOptions16 &opt, uint32_t flags, cudaStream_t s);
 
 int device_sm_count(int device);
 // api.cu: structure check of a foreign nanort-layout tree (see there); fills the statistics

@@ -5,6 +5,7 @@
 // traversal launches (radiance rays, shadow rays) -- the two Traverse calls per bounce of the reference
 // (main.cc:854 and :696).
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 #include "wavefront.cuh"
@@ -201,4 +202,66 @@ extern "C" int nrt_render_path_device(const nrt_accel *h, const nrt_path_params 
   if (e_begin) cudaEventDestroy(e_begin);
   if (e_end) cudaEventDestroy(e_end);
   return rc;
+}
+
+
+// One bounce of the wavefront path tracer on caller-owned queues: traverses the n radiance rays, runs the reference's
+// per-hit shading block in the retire step (PathShadeEpilogue), appends the continuation rays and the shadow (next-event)
+// rays to the caller's output queues, then -- unless skip_shadow_pass -- traverses the shadow rays and accumulates the
+// light samples that are not occluded.  This is the unit nrt_render_path_device repeats; it is exported for renderers
+// that own the bounce loop, and it is what tests/test_gpu_path.py checks bounce by bounce against the reference's own
+// functions (oracle/pt_ref_shim.cc).
+extern "C" int nrt_path_bounce_device(const nrt_accel *h, const nrt_path_params *pp, uint32_t bounce, uint64_t n_rays,
+                                      const void *d_org_tmin, const void *d_dir_tmax, const uint32_t *d_path_id,
+                                      void *d_weight, void *d_out_org_tmin, void *d_out_dir_tmax, uint32_t *d_out_path_id,
+                                      void *d_sh_org_tmin, void *d_sh_dir_tmax, void *d_sh_contrib_pix, float *d_accum_rgb,
+                                      uint64_t *n_continue, uint64_t *n_shadow, int skip_shadow_pass, void *stream) {
+  if (!h || !pp || !d_org_tmin || !d_dir_tmax || !d_path_id || !d_weight || !d_out_org_tmin || !d_out_dir_tmax ||
+      !d_out_path_id || !d_sh_org_tmin || !d_sh_dir_tmax || !d_sh_contrib_pix || !d_accum_rgb) {
+    set_error("nrt_path_bounce_device: NULL argument");
+    return NRT_ERR_INVALID;
+  }
+  Accel *a = const_cast<Accel *>(reinterpret_cast<const Accel *>(h));
+  const nrt_path_params p = *pp;
+  if (p.width == 0 || p.height == 0 || p.spp == 0 || p.n_shards == 0 || p.shard >= p.n_shards || p.tile_w == 0 ||
+      p.tile_h == 0 || (p.tile_w % 8) != 0 || (p.tile_h % 4) != 0 || p.max_bounces == 0 || p.n_materials == 0 ||
+      !p.d_materials || (p.n_emissive > 0 && !p.d_emissive_faces)) {
+    set_error("nrt_path_bounce_device: bad parameters");
+    return NRT_ERR_INVALID;
+  }
+  if (n_continue) *n_continue = 0;
+  if (n_shadow) *n_shadow = 0;
+  if (n_rays == 0) return NRT_OK;
+  NRT_DEVICE(a->device);
+  std::lock_guard<std::mutex> lock(a->host_mu);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PathQueues q;
+  q.org_tmin[0] = static_cast<float4 *>(const_cast<void *>(d_org_tmin));
+  q.dir_tmax[0] = static_cast<float4 *>(const_cast<void *>(d_dir_tmax));
+  q.path_id[0] = const_cast<uint32_t *>(d_path_id);
+  q.org_tmin[1] = static_cast<float4 *>(d_out_org_tmin);
+  q.dir_tmax[1] = static_cast<float4 *>(d_out_dir_tmax);
+  q.path_id[1] = d_out_path_id;
+  q.sh_org_tmin = static_cast<float4 *>(d_sh_org_tmin);
+  q.sh_dir_tmax = static_cast<float4 *>(d_sh_dir_tmax);
+  q.sh_contrib_pix = static_cast<float4 *>(d_sh_contrib_pix);
+  q.weight = static_cast<float4 *>(d_weight);
+  unsigned long long *ctr = reinterpret_cast<unsigned long long *>(a->d_counters) + 48;  // [0] cont, [1] shadow, [3] n
+  const unsigned long long init[4] = {0ull, 0ull, 0ull, (unsigned long long)n_rays};
+  NRT_CUDA(cudaMemcpyAsync(ctr, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  const TraceOptions16 opt = default_trace_options();
+  const uint32_t trav_flags = p.flags & 0xFFFFu;
+  PathShadeEpilogue epi{p, 0ull, 0, bounce, q, a->d_verts, a->d_faces, d_accum_rgb, ctr};
+  int rc = launch_traverse_path_radiance(a, epi, ctr + 3, (size_t)n_rays, opt, trav_flags, s);
+  if (rc != NRT_OK) return rc;
+  if (!skip_shadow_pass) {
+    rc = launch_traverse_path_shadow(a, q, ctr + 1, (size_t)n_rays, d_accum_rgb, opt, trav_flags, s);
+    if (rc != NRT_OK) return rc;
+  }
+  unsigned long long out[2] = {0, 0};
+  NRT_CUDA(cudaMemcpyAsync(out, ctr, sizeof(out), cudaMemcpyDeviceToHost, s));
+  NRT_CUDA(cudaStreamSynchronize(s));
+  if (n_continue) *n_continue = out[0];
+  if (n_shadow) *n_shadow = out[1];
+  return NRT_OK;
 }

@@ -548,6 +548,7 @@ static int launch_conf(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
 int launch_traverse(const Accel *a, const Ray36 *d_rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
                     const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   if (n == 0) return NRT_OK;
+  if (a->prim_kind != 0) return launch_traverse_prims(a, d_rays, n, d_hits, d_mask, opt, flags, s);  // spheres ...
   AosRays r{d_rays};
   if (flags & NRT_TRAVERSE_CONFORMANCE) return launch_conf<AosRays, false>(a, r, n, d_hits, d_mask, opt, flags, nullptr, s);
   return launch_fast<AosRays, false>(a, r, n, d_hits, d_mask, opt, flags, nullptr, s);

@@ -417,7 +417,12 @@ struct PathShadeEpilogue {
             nz *= il;
           }
         } else {
+          // no normals given: the flat normal the example's loader stores for such a mesh, calcNormal's
+          // cross(v2 - v0, v1 - v0) (main.cc:306-312, 566-601) -- the opposite of cross(e1, e2)
           geometric_normal(verts, faces, prim, nx, ny, nz, a2);
+          nx = -nx;
+          ny = -ny;
+          nz = -nz;
         }
         const float onx = nx, ony = ny, onz = nz;  // originalNorm
         const float ndotd = nx * d.x + ny * d.y + nz * d.z;
@@ -479,14 +484,17 @@ struct PathShadeEpilogue {
               float lx = c0 * v0[0] + c1 * v1[0] + c2 * v2[0] - Px, ly = c0 * v0[1] + c1 * v1[1] + c2 * v2[1] - Py,
                     lz = c0 * v0[2] + c1 * v1[2] + c2 * v2[2] - Pz;
               const float dist = sqrtf(lx * lx + ly * ly + lz * lz);
-              if (dist > 0.000001f && area > 0.0f) {
+              if (dist > 0.000001f) {
                 const float id = 1.0f / dist;
                 lx *= id;
                 ly *= id;
                 lz *= id;
+                // The reference traces the shadow ray whenever the solid-angle pdf is positive -- also when the light
+                // faces away (cosAtLight = 0 makes PdfAtoW infinite and the contribution exactly 0, main.cc:381-390,
+                // 943-950): those Traverse calls are part of its loop, so they are part of ours.
                 const float cos_l = fmaxf(-(lx * lnx + ly * lny + lz * lnz), 0.0f);
-                if (cos_l > 0.0f) {
-                  const float pdf = (1.0f / nf) * (1.0f / area) * (dist * dist) / cos_l;  // PdfAtoW
+                const float pdf = (1.0f / nf) * (1.0f / area) * (dist * dist) / fabsf(cos_l);  // PdfAtoW
+                if (pdf > 0.0f) {
                   const float cos_t = fabsf(lx * nx + ly * ny + lz * nz);
                   const float k = (1.0f / 3.14159265358979f) * cos_l * cos_t / pdf;  // brdf * cosine EDF * cos / pdf
                   so = make_float4(Px, Py, Pz, 0.00001f);

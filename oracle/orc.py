@@ -577,3 +577,106 @@ class ReferenceF64:
         if acc:
             acc._keep = (nodes, indices)
         return acc
+
+
+class ReferencePathTracer:
+    """The reference path tracer's own shading functions (oracle/_ref/libpt_ref.so = the unmodified
+    examples/path_tracer/main.cc behind oracle/pt_ref_shim.cc): MeshLight, sampleDirect, directionCosTheta,
+    fresnel_schlick, reflect, refract ... driven one bounce at a time with caller-supplied random numbers."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libpt_ref.so"))
+
+    def __init__(self, verts, faces, material_ids, materials16, facevarying_normals=None):
+        L = C.CDLL(os.path.join(HERE, "_ref", "libpt_ref.so"))
+        vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
+        L.pt_ref_scene.restype = vp
+        L.pt_ref_scene.argtypes = [vp, sz, vp, sz, vp, vp, vp, sz]
+        L.pt_ref_scene_free.argtypes = [vp]
+        L.pt_ref_emissive_faces.restype = sz
+        L.pt_ref_emissive_faces.argtypes = [vp, vp, sz]
+        L.pt_ref_face_normals.argtypes = [vp, vp, sz, vp]
+        L.pt_ref_unexpected_draws.restype = C.c_long
+        L.pt_ref_shade.argtypes = [vp, sz, u32, u32] + [vp] * 15
+        self.L = L
+        self.verts = np.ascontiguousarray(verts, np.float32)
+        self.faces = np.ascontiguousarray(faces, np.uint32)
+        self.ids = np.ascontiguousarray(material_ids, np.uint32)
+        self.mats = np.ascontiguousarray(np.asarray(materials16).view(np.float32).reshape(-1, 16))
+        if facevarying_normals is None:  # what the example's loader does for an OBJ without normals (calcNormal)
+            fvn = np.zeros((len(self.faces), 9), np.float32)
+            L.pt_ref_face_normals(self.verts.ctypes.data, self.faces.ctypes.data, len(self.faces), fvn.ctypes.data)
+            facevarying_normals = fvn
+        self.fvn = np.ascontiguousarray(facevarying_normals, np.float32)
+        self.h = L.pt_ref_scene(self.verts.ctypes.data, len(self.verts), self.faces.ctypes.data, len(self.faces),
+                                self.ids.ctypes.data, self.fvn.ctypes.data, self.mats.ctypes.data, len(self.mats))
+
+    def __del__(self):
+        try:
+            self.L.pt_ref_scene_free(self.h)
+        except Exception:
+            pass
+
+    def emissive_faces(self):
+        out = np.zeros(len(self.faces), np.uint32)
+        n = self.L.pt_ref_emissive_faces(self.h, out.ctypes.data, len(out))
+        return out[:n].copy()
+
+    def shade(self, bounce, max_bounces, org, dir, hit_uvt, hit_prim, weight_in, draws):
+        """One bounce of main.cc's per-hit block for rays that hit; see oracle/pt_ref_shim.cc:pt_ref_shade."""
+        n = len(hit_prim)
+        f32 = lambda a, w: np.ascontiguousarray(a, np.float32).reshape(n, w)
+        org, dir, hit_uvt, weight_in, draws = f32(org, 3), f32(dir, 3), f32(hit_uvt, 3), f32(weight_in, 4), f32(draws, 6)
+        hit_prim = np.ascontiguousarray(hit_prim, np.uint32)
+        out = {"flags": np.zeros(n, np.uint32), "next_org": np.zeros((n, 3), np.float32), "next_dir": np.zeros((n, 3), np.float32),
+               "weight": np.zeros((n, 4), np.float32), "shadow_org": np.zeros((n, 3), np.float32),
+               "shadow_dir": np.zeros((n, 3), np.float32), "shadow_max_t": np.zeros(n, np.float32),
+               "shadow_contrib": np.zeros((n, 3), np.float32), "emission": np.zeros((n, 3), np.float32)}
+        before = self.L.pt_ref_unexpected_draws()
+        self.L.pt_ref_shade(self.h, n, int(bounce), int(max_bounces), org.ctypes.data, dir.ctypes.data, hit_uvt.ctypes.data,
+                            hit_prim.ctypes.data, weight_in.ctypes.data, draws.ctypes.data, out["flags"].ctypes.data,
+                            out["next_org"].ctypes.data, out["next_dir"].ctypes.data, out["weight"].ctypes.data,
+                            out["shadow_org"].ctypes.data, out["shadow_dir"].ctypes.data, out["shadow_max_t"].ctypes.data,
+                            out["shadow_contrib"].ctypes.data, out["emission"].ctypes.data)
+        assert self.L.pt_ref_unexpected_draws() == before, "the reference drew a random number the harness did not queue"
+        return out
+
+
+class ReferenceSpheres:
+    """The reference's custom-primitive model (oracle/_ref/libprim_ref.so = the unmodified
+    examples/particle_primitive/main.cc: SphereGeometry, SpherePred, SphereIntersector) on the unmodified BVHAccel."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libprim_ref.so"))
+
+    def __init__(self, centers, radii):
+        L = C.CDLL(os.path.join(HERE, "_ref", "libprim_ref.so"))
+        L.refsph_build.restype = C.c_void_p
+        L.refsph_build.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.refsph_free.argtypes = [C.c_void_p]
+        L.refsph_bounding_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refsph_traverse.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        self.L = L
+        self.centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        self.radii = np.ascontiguousarray(radii, np.float32)
+        self.h = L.refsph_build(_p(self.centers), _p(self.radii), len(self.radii))
+        assert self.h, "reference Build returned false"
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refsph_free(self.h)
+            self.h = None
+
+    def bounding_box(self):
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self.L.refsph_bounding_box(self.h, _p(a), _p(b))
+        return a, b
+
+    def traverse(self, rays, prim_range=(0, 0x7FFFFFFF), threads=8):
+        rays = np.ascontiguousarray(rays)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        mask = np.zeros(len(rays), np.uint8)
+        self.L.refsph_traverse(self.h, _p(rays), len(rays), _p(hits), _p(mask), int(prim_range[0]), int(prim_range[1]), int(threads))
+        return hits, mask

@@ -143,3 +143,19 @@ def test_reference_objrender_program_renders_the_reference_image(tmp_path):
               f"({512 * 512 / max(float(render[-1].split()[1]), 1e-9) / 1e6 if render else 0:.3f} Mrays/s per-ray Traverse)")
     assert imgs["b200"][0] == imgs["ref"][0], "render.exr differs from the reference program's"
     assert imgs["b200"][1] == imgs["ref"][1], "render.png differs from the reference program's"
+
+
+def test_reference_particle_primitive_program_renders_the_reference_image(tmp_path):
+    """The reference's custom-primitive example (examples/particle_primitive/main.cc, unmodified: its own SphereGeometry,
+    SpherePred and SphereIntersector classes handed to BVHAccel::Build / Traverse) compiled against include/nanort.h runs
+    its spheres on the device kind NRT_PRIM_SPHERES and must write the image the reference header's build writes."""
+    exe_b, exe_r = os.path.join(BIN, "ref_particle_b200"), os.path.join(BIN, "ref_particle_ref")
+    if not (os.path.exists(exe_b) and os.path.exists(exe_r)):
+        pytest.skip("reference example binaries were not built (authoring container without /root/reference)")
+    imgs = {}
+    for tag, exe in (("b200", exe_b), ("ref", exe_r)):
+        d = tmp_path / tag
+        d.mkdir()
+        subprocess.run([exe], cwd=d, check=True, capture_output=True, text=True, timeout=900)
+        imgs[tag] = open(d / "render.png", "rb").read()
+    assert imgs["b200"] == imgs["ref"], "render.png differs from the reference program's"
