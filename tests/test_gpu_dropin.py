@@ -156,6 +156,6 @@ def test_reference_particle_primitive_program_renders_the_reference_image(tmp_pa
     for tag, exe in (("b200", exe_b), ("ref", exe_r)):
         d = tmp_path / tag
         d.mkdir()
-        subprocess.run([exe], cwd=d, check=True, capture_output=True, text=True, timeout=900)
+        subprocess.run([exe, "2000"], cwd=d, check=True, capture_output=True, text=True, timeout=900)  # argv[1] = number of spheres
         imgs[tag] = open(d / "render.png", "rb").read()
     assert imgs["b200"] == imgs["ref"], "render.png differs from the reference program's"
