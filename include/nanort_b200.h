@@ -156,6 +156,17 @@ int nrt_traverse_count_device(const nrt_accel *a, const void *d_rays_36B, size_t
                               const void *trace_opts_16B, uint32_t flags, uint64_t *boxes_tested,
                               uint64_t *prims_tested, void *stream);
 
+/*
+ * Profiling aid (not timed anywhere): the same counting walk, returning how the 32 lanes of the persistent warps
+ * spent their steps.  stats16 (host): [0] boxes tested, [1] triangles tested, [2] refill events, [3] lanes refilled,
+ * [4] node-phase warp steps, and summed over those steps the lanes [5] testing a child pair, [6] without a ray,
+ * [7] whose ray has finished and waits for the retire step, [8] parked on postponed leaves; [9] leaf-phase rounds,
+ * [10] lanes entering a round with a leaf, [11] triangle-test warp steps, [12] retire events, [13] lanes retired,
+ * [14] outer iterations, [15] reserved.  Explains smsp__thread_inst_executed_per_inst_executed in the ncu captures.
+ */
+int nrt_traverse_lane_stats_device(const nrt_accel *a, const void *d_rays_36B, size_t n_rays,
+                                   const void *trace_opts_16B, uint32_t flags, uint64_t *stats16, void *stream);
+
 /* Measured roofs for benchmark reports (bench.py's roofline block), same process / device / clocks as the traversal:
  * streaming read bandwidth over `bytes` of device memory with 16-byte loads (<= ~64 MB: L2-resident after the warm-up
  * pass -> L2 roof; >= 1 GB -> HBM roof), and the pinned host <-> device copy rate (direction 0 = H2D, 1 = D2H).

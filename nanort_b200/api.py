@@ -56,7 +56,7 @@ EXPORTS = [
     "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
     "nrt_path_bounce_device", "nrt_build_prims", "nrt_list_node_intersections",
     "nrt_comm_unique_id", "nrt_comm_init", "nrt_comm_free", "nrt_comm_rank", "nrt_render_ao_sharded",
-    "nrt_probe_read_gbs", "nrt_probe_copy_gbs",
+    "nrt_probe_read_gbs", "nrt_probe_copy_gbs", "nrt_traverse_lane_stats_device",
 ]
 
 
@@ -138,6 +138,7 @@ def lib():
     L.nrt_traverse.argtypes = [vp, vp, sz, vp, vp, vp, u32]
     L.nrt_traverse_device.argtypes = [vp, vp, sz, vp, vp, vp, u32, vp]
     L.nrt_traverse_count_device.argtypes = [vp, vp, sz, vp, u32, u64p, u64p, vp]
+    L.nrt_traverse_lane_stats_device.argtypes = [vp, vp, sz, vp, u32, u64p, vp]
     L.nrt_host_alloc.argtypes = [sz]
     L.nrt_host_alloc.restype = vp
     L.nrt_host_free.argtypes = [vp]
@@ -413,6 +414,17 @@ class BVHAccel:
         _check(lib().nrt_traverse_count_device(self._h, C.c_void_p(d_rays_ptr), int(n), _p(options), int(flags),
                                                C.byref(b), C.byref(p), C.c_void_p(stream) if stream else None))
         return b.value, p.value
+
+    LANE_STAT_NAMES = ("boxes", "prims", "refill_events", "lanes_refilled", "node_steps", "lanes_testing", "lanes_no_ray",
+                       "lanes_finished", "lanes_parked_on_leaves", "leaf_rounds", "lanes_with_leaf", "tri_steps",
+                       "retire_events", "lanes_retired", "outer_iterations", "reserved")
+
+    def LaneStatsDevice(self, d_rays_ptr, n, options=None, flags=TRAVERSE_FAST, stream=None):
+        """How the persistent warps' lanes spent their steps on these rays (nrt_traverse_lane_stats_device)."""
+        out = (C.c_uint64 * 16)()
+        _check(lib().nrt_traverse_lane_stats_device(self._h, C.c_void_p(d_rays_ptr), int(n), _p(options), int(flags), out,
+                                                    C.c_void_p(stream) if stream else None))
+        return dict(zip(self.LANE_STAT_NAMES, [int(x) for x in out]))
 
     def ExportAOWorkload(self, params: AoParams, d_accum_ptr, d_primary_ptr, d_ao_ptr, stream=None):
         """Same pass, also writing both ray queues as 36-byte rays (nrt_ao_workload_device)."""

@@ -183,8 +183,8 @@ bool validate_foreign_tree64(const void *nodes_64B, size_t n_nodes, const uint32
 
 static int common_init(Accel *a) {
   a->device = g_device;
-  NRT_CUDA(cudaMalloc(&a->d_counters, 64 * sizeof(uint64_t)));
-  NRT_CUDA(cudaMemset(a->d_counters, 0, 64 * sizeof(uint64_t)));
+  NRT_CUDA(cudaMalloc(&a->d_counters, 96 * sizeof(uint64_t)));
+  NRT_CUDA(cudaMemset(a->d_counters, 0, 96 * sizeof(uint64_t)));
   for (int i = 0; i < 3; i++) NRT_CUDA(cudaStreamCreateWithFlags(&a->streams[i], cudaStreamNonBlocking));
   return NRT_OK;
 }
@@ -413,9 +413,9 @@ int nrt_traverse_count_device(const nrt_accel *h, const void *d_rays_36B, size_t
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
   NRT_DEVICE(a->device);
-  std::lock_guard<std::mutex> lock(const_cast<Accel *>(a)->host_mu);  // d_counters[8..9] is per-accel scratch
+  std::lock_guard<std::mutex> lock(const_cast<Accel *>(a)->host_mu);  // d_counters[64..79] is per-accel scratch
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  uint64_t *d_counts = a->d_counters + 8;
+  uint64_t *d_counts = a->d_counters + 64;
   int rc = launch_traverse_count(a, static_cast<const Ray36 *>(d_rays_36B), n_rays, opt, flags, d_counts, s);
   if (rc != NRT_OK) return rc;
   uint64_t hc[2] = {0, 0};
@@ -423,6 +423,26 @@ int nrt_traverse_count_device(const nrt_accel *h, const void *d_rays_36B, size_t
   NRT_CUDA(cudaStreamSynchronize(s));
   if (boxes_tested) *boxes_tested = hc[0];
   if (prims_tested) *prims_tested = hc[1];
+  return NRT_OK;
+}
+
+int nrt_traverse_lane_stats_device(const nrt_accel *h, const void *d_rays_36B, size_t n_rays, const void *trace_opts_16B,
+                                   uint32_t flags, uint64_t *stats16, void *stream) {
+  if (!h || !stats16 || (n_rays && !d_rays_36B)) {
+    g_err = "nrt_traverse_lane_stats_device: NULL argument";
+    return NRT_ERR_INVALID;
+  }
+  const Accel *a = reinterpret_cast<const Accel *>(h);
+  TraceOptions16 opt = default_trace_options();
+  if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
+  NRT_DEVICE(a->device);
+  std::lock_guard<std::mutex> lock(const_cast<Accel *>(a)->host_mu);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint64_t *d_counts = a->d_counters + 64;
+  int rc = launch_traverse_count(a, static_cast<const Ray36 *>(d_rays_36B), n_rays, opt, flags, d_counts, s);
+  if (rc != NRT_OK) return rc;
+  NRT_CUDA(cudaMemcpyAsync(stats16, d_counts, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  NRT_CUDA(cudaStreamSynchronize(s));
   return NRT_OK;
 }
 

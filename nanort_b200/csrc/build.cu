@@ -40,6 +40,8 @@ namespace {
 
 constexpr int kSubtree = 128;     // phase B handles nodes with at most this many primitives (one warp each)
 constexpr int kSubWarps = 4;      // warps (= subtrees) per phase-B CTA
+constexpr int kSubStack = 8;      // log2(kSubtree) + 1 parked nodes per subtree
+constexpr uint32_t kDeadNode = 0xFFFFFFFFu;  // BNode.depth of a reserved but unused pool slot
 
 // ------------------------------------------------------------------ primitives
 // plo = (bmin.xyz, c.x), phi = (bmax.xyz, c.y), pcz = c.z
@@ -434,7 +436,10 @@ struct WarpSub {
   float4 phi[kSubtree];
   float pcz[kSubtree];
   uint32_t gslot[kSubtree];  // global primitive slot of local primitive i
-  uint32_t stack[kSubtree];  // pool ids of nodes still to split
+  // nodes still to split, as full descriptors {pool id, lo | n << 16, depth, rturns, box[6]}: the larger child is
+  // parked and the smaller one split next, so the stack never holds more than log2(kSubtree) entries -- and no
+  // split waits for a node record to come back from global memory
+  uint32_t stack[kSubStack][10];
   uint16_t ids[kSubtree];    // current order (local ids) of the subtree's range
   uint16_t tmp[kSubtree];
 };
@@ -463,14 +468,39 @@ __global__ void __launch_bounds__(kSubWarps * 32)
     S.pcz[i] = pcz[s];
     S.ids[i] = (uint16_t)i;
   }
-  int sp = 1;  // warp-uniform register copy of the stack pointer
-  if (lane == 0) S.stack[0] = root;
+  // Pool ids are reserved a chunk at a time (one atomic per chunk instead of one per split; pre-order indices are
+  // computed in closed form later, so pool order is free).  First chunk: `total` slots, enough whenever the leaves
+  // hold two primitives on average; what a subtree leaves unused is marked dead for phase C.
+  uint32_t id_next = 0, id_end = 0;
+  {
+    const uint32_t want = (total + 1u) & ~1u;
+    if (lane == 0) id_next = atomicAdd(&ctr->pool, want);
+    id_next = __shfl_sync(0xFFFFFFFFu, id_next, 0);
+    id_end = id_next + want;
+  }
+  // a subtree of t primitives has at most 2t - 2 nodes below its root; reservations never exceed that, which keeps
+  // the whole pool within its 2n slots (want <= 2t - 2 for t >= 2)
+  uint32_t id_cap_left = 2u * total - 2u - (id_end - id_next);
+  // the node being split: warp-uniform registers
+  struct Cur {
+    uint32_t nid, lo, n, depth, rturns;
+    float bmin[3], bmax[3];
+  } nd;
+  nd.nid = root;
+  nd.lo = 0;
+  nd.n = total;
+  nd.depth = rootn.depth;
+  nd.rturns = rootn.rturns;
+  for (int k = 0; k < 3; k++) {
+    nd.bmin[k] = rootn.bmin[k];
+    nd.bmax[k] = rootn.bmax[k];
+  }
+  int sp = 0;  // warp-uniform
   __syncwarp();
 
-  while (sp > 0) {
-    const uint32_t nid = S.stack[--sp];
-    const BNode nd = pool[nid];
-    const uint32_t lo = nd.l - base, n = nd.r - nd.l;
+  for (;;) {
+    const uint32_t nid = nd.nid;
+    const uint32_t lo = nd.lo, n = nd.n;
     const bool small = n <= 32u;
     const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
                          inv_extent(nd.bmin[2], nd.bmax[2], B)};
@@ -654,18 +684,24 @@ __global__ void __launch_bounds__(kSubWarps * 32)
       for (uint32_t i = lane; i < n; i += 32) S.ids[lo + i] = S.tmp[lo + i];
     }
     // ---- children
-    uint32_t left = 0;
-    if (lane == 0) left = atomicAdd(&ctr->pool, 2u);
-    left = __shfl_sync(0xFFFFFFFFu, left, 0);
+    if (id_next + 2u > id_end) {  // chunk used up (rare): reserve another one
+      const uint32_t chunk = id_cap_left < 32u ? id_cap_left : 32u;
+      uint32_t more = 0;
+      if (lane == 0) more = atomicAdd(&ctr->pool, chunk);
+      id_next = __shfl_sync(0xFFFFFFFFu, more, 0);
+      id_end = id_next + chunk;
+      id_cap_left -= chunk;
+    }
+    const uint32_t left = id_next;
+    id_next += 2u;
     const uint32_t cdepth = nd.depth + 1;
     const uint32_t n_side[2] = {nl, n - nl};
-    if (lane == 0) {
-      BNode me = nd;
-      me.left = left;
-      me.axis = (uint32_t)(median ? (ax + 2) % 3 : ax);
-      me.split_bin = median ? kMedian : (uint32_t)cut[ax];
-      me.nleft = nl;
-      pool[nid] = me;
+    if (lane == 0) {  // the parent's record is complete now; its range, box, depth and right turns were written by its parent
+      BNode *me = pool + nid;
+      me->left = left;
+      me->axis = (uint32_t)(median ? (ax + 2) % 3 : ax);
+      me->split_bin = median ? kMedian : (uint32_t)cut[ax];
+      me->nleft = nl;
     }
     if (lane < 2) {
       const int side = lane;
@@ -675,8 +711,8 @@ __global__ void __launch_bounds__(kSubWarps * 32)
         c.bmin[k] = bx.v[k];
         c.bmax[k] = bx.v[3 + k];
       }
-      c.l = side ? nd.l + nl : nd.l;
-      c.r = side ? nd.r : nd.l + nl;
+      c.l = base + lo + (side ? nl : 0u);
+      c.r = base + lo + (side ? n : nl);
       c.left = kInactive;
       c.depth = cdepth;
       c.rturns = nd.rturns + (uint32_t)side;
@@ -687,15 +723,53 @@ __global__ void __launch_bounds__(kSubWarps * 32)
       c.pad = 0;
       pool[left + side] = c;
     }
-    // right first, so that the left child is split next (all lanes track sp identically)
-    for (int side = 1; side >= 0; side--) {
-      if (child_class(n_side[side], cdepth, min_leaf, max_depth) != 0) {
-        if (lane == 0) S.stack[sp] = left + side;
+    // next node: a child that still splits (the smaller one first, the other parked), else a parked node
+    const bool more0 = child_class(n_side[0], cdepth, min_leaf, max_depth) != 0;
+    const bool more1 = child_class(n_side[1], cdepth, min_leaf, max_depth) != 0;
+    if (more0 || more1) {
+      const int go = (more0 && more1) ? (n_side[1] < n_side[0] ? 1 : 0) : (more1 ? 1 : 0);
+      if (more0 && more1) {
+        const int park = go ^ 1;
+        const Box6 &pb = park ? rb : lb;
+        if (lane == 0) {
+          uint32_t *e = S.stack[sp];
+          e[0] = left + (uint32_t)park;
+          e[1] = (lo + (park ? nl : 0u)) | (n_side[park] << 16);
+          e[2] = cdepth;
+          e[3] = nd.rturns + (uint32_t)park;
+          for (int k = 0; k < 6; k++) e[4 + k] = __float_as_uint(pb.v[k]);
+        }
         sp++;
+      }
+      const Box6 &gb = go ? rb : lb;
+      nd.nid = left + (uint32_t)go;
+      nd.lo = lo + (go ? nl : 0u);
+      nd.n = n_side[go];
+      nd.depth = cdepth;
+      nd.rturns = nd.rturns + (uint32_t)go;
+      for (int k = 0; k < 3; k++) {
+        nd.bmin[k] = gb.v[k];
+        nd.bmax[k] = gb.v[3 + k];
+      }
+    } else {
+      if (sp == 0) break;
+      --sp;
+      __syncwarp();
+      const uint32_t *e = S.stack[sp];
+      nd.nid = e[0];
+      nd.lo = e[1] & 0xFFFFu;
+      nd.n = e[1] >> 16;
+      nd.depth = e[2];
+      nd.rturns = e[3];
+      for (int k = 0; k < 3; k++) {
+        nd.bmin[k] = __uint_as_float(e[4 + k]);
+        nd.bmax[k] = __uint_as_float(e[7 + k]);
       }
     }
     __syncwarp();
   }
+  // reserved slots this subtree did not need
+  for (uint32_t i = id_next + lane; i < id_end; i += 32) pool[i].depth = kDeadNode;
   // final order of this subtree's range
   for (uint32_t i = lane; i < total; i += 32) idx[base + i] = S.gslot[S.ids[i]];
 }
@@ -705,7 +779,7 @@ __global__ void mark_leaves_kernel(const BNode *__restrict__ pool, uint32_t n_no
                                    BuildCounters *ctr) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t depth = 0, leaf = 0;
-  if (i < n_nodes) {
+  if (i < n_nodes && pool[i].depth != kDeadNode) {
     const BNode nd = pool[i];
     depth = nd.depth;
     if (nd.left == kInactive) {
@@ -729,6 +803,7 @@ __global__ void emit_nodes_kernel(const BNode *__restrict__ pool, uint32_t n_nod
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes) return;
   const BNode nd = pool[i];
+  if (nd.depth == kDeadNode) return;  // reserved by a subtree, never used
   const uint32_t lb = leaves_before[nd.l];
   const uint32_t pre = 2u * lb - nd.rturns + nd.depth;
   Node40 o;
@@ -940,6 +1015,7 @@ int build_on_device(Accel *a, cudaStream_t s) {
   {
     float ms = 0.0f;
     BUILD_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    n_nodes = 2u * hc.n_leaves - 1u;  // live nodes (the pool also holds the slots subtrees reserved and left unused)
     a->n_nodes = n_nodes;
     a->stats.max_tree_depth = hc.max_depth;
     a->stats.num_leaf_nodes = hc.n_leaves;

@@ -303,8 +303,8 @@ int nrt_build_prims(uint32_t kind, const float *data, size_t stride_bytes, const
     set_error("nrt_build_prims: bin_size must be > 1 and max_tree_depth <= 500");
     return fail(NRT_ERR_INVALID);
   }
-  e = cudaMalloc(&a->d_counters, 64 * sizeof(uint64_t));
-  if (e == cudaSuccess) e = cudaMemset(a->d_counters, 0, 64 * sizeof(uint64_t));
+  e = cudaMalloc(&a->d_counters, 96 * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMemset(a->d_counters, 0, 96 * sizeof(uint64_t));
   for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&a->streams[i], cudaStreamNonBlocking);
   cudaStream_t s = a->streams[0];
   if (e == cudaSuccess) e = cudaMalloc(&a->d_prim_boxes, sizeof(float) * 6 * (size_t)n_prims);

@@ -622,7 +622,7 @@ int launch_traverse_path_shadow(const Accel *a, const PathQueues &q, const unsig
 
 int launch_traverse_count(const Accel *a, const Ray36 *d_rays, size_t n, const TraceOptions16 &opt,
                           uint32_t flags, uint64_t *d_counts2, cudaStream_t s) {
-  NRT_CUDA(cudaMemsetAsync(d_counts2, 0, 2 * sizeof(uint64_t), s));
+  NRT_CUDA(cudaMemsetAsync(d_counts2, 0, 16 * sizeof(uint64_t), s));  // [0] boxes, [1] prims, [2..15] lane statistics
   if (n == 0) return NRT_OK;
   AosRays r{d_rays};
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(d_counts2);

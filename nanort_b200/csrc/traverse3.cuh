@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
   int cur = kNone3, leaf = kNone3;
   bool exhausted = false;
   unsigned long long n_boxes = 0, n_prims = 0;
+  // COUNT only: lane-state histogram of the warp's iterations (nrt_traverse_lane_stats_device; lane 0 accumulates)
+  unsigned long long st[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   for (;;) {
     // ---- replace retired rays (warp-ballot compaction of the ray pool)
@@ -184,6 +186,10 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
     if (dead != 0u && !exhausted && (dead == FULL_MASK || __popc(dead) >= P::kRefillMin)) {
       const int cnt = __popc(dead);
       const int leader = __ffs(dead) - 1;
+      if (COUNT) {
+        st[0] += 1;    // refill events
+        st[1] += cnt;  // lanes refilled (incl. lanes past the end of the ray set)
+      }
       unsigned long long base = 0;
       if (lane == leader) base = atomicAdd(cursor, (unsigned long long)cnt);
       base = __shfl_sync(FULL_MASK, base, leader);
@@ -239,6 +245,16 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
             }
           }
         }
+      }
+      if (COUNT) {  // who does what in this warp step
+        const bool fin = alive && cur == kNone3 && leaf == kNone3 && sp == 0;
+        st[2] += 1;                                                  // node-phase warp steps
+        st[3] += __popc(__ballot_sync(FULL_MASK, cur >= 0));          // lanes testing a child pair
+        st[4] += __popc(__ballot_sync(FULL_MASK, !alive));            // lanes without a ray
+        st[5] += __popc(__ballot_sync(FULL_MASK, fin));               // lanes whose ray is finished (waits for the retire step)
+        st[6] += __popc(__ballot_sync(FULL_MASK, alive && !fin && cur < 0));  // lanes parked on leaves
+      }
+      if (want) {
         if (cur >= 0) {
           bool h0, h1;
           float t0, t1;
@@ -282,9 +298,14 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
     // ---- leaves
     for (;;) {
       if (!__any_sync(FULL_MASK, leaf != kNone3)) break;
+      if (COUNT) {
+        st[7] += 1;                                                // leaf-phase rounds
+        st[8] += __popc(__ballot_sync(FULL_MASK, leaf != kNone3));  // lanes that enter a round with a leaf
+      }
       if (leaf != kNone3) {
         uint32_t slot = (uint32_t)(~leaf);
         for (;;) {
+          if (COUNT && lane == __ffs(__activemask()) - 1) st[9] += 1;  // triangle-test warp steps
           const uint32_t s3 = slot * 3u;
           const float4 VX = __ldg(tris4 + (s3 + c.tx));
           const float4 VY = __ldg(tris4 + (s3 + c.ty));
@@ -304,6 +325,14 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
 
     // ---- retire: the epilogue (store the hit / spawn the AO ray / accumulate / shade) runs warp-wide
     const bool retiring = alive && cur == kNone3 && leaf == kNone3 && sp == 0;
+    if (COUNT) {
+      st[12] += 1;  // outer iterations
+      const unsigned rm = __ballot_sync(FULL_MASK, retiring);
+      if (rm) {
+        st[10] += 1;           // retire events
+        st[11] += __popc(rm);  // lanes retiring
+      }
+    }
     if (__any_sync(FULL_MASK, retiring)) {
       size_t ray_idx = 0;
       float max_t = 0.0f;
@@ -330,9 +359,13 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
       n_boxes += __shfl_down_sync(FULL_MASK, n_boxes, o);
       n_prims += __shfl_down_sync(FULL_MASK, n_prims, o);
     }
+    // warp-uniform statistics were added by every lane alike: lane 0's copy is the warp's; st[9] is per lane
+    for (int o = 16; o > 0; o >>= 1) st[9] += __shfl_down_sync(FULL_MASK, st[9], o);
     if (lane == 0) {
       atomicAdd(counts + 0, n_boxes);
       atomicAdd(counts + 1, n_prims);
+#pragma unroll
+      for (int k = 0; k < 14; ++k) atomicAdd(counts + 2 + k, st[k]);
     }
   }
 }

@@ -340,6 +340,26 @@ class PortScene:
         return hits, mask
 
 
+def list_node_intersections_on_tree(port, nodes, indices, sg_nodes, ray, max_hits=64, cpp11=True):
+    """BVHAccel::ListNodeIntersections (restatement pinned to nanosg.h by tests/test_oracle_scene.py) over ANY node
+    array built on the world boxes sg_nodes["xbmin"/"xbmax"] -- e.g. the one a device build produced.  The list is a
+    property of the tree's leaves (NodeBBoxIntersector has no [min_t, max_t] clamp, nanosg.h:597-634: a box behind the
+    origin or beyond max_t is listed iff it shares a leaf with a box the range-clamped node test lets through), so a
+    device list is compared on the device's own tree."""
+    L = port.lib
+    L.orc_sg_list.restype = C.c_int
+    L.orc_sg_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                              C.c_void_p, C.c_void_p]
+    nodes = np.ascontiguousarray(nodes)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    sg_nodes = np.ascontiguousarray(sg_nodes)
+    ray = np.ascontiguousarray(ray).reshape(1)
+    tmin, tmax, ids = np.zeros(128, np.float32), np.zeros(128, np.float32), np.zeros(128, np.uint32)
+    n = L.orc_sg_list(_p(nodes), _p(indices), _p(sg_nodes), _p(ray), max_hits, 1 if cpp11 else 0, _p(tmin), _p(tmax),
+                      _p(ids))
+    return tmin[:n], tmax[:n], ids[:n]
+
+
 class ReferenceScene:
     """The unmodified nanosg::Scene (oracle/_ref/libnanosg_ref*.so)."""
 
