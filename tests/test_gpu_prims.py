@@ -113,6 +113,18 @@ def test_list_node_intersections_matches_the_reference(max_hits):
     dev_nodes, dev_idx = acc.GetNodes(), acc.GetIndices()
     bmin, bmax = boxes[:, :3].min(axis=0), boxes[:, 3:].max(axis=0)
     rays = S.incoherent_rays(bmin - 1, bmax + 1, 3000, seed=4, axis_parallel_fraction=0.25)
+    # rays down the row (both ways, slightly tilted, some starting inside it): these pierce tens of boxes, more than 64
+    # for the long ones, and meet the coincident instances at exactly equal distances
+    k = np.arange(240)
+    down = np.zeros(len(k), S.RAY_DTYPE)
+    fwd = (k % 2) == 0
+    down["org"][:, 0] = np.where(fwd, -2.0 + 0.37 * (k % 60), 82.0 - 0.41 * (k % 50))
+    down["org"][:, 1] = 0.3 * np.sin(k * 0.7)
+    down["org"][:, 2] = 0.3 * np.cos(k * 1.3)
+    d = np.stack([np.where(fwd, 1.0, -1.0), 0.004 * np.sin(k * 2.1), 0.004 * np.cos(k * 0.9)], axis=1)
+    down["dir"] = (d / np.linalg.norm(d, axis=1)[:, None]).astype(np.float32)
+    down["max_t"] = np.where(k % 3 == 0, 30.0, 1e30)
+    rays = np.concatenate([rays, down])
     rays["min_t"] = 0.0
     hits, counts = acc.ListNodeIntersections(rays, max_intersections=max_hits)
     many = tree_independent = 0
