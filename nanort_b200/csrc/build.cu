@@ -444,6 +444,254 @@ struct WarpSub {
   uint16_t tmp[kSubtree];
 };
 
+// Pool ids for one warp's subtree: reserved a chunk at a time (one atomic per chunk instead of one per split; the
+// pre-order indices are computed in closed form in phase C, so pool order is free).  A subtree of t primitives has at
+// most 2t - 2 nodes below its root and the reservations never exceed that, which keeps the whole pool within its 2n
+// slots; what is left of the last chunk is marked dead for phase C.  All members are warp-uniform.
+struct IdChunks {
+  uint32_t next, end, cap_left;  // current chunk [next, end); slots this subtree may still reserve
+  uint32_t next2, end2;          // a second chunk, while a request straddles two
+  __device__ void init(BuildCounters *ctr, uint32_t total, int lane) {
+    const uint32_t want = (total + 1u) & ~1u;  // enough whenever the leaves hold two primitives on average
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&ctr->pool, want);
+    next = __shfl_sync(0xFFFFFFFFu, b, 0);
+    end = next + want;
+    cap_left = 2u * total - 2u - want;  // want <= 2t - 2 for every t >= 2
+    next2 = end2 = 0;
+  }
+  // makes `pairs` child pairs available: pair r lives at id(r), r < pairs; then call commit(pairs)
+  __device__ void ensure(BuildCounters *ctr, uint32_t pairs, int lane) {
+    const uint32_t need = 2u * pairs, avail = end - next;
+    if (need > avail) {
+      uint32_t chunk = need - avail < 32u ? 32u : need - avail;
+      if (chunk > cap_left) chunk = cap_left;
+      uint32_t b = 0;
+      if (lane == 0) b = atomicAdd(&ctr->pool, chunk);
+      next2 = __shfl_sync(0xFFFFFFFFu, b, 0);
+      end2 = next2 + chunk;
+      cap_left -= chunk;
+    }
+  }
+  __device__ uint32_t id(uint32_t r) const {
+    const uint32_t avail = end - next;  // even: ids are handed out in pairs
+    return 2u * r < avail ? next + 2u * r : next2 + (2u * r - avail);
+  }
+  __device__ void commit(uint32_t pairs) {
+    const uint32_t need = 2u * pairs, avail = end - next;
+    if (need <= avail) {
+      next += need;
+    } else {
+      next = next2 + (need - avail);
+      end = end2;
+      next2 = end2 = 0;
+    }
+  }
+};
+
+// the node a warp is splitting: warp-uniform registers
+struct SubNode {
+  uint32_t nid, lo, n, depth, rturns;
+  float bmin[3], bmax[3];
+};
+
+// A node with at most 32 primitives, built to its leaves level by level: one primitive per lane, every node of the
+// current level is a SEGMENT of consecutive lanes, and one pass of segmented warp operations splits them all -- per
+// axis a 32-lane bitonic sort by (segment, bin), prefix / suffix box scans that stop at segment borders, candidates
+// where the bin changes, a segmented argmin.  Same candidates, cost arithmetic and tie rules as the binned sweep
+// (lowest boundary, then lowest axis), so the tree is the one a split-at-a-time build produces; a 32-primitive node
+// takes three passes instead of seven splits.
+__device__ void small_block(const SubNode &root, BNode *pool, BuildCounters *ctr, IdChunks &ids, WarpSub &S, uint32_t base,
+                            int B, uint32_t min_leaf, uint32_t max_depth, int lane) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool valid = (uint32_t)lane < root.n;
+  // segment state, identical in all lanes of a segment (lanes beyond the node: a dead segment of their own)
+  uint32_t seg_start = valid ? 0u : (uint32_t)lane, seg_len = valid ? root.n : 1u;
+  uint32_t seg_nid = root.nid, seg_depth = root.depth, seg_rturns = root.rturns;
+  float sb_min[3] = {root.bmin[0], root.bmin[1], root.bmin[2]}, sb_max[3] = {root.bmax[0], root.bmax[1], root.bmax[2]};
+  uint32_t q = valid ? (uint32_t)S.ids[root.lo + lane] : 0u;
+  for (;;) {
+    const bool active = valid && child_class(seg_len, seg_depth, min_leaf, max_depth) != 0;
+    const unsigned act = __ballot_sync(FULL, active);
+    if (act == 0u) break;
+    const uint32_t seg_end = seg_start + seg_len;
+    Box6 mine;
+    box_empty(mine);
+    float c3[3] = {0.0f, 0.0f, 0.0f};
+    if (valid) {
+      const float4 l4 = S.plo[q], h4 = S.phi[q];
+      mine.v[0] = l4.x, mine.v[1] = l4.y, mine.v[2] = l4.z, mine.v[3] = h4.x, mine.v[4] = h4.y, mine.v[5] = h4.z;
+      c3[0] = l4.w, c3[1] = h4.w, c3[2] = S.pcz[q];
+    }
+    const uint32_t maxlen = __reduce_max_sync(FULL, active ? seg_len : 0u);  // scans need ceil(log2(maxlen)) rounds
+    float best = FLT_MAX;
+    int ax = 0, cutbin = 0;
+    uint32_t nl = 0;
+    Box6 lb, rb;
+    box_empty(lb);
+    box_empty(rb);
+    uint32_t mybin[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float iv = inv_extent(sb_min[a], sb_max[a], B);
+      const uint32_t bin = active ? (uint32_t)bin_of(c3[a], sb_min[a], iv, B) : 0u;
+      mybin[a] = bin;
+      uint32_t key = (seg_start << 13) | (bin << 5) | (uint32_t)lane;  // segments keep their lane ranges
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const uint32_t other = __shfl_xor_sync(FULL, key, j);
+          const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+          key = keep_min ? min(key, other) : max(key, other);
+        }
+      }
+      const int src = (int)(key & 31u);
+      const uint32_t sb = (key >> 5) & 0xFFu;
+      Box6 pre, suf;
+#pragma unroll
+      for (int k = 0; k < 6; k++) pre.v[k] = suf.v[k] = __shfl_sync(FULL, mine.v[k], src);
+      for (uint32_t o = 1; o < maxlen; o <<= 1) {
+        Box6 t, u;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          t.v[k] = __shfl_up_sync(FULL, pre.v[k], o);
+          u.v[k] = __shfl_down_sync(FULL, suf.v[k], o);
+        }
+        if ((uint32_t)lane >= seg_start + o) box_merge(pre, t);
+        if ((uint32_t)lane + o < seg_end) box_merge(suf, u);
+      }
+      Box6 epre;
+#pragma unroll
+      for (int k = 0; k < 6; k++) epre.v[k] = __shfl_up_sync(FULL, pre.v[k], 1);
+      const uint32_t prev_bin = __shfl_up_sync(FULL, sb, 1);
+      const bool cand = active && (uint32_t)lane > seg_start && sb != prev_bin;
+      float bc = FLT_MAX;
+      int bp = 0x7FFFFFFF;
+      if (cand) {
+        bc = (float)((uint32_t)lane - seg_start) * box_area(epre.v[0], epre.v[1], epre.v[2], epre.v[3], epre.v[4], epre.v[5]) +
+             (float)(seg_end - (uint32_t)lane) * box_area(suf.v[0], suf.v[1], suf.v[2], suf.v[3], suf.v[4], suf.v[5]);
+        bp = lane;
+      }
+      // segmented argmin (lowest position among equal costs): inclusive prefix-min, read at the segment's last lane
+      for (uint32_t o = 1; o < maxlen; o <<= 1) {
+        const float oc = __shfl_up_sync(FULL, bc, o);
+        const int op = __shfl_up_sync(FULL, bp, o);
+        if ((uint32_t)lane >= seg_start + o && (oc < bc || (oc == bc && op < bp))) {
+          bc = oc;
+          bp = op;
+        }
+      }
+      bc = __shfl_sync(FULL, bc, (int)(seg_end - 1u));
+      bp = __shfl_sync(FULL, bp, (int)(seg_end - 1u));
+      const int bsrc = bp & 31;  // 0x7FFFFFFF (no candidate) reads lane 31: ignored below
+      const uint32_t cb = __shfl_sync(FULL, prev_bin, bsrc) + 1u;
+      Box6 cl, cr;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        cl.v[k] = __shfl_sync(FULL, epre.v[k], bsrc);
+        cr.v[k] = __shfl_sync(FULL, suf.v[k], bsrc);
+      }
+      if (bc < best) {  // uniform within a segment; strict, so a tie keeps the lower axis
+        best = bc;
+        ax = a;
+        cutbin = (int)cb;
+        nl = (uint32_t)bp - seg_start;
+        lb = cl;
+        rb = cr;
+      }
+    }
+    const bool median = active && !(best < FLT_MAX);
+    if (__any_sync(FULL, median)) {
+      // no plane separates the centroids: cut at the median index of the current order, exact boxes of the halves
+      Box6 pre = mine, suf = mine;
+      for (uint32_t o = 1; o < maxlen; o <<= 1) {
+        Box6 t, u;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          t.v[k] = __shfl_up_sync(FULL, pre.v[k], o);
+          u.v[k] = __shfl_down_sync(FULL, suf.v[k], o);
+        }
+        if ((uint32_t)lane >= seg_start + o) box_merge(pre, t);
+        if ((uint32_t)lane + o < seg_end) box_merge(suf, u);
+      }
+      const uint32_t half = seg_len >> 1;
+      const int ls = (int)((seg_start + half - 1u) & 31u), rs = (int)((seg_start + half) & 31u);
+      Box6 ml, mr;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        ml.v[k] = __shfl_sync(FULL, pre.v[k], ls);
+        mr.v[k] = __shfl_sync(FULL, suf.v[k], rs);
+      }
+      if (median) {
+        nl = half;
+        lb = ml;
+        rb = mr;
+      }
+    }
+    // ---- stable partition inside every segment
+    const uint32_t segmask = (seg_len >= 32u ? 0xFFFFFFFFu : ((1u << seg_len) - 1u)) << seg_start;
+    const uint32_t mb = ax == 0 ? mybin[0] : (ax == 1 ? mybin[1] : mybin[2]);
+    const bool f = median ? ((uint32_t)lane - seg_start) < nl : mb < (uint32_t)cutbin;
+    const unsigned mf = __ballot_sync(FULL, active && f) & segmask, mr_ = __ballot_sync(FULL, active && !f) & segmask;
+    if (active) {
+      const uint32_t pos = f ? seg_start + (uint32_t)__popc(mf & lt) : seg_start + nl + (uint32_t)__popc(mr_ & lt);
+      S.ids[root.lo + pos] = (uint16_t)q;
+    }
+    // ---- node records: the segment's first lane completes the parent and writes the left child, its second lane the
+    // right child (an active segment has at least two primitives)
+    const unsigned leaders = __ballot_sync(FULL, active && (uint32_t)lane == seg_start);
+    const uint32_t pairs = (uint32_t)__popc(leaders);
+    ids.ensure(ctr, pairs, lane);
+    const uint32_t left = ids.id((uint32_t)__popc(leaders & ((seg_start >= 32u ? 0u : (1u << seg_start)) - 1u)));
+    ids.commit(pairs);
+    if (active) {
+      const uint32_t rel = (uint32_t)lane - seg_start;
+      if (rel == 0u) {
+        BNode *me = pool + seg_nid;
+        me->left = left;
+        me->axis = (uint32_t)(median ? (ax + 2) % 3 : ax);
+        me->split_bin = median ? kMedian : (uint32_t)cutbin;
+        me->nleft = nl;
+      }
+      if (rel < 2u) {
+        const Box6 &bx = rel ? rb : lb;
+        BNode c;
+        for (int k = 0; k < 3; k++) {
+          c.bmin[k] = bx.v[k];
+          c.bmax[k] = bx.v[3 + k];
+        }
+        c.l = base + root.lo + seg_start + (rel ? nl : 0u);
+        c.r = base + root.lo + seg_start + (rel ? seg_len : nl);
+        c.left = kInactive;
+        c.depth = seg_depth + 1u;
+        c.rturns = seg_rturns + rel;
+        c.axis = 0;
+        c.split_bin = 0;
+        c.nleft = 0;
+        c.slot = kInactive;
+        c.pad = 0;
+        pool[left + rel] = c;
+      }
+      // the lane now stands for the primitive at ITS position of the new order: which child is that?
+      const uint32_t side = rel < nl ? 0u : 1u;
+      const Box6 &nb = side ? rb : lb;
+      seg_nid = left + side;
+      seg_depth += 1u;
+      seg_rturns += side;
+      seg_len = side ? seg_len - nl : nl;
+      seg_start = side ? seg_start + nl : seg_start;
+      for (int k = 0; k < 3; k++) {
+        sb_min[k] = nb.v[k];
+        sb_max[k] = nb.v[3 + k];
+      }
+    }
+    __syncwarp();
+    if (valid) q = (uint32_t)S.ids[root.lo + lane];
+  }
+}
+
 __global__ void __launch_bounds__(kSubWarps * 32)
     subtree_kernel(BNode *pool, BuildCounters *ctr, const uint32_t *__restrict__ subtrees, uint32_t n_subtrees,
                    uint32_t *__restrict__ idx, const float4 *__restrict__ plo, const float4 *__restrict__ phi,
@@ -468,24 +716,9 @@ __global__ void __launch_bounds__(kSubWarps * 32)
     S.pcz[i] = pcz[s];
     S.ids[i] = (uint16_t)i;
   }
-  // Pool ids are reserved a chunk at a time (one atomic per chunk instead of one per split; pre-order indices are
-  // computed in closed form later, so pool order is free).  First chunk: `total` slots, enough whenever the leaves
-  // hold two primitives on average; what a subtree leaves unused is marked dead for phase C.
-  uint32_t id_next = 0, id_end = 0;
-  {
-    const uint32_t want = (total + 1u) & ~1u;
-    if (lane == 0) id_next = atomicAdd(&ctr->pool, want);
-    id_next = __shfl_sync(0xFFFFFFFFu, id_next, 0);
-    id_end = id_next + want;
-  }
-  // a subtree of t primitives has at most 2t - 2 nodes below its root; reservations never exceed that, which keeps
-  // the whole pool within its 2n slots (want <= 2t - 2 for t >= 2)
-  uint32_t id_cap_left = 2u * total - 2u - (id_end - id_next);
-  // the node being split: warp-uniform registers
-  struct Cur {
-    uint32_t nid, lo, n, depth, rturns;
-    float bmin[3], bmax[3];
-  } nd;
+  IdChunks ids;
+  ids.init(ctr, total, lane);
+  SubNode nd;
   nd.nid = root;
   nd.lo = 0;
   nd.n = total;
@@ -499,121 +732,42 @@ __global__ void __launch_bounds__(kSubWarps * 32)
   __syncwarp();
 
   for (;;) {
-    const uint32_t nid = nd.nid;
-    const uint32_t lo = nd.lo, n = nd.n;
-    const bool small = n <= 32u;
-    const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
-                         inv_extent(nd.bmin[2], nd.bmax[2], B)};
-    // ---- bins (nodes with more than 32 primitives)
-    // nodes with more than 32 primitives (3 of the 31 splits of a full subtree) bin ONE axis at a time into a single
-    // B-bin array -- a third of the shared memory, i.e. half again as many resident warps for the whole kernel
-    auto bin_axis = [&](int a) {
-      for (int i = lane; i < B * kBinWords; i += 32) {
-        const int w = i & (kBinWords - 1);
-        sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
-      }
-      __syncwarp();
-      for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t q = S.ids[lo + i];
-        const float4 l4 = S.plo[q], h4 = S.phi[q];
-        const float c = a == 0 ? l4.w : (a == 1 ? h4.w : S.pcz[q]);
-        uint32_t *w = sbin + (size_t)bin_of(c, nd.bmin[a], iv[a], B) * kBinWords;
-        atomicAdd(w, 1u);
-        atomicMin(w + 1, fkey(l4.x));
-        atomicMin(w + 2, fkey(l4.y));
-        atomicMin(w + 3, fkey(l4.z));
-        atomicMax(w + 4, fkey(h4.x));
-        atomicMax(w + 5, fkey(h4.y));
-        atomicMax(w + 6, fkey(h4.z));
-      }
-      __syncwarp();
-    };
-    // ---- sweep the three axes, pick the split
-    float cost[3];
-    int cut[3];
-    int ax = 0;
-    Box6 lb, rb;
-    uint32_t nl = 0, nr = 0;
-    if (small) {
-      // n <= 32: one primitive per lane, no bins in memory.  Per axis: sort the lanes by bin, scan boxes along the
-      // sorted order; a boundary exists wherever the bin changes, its left count is the sorted position.  Same
-      // candidates, same cost arithmetic and same tie rule (lowest boundary) as the binned sweep below.
-      Box6 mine;
-      box_empty(mine);
-      float c3[3] = {0.0f, 0.0f, 0.0f};
-      const bool valid = (uint32_t)lane < n;
-      if (valid) {
-        const uint32_t q = S.ids[lo + lane];
-        const float4 l4 = S.plo[q], h4 = S.phi[q];
-        mine.v[0] = l4.x, mine.v[1] = l4.y, mine.v[2] = l4.z, mine.v[3] = h4.x, mine.v[4] = h4.y, mine.v[5] = h4.z;
-        c3[0] = l4.w, c3[1] = h4.w, c3[2] = S.pcz[q];
-      }
-      float best = FLT_MAX;
-      cost[0] = cost[1] = cost[2] = FLT_MAX;
-      cut[0] = cut[1] = cut[2] = 0x7FFFFFFF;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        const uint32_t bin = valid ? (uint32_t)bin_of(c3[a], nd.bmin[a], iv[a], B) : 0x03FFFFFFu;
-        uint32_t key = (bin << 5) | (uint32_t)lane;
-#pragma unroll
-        for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-          for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, key, j);
-            const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
-            key = keep_min ? min(key, other) : max(key, other);
-          }
-        }
-        const int src = (int)(key & 31u);
-        const uint32_t sb = key >> 5;
-        Box6 pre, suf;
-#pragma unroll
-        for (int k = 0; k < 6; k++) pre.v[k] = suf.v[k] = __shfl_sync(0xFFFFFFFFu, mine.v[k], src);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          Box6 t, u;
-#pragma unroll
-          for (int k = 0; k < 6; k++) {
-            t.v[k] = __shfl_up_sync(0xFFFFFFFFu, pre.v[k], o);
-            u.v[k] = __shfl_down_sync(0xFFFFFFFFu, suf.v[k], o);
-          }
-          if (lane >= o) box_merge(pre, t);
-          if (lane + o < 32) box_merge(suf, u);
-        }
-        Box6 epre;
-#pragma unroll
-        for (int k = 0; k < 6; k++) epre.v[k] = __shfl_up_sync(0xFFFFFFFFu, pre.v[k], 1);
-        const uint32_t prev_bin = __shfl_up_sync(0xFFFFFFFFu, sb, 1);
-        const bool cand = lane >= 1 && (uint32_t)lane < n && sb != prev_bin;
-        float cst = FLT_MAX;
-        if (cand)
-          cst = (float)lane * box_area(epre.v[0], epre.v[1], epre.v[2], epre.v[3], epre.v[4], epre.v[5]) +
-                (float)(n - (uint32_t)lane) * box_area(suf.v[0], suf.v[1], suf.v[2], suf.v[3], suf.v[4], suf.v[5]);
-        float bc = cst;
-        int bp = cand ? lane : 0x7FFFFFFF;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float oc = __shfl_xor_sync(0xFFFFFFFFu, bc, o);
-          const int op = __shfl_xor_sync(0xFFFFFFFFu, bp, o);
-          if (oc < bc || (oc == bc && op < bp)) {
-            bc = oc;
-            bp = op;
-          }
-        }
-        cost[a] = bc;
-        if (bc < best) {  // warp-uniform; strict, so a tie keeps the lower axis
-          best = bc;
-          ax = a;
-          cut[a] = (int)__shfl_sync(0xFFFFFFFFu, prev_bin, bp) + 1;
-          nl = (uint32_t)bp;
-#pragma unroll
-          for (int k = 0; k < 6; k++) {
-            lb.v[k] = __shfl_sync(0xFFFFFFFFu, epre.v[k], bp);
-            rb.v[k] = __shfl_sync(0xFFFFFFFFu, suf.v[k], bp);
-          }
-        }
-      }
+    bool pop = false;
+    if (nd.n <= 32u) {
+      small_block(nd, pool, ctr, ids, S, base, B, min_leaf, max_depth, lane);
+      pop = true;
     } else {
+      // ---- more than 32 primitives (3 of the 31 splits of a full subtree): bin ONE axis at a time into a single
+      // B-bin array -- a third of the shared memory, i.e. half again as many resident warps for the whole kernel
+      const uint32_t nid = nd.nid, lo = nd.lo, n = nd.n;
+      const float iv[3] = {inv_extent(nd.bmin[0], nd.bmax[0], B), inv_extent(nd.bmin[1], nd.bmax[1], B),
+                           inv_extent(nd.bmin[2], nd.bmax[2], B)};
+      auto bin_axis = [&](int a) {
+        for (int i = lane; i < B * kBinWords; i += 32) {
+          const int w = i & (kBinWords - 1);
+          sbin[i] = (w >= 1 && w <= 3) ? 0xFFFFFFFFu : 0u;
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+          const uint32_t q = S.ids[lo + i];
+          const float4 l4 = S.plo[q], h4 = S.phi[q];
+          const float c = a == 0 ? l4.w : (a == 1 ? h4.w : S.pcz[q]);
+          uint32_t *w = sbin + (size_t)bin_of(c, nd.bmin[a], iv[a], B) * kBinWords;
+          atomicAdd(w, 1u);
+          atomicMin(w + 1, fkey(l4.x));
+          atomicMin(w + 2, fkey(l4.y));
+          atomicMin(w + 3, fkey(l4.z));
+          atomicMax(w + 4, fkey(h4.x));
+          atomicMax(w + 5, fkey(h4.y));
+          atomicMax(w + 6, fkey(h4.z));
+        }
+        __syncwarp();
+      };
+      float cost[3];
+      int cut[3];
+      int ax = 0;
+      Box6 lb, rb;
+      uint32_t nl = 0, nr = 0;
       for (int a = 0; a < 3; a++) {
         bin_axis(a);
         sweep_axis(sbin, B, sweep, sweep + B, cost[a], cut[a]);
@@ -621,137 +775,131 @@ __global__ void __launch_bounds__(kSubWarps * 32)
       if (cost[0] > cost[1]) ax = 1;
       if (cost[ax] > cost[2]) ax = 2;
       if (ax != 2 && cost[ax] < FLT_MAX) bin_axis(ax);  // the child boxes come from the chosen axis' bins
-    }
-    const bool median = !(cost[ax] < FLT_MAX);
-    if (!median) {
-      if (!small) {
+      const bool median = !(cost[ax] < FLT_MAX);
+      if (!median) {
         range_union(sbin, 0, cut[ax], lb, nl);
         range_union(sbin, cut[ax], B, rb, nr);
-      }
-    } else {
-      nl = n >> 1;
-      box_empty(lb);
-      box_empty(rb);
-      for (uint32_t i = lane; i < n; i += 32) {  // exact boxes of the two halves of the current order
-        const uint32_t q = S.ids[lo + i];
-        const float4 l4 = S.plo[q], h4 = S.phi[q];
-        Box6 &t = i < nl ? lb : rb;
-        t.v[0] = fminf(t.v[0], l4.x);
-        t.v[1] = fminf(t.v[1], l4.y);
-        t.v[2] = fminf(t.v[2], l4.z);
-        t.v[3] = fmaxf(t.v[3], h4.x);
-        t.v[4] = fmaxf(t.v[4], h4.y);
-        t.v[5] = fmaxf(t.v[5], h4.z);
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        for (int k = 0; k < 3; k++) {
-          lb.v[k] = fminf(lb.v[k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[k], o));
-          rb.v[k] = fminf(rb.v[k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[k], o));
-          lb.v[3 + k] = fmaxf(lb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[3 + k], o));
-          rb.v[3 + k] = fmaxf(rb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[3 + k], o));
+      } else {
+        nl = n >> 1;
+        box_empty(lb);
+        box_empty(rb);
+        for (uint32_t i = lane; i < n; i += 32) {  // exact boxes of the two halves of the current order
+          const uint32_t q = S.ids[lo + i];
+          const float4 l4 = S.plo[q], h4 = S.phi[q];
+          Box6 &t = i < nl ? lb : rb;
+          t.v[0] = fminf(t.v[0], l4.x);
+          t.v[1] = fminf(t.v[1], l4.y);
+          t.v[2] = fminf(t.v[2], l4.z);
+          t.v[3] = fmaxf(t.v[3], h4.x);
+          t.v[4] = fmaxf(t.v[4], h4.y);
+          t.v[5] = fmaxf(t.v[5], h4.z);
         }
-      }
-    }
-    // ---- stable partition of ids[lo, lo+n) by warp ballots
-    {
-      uint32_t done_l = 0, done_r = 0;
-      for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool valid = i < n;
-        uint32_t q = 0;
-        bool f = false;
-        if (valid) {
-          q = S.ids[lo + i];
-          if (median) {
-            f = i < nl;
-          } else {
-            const float c = ax == 0 ? S.plo[q].w : (ax == 1 ? S.phi[q].w : S.pcz[q]);
-            f = (uint32_t)bin_of(c, nd.bmin[ax], iv[ax], B) < (uint32_t)cut[ax];
+        for (int o = 16; o > 0; o >>= 1) {
+          for (int k = 0; k < 3; k++) {
+            lb.v[k] = fminf(lb.v[k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[k], o));
+            rb.v[k] = fminf(rb.v[k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[k], o));
+            lb.v[3 + k] = fmaxf(lb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, lb.v[3 + k], o));
+            rb.v[3 + k] = fmaxf(rb.v[3 + k], __shfl_xor_sync(0xFFFFFFFFu, rb.v[3 + k], o));
           }
         }
-        const unsigned ml = __ballot_sync(0xFFFFFFFFu, valid && f), mr = __ballot_sync(0xFFFFFFFFu, valid && !f);
-        const unsigned lt = (1u << lane) - 1u;
-        if (valid) {
-          if (f)
-            S.tmp[lo + done_l + __popc(ml & lt)] = (uint16_t)q;
-          else
-            S.tmp[lo + nl + done_r + __popc(mr & lt)] = (uint16_t)q;
+      }
+      // ---- stable partition of ids[lo, lo+n) by warp ballots
+      {
+        uint32_t done_l = 0, done_r = 0;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+          const uint32_t i = i0 + lane;
+          const bool valid = i < n;
+          uint32_t q = 0;
+          bool f = false;
+          if (valid) {
+            q = S.ids[lo + i];
+            if (median) {
+              f = i < nl;
+            } else {
+              const float c = ax == 0 ? S.plo[q].w : (ax == 1 ? S.phi[q].w : S.pcz[q]);
+              f = (uint32_t)bin_of(c, nd.bmin[ax], iv[ax], B) < (uint32_t)cut[ax];
+            }
+          }
+          const unsigned ml = __ballot_sync(0xFFFFFFFFu, valid && f), mr = __ballot_sync(0xFFFFFFFFu, valid && !f);
+          const unsigned lt = (1u << lane) - 1u;
+          if (valid) {
+            if (f)
+              S.tmp[lo + done_l + __popc(ml & lt)] = (uint16_t)q;
+            else
+              S.tmp[lo + nl + done_r + __popc(mr & lt)] = (uint16_t)q;
+          }
+          done_l += __popc(ml);
+          done_r += __popc(mr);
         }
-        done_l += __popc(ml);
-        done_r += __popc(mr);
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) S.ids[lo + i] = S.tmp[lo + i];
       }
-      __syncwarp();
-      for (uint32_t i = lane; i < n; i += 32) S.ids[lo + i] = S.tmp[lo + i];
-    }
-    // ---- children
-    if (id_next + 2u > id_end) {  // chunk used up (rare): reserve another one
-      const uint32_t chunk = id_cap_left < 32u ? id_cap_left : 32u;
-      uint32_t more = 0;
-      if (lane == 0) more = atomicAdd(&ctr->pool, chunk);
-      id_next = __shfl_sync(0xFFFFFFFFu, more, 0);
-      id_end = id_next + chunk;
-      id_cap_left -= chunk;
-    }
-    const uint32_t left = id_next;
-    id_next += 2u;
-    const uint32_t cdepth = nd.depth + 1;
-    const uint32_t n_side[2] = {nl, n - nl};
-    if (lane == 0) {  // the parent's record is complete now; its range, box, depth and right turns were written by its parent
-      BNode *me = pool + nid;
-      me->left = left;
-      me->axis = (uint32_t)(median ? (ax + 2) % 3 : ax);
-      me->split_bin = median ? kMedian : (uint32_t)cut[ax];
-      me->nleft = nl;
-    }
-    if (lane < 2) {
-      const int side = lane;
-      const Box6 &bx = side ? rb : lb;
-      BNode c;
-      for (int k = 0; k < 3; k++) {
-        c.bmin[k] = bx.v[k];
-        c.bmax[k] = bx.v[3 + k];
+      // ---- children
+      ids.ensure(ctr, 1u, lane);
+      const uint32_t left = ids.id(0u);
+      ids.commit(1u);
+      const uint32_t cdepth = nd.depth + 1;
+      const uint32_t n_side[2] = {nl, n - nl};
+      if (lane == 0) {  // the parent's record is complete now; range, box, depth, right turns came from its own parent
+        BNode *me = pool + nid;
+        me->left = left;
+        me->axis = (uint32_t)(median ? (ax + 2) % 3 : ax);
+        me->split_bin = median ? kMedian : (uint32_t)cut[ax];
+        me->nleft = nl;
       }
-      c.l = base + lo + (side ? nl : 0u);
-      c.r = base + lo + (side ? n : nl);
-      c.left = kInactive;
-      c.depth = cdepth;
-      c.rturns = nd.rturns + (uint32_t)side;
-      c.axis = 0;
-      c.split_bin = 0;
-      c.nleft = 0;
-      c.slot = kInactive;
-      c.pad = 0;
-      pool[left + side] = c;
-    }
-    // next node: a child that still splits (the smaller one first, the other parked), else a parked node
-    const bool more0 = child_class(n_side[0], cdepth, min_leaf, max_depth) != 0;
-    const bool more1 = child_class(n_side[1], cdepth, min_leaf, max_depth) != 0;
-    if (more0 || more1) {
-      const int go = (more0 && more1) ? (n_side[1] < n_side[0] ? 1 : 0) : (more1 ? 1 : 0);
-      if (more0 && more1) {
-        const int park = go ^ 1;
-        const Box6 &pb = park ? rb : lb;
-        if (lane == 0) {
-          uint32_t *e = S.stack[sp];
-          e[0] = left + (uint32_t)park;
-          e[1] = (lo + (park ? nl : 0u)) | (n_side[park] << 16);
-          e[2] = cdepth;
-          e[3] = nd.rturns + (uint32_t)park;
-          for (int k = 0; k < 6; k++) e[4 + k] = __float_as_uint(pb.v[k]);
+      if (lane < 2) {
+        const int side = lane;
+        const Box6 &bx = side ? rb : lb;
+        BNode c;
+        for (int k = 0; k < 3; k++) {
+          c.bmin[k] = bx.v[k];
+          c.bmax[k] = bx.v[3 + k];
         }
-        sp++;
+        c.l = base + lo + (side ? nl : 0u);
+        c.r = base + lo + (side ? n : nl);
+        c.left = kInactive;
+        c.depth = cdepth;
+        c.rturns = nd.rturns + (uint32_t)side;
+        c.axis = 0;
+        c.split_bin = 0;
+        c.nleft = 0;
+        c.slot = kInactive;
+        c.pad = 0;
+        pool[left + side] = c;
       }
-      const Box6 &gb = go ? rb : lb;
-      nd.nid = left + (uint32_t)go;
-      nd.lo = lo + (go ? nl : 0u);
-      nd.n = n_side[go];
-      nd.depth = cdepth;
-      nd.rturns = nd.rturns + (uint32_t)go;
-      for (int k = 0; k < 3; k++) {
-        nd.bmin[k] = gb.v[k];
-        nd.bmax[k] = gb.v[3 + k];
+      // next node: a child that still splits (the smaller one first, the other parked), else a parked node
+      const bool more0 = child_class(n_side[0], cdepth, min_leaf, max_depth) != 0;
+      const bool more1 = child_class(n_side[1], cdepth, min_leaf, max_depth) != 0;
+      if (more0 || more1) {
+        const int go = (more0 && more1) ? (n_side[1] < n_side[0] ? 1 : 0) : (more1 ? 1 : 0);
+        if (more0 && more1) {
+          const int park = go ^ 1;
+          const Box6 &pb = park ? rb : lb;
+          if (lane == 0) {
+            uint32_t *e = S.stack[sp];
+            e[0] = left + (uint32_t)park;
+            e[1] = (lo + (park ? nl : 0u)) | (n_side[park] << 16);
+            e[2] = cdepth;
+            e[3] = nd.rturns + (uint32_t)park;
+            for (int k = 0; k < 6; k++) e[4 + k] = __float_as_uint(pb.v[k]);
+          }
+          sp++;
+        }
+        const Box6 &gb = go ? rb : lb;
+        nd.nid = left + (uint32_t)go;
+        nd.lo = lo + (go ? nl : 0u);
+        nd.n = n_side[go];
+        nd.depth = cdepth;
+        nd.rturns = nd.rturns + (uint32_t)go;
+        for (int k = 0; k < 3; k++) {
+          nd.bmin[k] = gb.v[k];
+          nd.bmax[k] = gb.v[3 + k];
+        }
+      } else {
+        pop = true;
       }
-    } else {
+    }
+    if (pop) {
       if (sp == 0) break;
       --sp;
       __syncwarp();
@@ -769,7 +917,7 @@ __global__ void __launch_bounds__(kSubWarps * 32)
     __syncwarp();
   }
   // reserved slots this subtree did not need
-  for (uint32_t i = id_next + lane; i < id_end; i += 32) pool[i].depth = kDeadNode;
+  for (uint32_t i = ids.next + lane; i < ids.end; i += 32) pool[i].depth = kDeadNode;
   // final order of this subtree's range
   for (uint32_t i = lane; i < total; i += 32) idx[base + i] = S.gslot[S.ids[i]];
 }
