@@ -38,7 +38,7 @@ struct BuildCounters {
   uint32_t max_depth;
   uint32_t n_leaves;
   uint32_t error;
-  uint32_t pad;
+  uint32_t n_mids;      // nodes handed to the one-CTA-per-node middle phase
 };
 
 // order-preserving float <-> uint key for atomicMin / atomicMax

@@ -115,10 +115,12 @@ static __global__ void __launch_bounds__(kSortBlock)
 
 // Sorts in place logically: on return (keys, vals) hold the sorted pairs (the *_tmp arrays are scratch).
 // `table` needs 16 * n_tiles + 1 words, `scratch` scan_scratch_words(16 * n_tiles) words.
+// Only key bits [first_bit, key_bits) take part (a stable sort on the high bits alone: equal prefixes keep their input
+// order).
 static int radix_sort_pairs(uint32_t *&keys, uint32_t *&vals, uint32_t *&keys_tmp, uint32_t *&vals_tmp, uint32_t n,
-                            int key_bits, uint32_t *table, uint32_t *scratch, cudaStream_t s) {
+                            int first_bit, int key_bits, uint32_t *table, uint32_t *scratch, cudaStream_t s) {
   const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
-  for (int shift = 0; shift < key_bits; shift += 4) {
+  for (int shift = first_bit; shift < key_bits; shift += 4) {
     radix_hist_kernel<<<n_tiles, kSortBlock, 0, s>>>(keys, n, shift, n_tiles, table);
     NRT_CUDA(cudaGetLastError());
     int rc = exclusive_scan_u32_async(table, table, kSortDigits * n_tiles, scratch, s);
