@@ -146,6 +146,7 @@ int run_rank(int rank, int world, const unsigned char *id, int width, int height
   cudaFree(d_frame);
   nrt_comm_free(comm);
   nrt_free(accel);
+  fflush(stdout);  // the caller leaves through _exit(), which does not flush stdio
   return 0;
 }
 
