@@ -13,6 +13,8 @@
 #include <float.h>
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "trav_common.cuh"
 #include "wavefront.cuh"
@@ -427,7 +429,12 @@ static cudaError_t launch_fast3(const Accel *a, Rays rays, size_t n, Epi epi, co
   if (grid > need_blocks) grid = need_blocks;
   if (grid == 0) grid = 1;
   const void *nodes = P::kPair128 ? static_cast<const void *>(a->d_pair) : static_cast<const void *>(a->d_wide);
-  traverse_fast3_kernel<Rays, DEPTH, COUNT, P, Epi><<<(unsigned)grid, P::kBlock, 0, s>>>(
+  // experiment knob (tools/trav_sweep.py): unused dynamic shared memory per CTA, i.e. that much less L1 per SM --
+  // measures how much a shared-memory staging scheme would cost before it saves anything
+  static const size_t pad = getenv("NRT_SMEM_PAD") ? (size_t)atoi(getenv("NRT_SMEM_PAD")) : 0;
+  if (pad > 48 * 1024)
+    cudaFuncSetAttribute(traverse_fast3_kernel<Rays, DEPTH, COUNT, P, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+  traverse_fast3_kernel<Rays, DEPTH, COUNT, P, Epi><<<(unsigned)grid, P::kBlock, pad, s>>>(
       nodes, a->d_tris_cm, rays, n, epi, opt, flags, cursor, d_counts, n_ptr);
   return cudaGetLastError();
 }
