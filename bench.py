@@ -906,7 +906,7 @@ def main():
                     configs.append(fn())
                 except Exception as e:  # a failing extra config is reported, it does not take the headline line with it
                     configs.append({"error": repr(e)})
-        elif world >= 8:
+        elif world >= int(os.environ.get("NRT_BENCH_C5_MIN_WORLD", "8")):  # configs[4] names 8 GPUs; lower it to rehearse the path
             try:
                 configs.append(config_c5_sharded(torch, dist, api, S, dev, local_rank, rank, world, comm, sampler))
             except Exception as e:
