@@ -789,8 +789,9 @@ class BVHAccel<double> {
     stats_ = BVHBuildStatistics();
     if (num_primitives == 0) return false;
     nrt_accel_f64 *h = NULL;
-    if (nrt_build_f64(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), num_primitives, &options, &h) !=
-        NRT_OK) {
+    // -DNANORT_B200_CONFORMANCE: the reference's own BVHNode<double> array and indices_ (csrc/build_ref64.cu)
+    if (nrt_build_f64_ex(p.GetVertices(), p.GetVertexStrideBytes(), 0, p.GetFaces(), num_primitives, &options,
+                         NANORT_B200_BUILD_FLAGS, &h) != NRT_OK) {
       fprintf(stderr, "nanort_b200: Build<double> failed: %s\n", nrt_last_error());
       return false;
     }

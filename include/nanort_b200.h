@@ -367,6 +367,12 @@ int nrt_build_f64(const double *verts, size_t stride_bytes, size_t n_verts_or_0,
                   uint32_t n_prims, const void *build_opts_32B, nrt_accel_f64 **out);
 /* BVHAccel<double>::Load (nanort.h:2252-2275) + the geometry the first Traverse brings: an existing BVHNode<double>
  * array, e.g. one dumped by CPU nanort, validated and walked in the reference's order */
+/* Same with the flags of nrt_build_ex: NRT_BUILD_REFERENCE_TREE makes the device write the very BVHNode<double> array and
+ * indices_ the reference's BVHAccel<double>::Build writes (x-only binning, axis retry / median fallback, std::partition's
+ * element order, all split decisions in double; C++11 joined node order unless NRT_BUILD_REFERENCE_CPP03_ORDER), so that
+ * GetNodes() / GetIndices() / Dump() equal CPU nanort's for T = double too (csrc/build_ref64.cu). */
+int nrt_build_f64_ex(const double *verts, size_t stride_bytes, size_t n_verts_or_0, const uint32_t *faces,
+                     uint32_t n_prims, const void *build_opts_32B, uint32_t flags, nrt_accel_f64 **out);
 int nrt_adopt_f64(const void *nodes_64B, size_t n_nodes, const uint32_t *indices, size_t n_indices, const double *verts,
                   size_t stride_bytes, size_t n_verts_or_0, const uint32_t *faces, uint32_t n_prims,
                   nrt_accel_f64 **out);

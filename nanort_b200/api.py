@@ -56,7 +56,7 @@ EXPORTS = [
     "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
     "nrt_path_bounce_device", "nrt_build_prims", "nrt_list_node_intersections",
     "nrt_comm_unique_id", "nrt_comm_init", "nrt_comm_free", "nrt_comm_rank", "nrt_render_ao_sharded",
-    "nrt_probe_read_gbs", "nrt_probe_copy_gbs", "nrt_traverse_lane_stats_device",
+    "nrt_probe_read_gbs", "nrt_probe_copy_gbs", "nrt_traverse_lane_stats_device", "nrt_build_f64_ex",
 ]
 
 
@@ -155,6 +155,7 @@ def lib():
     L.nrt_scene_traverse.argtypes = [vp, vp, sz, vp, vp, u32]
     L.nrt_scene_traverse_device.argtypes = [vp, vp, sz, vp, vp, u32, vp]
     L.nrt_build_f64.argtypes = [vp, sz, sz, vp, u32, vp, C.POINTER(vp)]
+    L.nrt_build_f64_ex.argtypes = [vp, sz, sz, vp, u32, vp, u32, C.POINTER(vp)]
     L.nrt_adopt_f64.argtypes = [vp, sz, vp, sz, vp, sz, sz, vp, u32, C.POINTER(vp)]
     L.nrt_free_f64.argtypes = [vp]
     L.nrt_free_f64.restype = None
@@ -618,7 +619,8 @@ class BVHAccelF64:
         except Exception:
             pass
 
-    def Build(self, num_primitives, vertices, faces, options=None, vertex_stride_bytes=24):
+    def Build(self, num_primitives, vertices, faces, options=None, vertex_stride_bytes=24, flags=BUILD_FAST):
+        """flags=BUILD_REFERENCE_TREE: the reference's own BVHNode<double> array, bit for bit (nrt_build_f64_ex)."""
         self.free()
         if num_primitives == 0:
             return False
@@ -628,8 +630,8 @@ class BVHAccelF64:
             _check(lib().nrt_set_device(int(self._device)))
         h = C.c_void_p()
         n_verts = vertices.size * 8 // vertex_stride_bytes
-        _check(lib().nrt_build_f64(_p(vertices), vertex_stride_bytes, n_verts, _p(faces), int(num_primitives),
-                                   _p(options), C.byref(h)))
+        _check(lib().nrt_build_f64_ex(_p(vertices), vertex_stride_bytes, n_verts, _p(faces), int(num_primitives),
+                                      _p(options), int(flags), C.byref(h)))
         self._h = h
         return True
 

@@ -25,6 +25,12 @@
 
 namespace nrt {
 
+int build_reference_tree_f64_on_device(const double *d_verts, const uint32_t *d_faces, uint32_t n, uint32_t bin_size,
+                                       uint32_t min_leaf_primitives, uint32_t max_tree_depth, uint32_t shallow_depth,
+                                       uint32_t min_primitives_for_parallel_build, bool cpp11_order, void **d_nodes_out,
+                                       uint32_t **d_indices_out, size_t *n_nodes_out, BuildStats16 *stats_out,
+                                       double root_bmin[3], double root_bmax[3], cudaStream_t s);
+
 namespace {
 
 struct Node64 {
@@ -330,6 +336,11 @@ extern "C" {
 
 int nrt_build_f64(const double *verts, size_t stride_bytes, size_t n_verts, const uint32_t *faces, uint32_t n_prims,
                   const void *build_opts_32B, nrt_accel_f64 **out) {
+  return nrt_build_f64_ex(verts, stride_bytes, n_verts, faces, n_prims, build_opts_32B, NRT_BUILD_FAST, out);
+}
+
+int nrt_build_f64_ex(const double *verts, size_t stride_bytes, size_t n_verts, const uint32_t *faces, uint32_t n_prims,
+                     const void *build_opts_32B, uint32_t flags, nrt_accel_f64 **out) {
   if (!out) {
     set_error("nrt_build_f64: out is NULL");
     return NRT_ERR_INVALID;
@@ -394,6 +405,21 @@ int nrt_build_f64(const double *verts, size_t stride_bytes, size_t n_verts, cons
     F64_CUDA(cudaMemcpyAsync(a->d_verts, packed.data(), sizeof(double) * 3 * n_verts, cudaMemcpyHostToDevice, a->stream));
     F64_CUDA(cudaMemcpyAsync(a->d_faces, faces, sizeof(uint32_t) * 3 * (size_t)n_prims, cudaMemcpyHostToDevice, a->stream));
     F64_CUDA(cudaStreamSynchronize(a->stream));
+  }
+  if (flags & NRT_BUILD_REFERENCE_TREE) {
+    // conformance build: the reference's own BVHNode<double> array and indices_, bit for bit (build_ref64.cu)
+    void *d_nodes = nullptr;
+    cudaFree(t->d_verts);
+    t->d_verts = nullptr;
+    rc = build_reference_tree_f64_on_device(a->d_verts, a->d_faces, n_prims, o64.bin_size, o64.min_leaf_primitives,
+                                            o64.max_tree_depth, o64.shallow_depth, o64.min_primitives_for_parallel_build,
+                                            (flags & NRT_BUILD_REFERENCE_CPP03_ORDER) == 0, &d_nodes, &a->d_indices,
+                                            &a->n_nodes, &a->stats, a->root_bmin, a->root_bmax, a->stream);
+    if (rc != NRT_OK) goto fail;
+    a->d_nodes = static_cast<Node64 *>(d_nodes);
+    delete t;
+    *out = reinterpret_cast<nrt_accel_f64 *>(a);
+    return NRT_OK;
   }
   t->d_faces = a->d_faces;  // shared, freed with `a`
   t->options = default_build_options();

@@ -181,3 +181,52 @@ def test_f64_against_the_c_restatement(cpp11):
     assert np.array_equal(qm, am)
     for k in ("t", "u", "v", "prim_id"):
         assert qh[k][qm == 1].tobytes() == ah[k][am == 1].tobytes(), k
+
+
+@pytest.mark.parametrize("cpp11", [True, False])
+def test_f64_conformance_build_writes_the_references_arrays(cpp11):
+    """nrt_build_f64_ex(NRT_BUILD_REFERENCE_TREE): the device writes the very BVHNode<double> array and indices_ that
+    BVHAccel<double>::Build writes -- checked against the oracle's double instantiation (pinned to the unmodified
+    reference's BVHAccel<double> by tests/test_oracle_f64.py) and, where oracle/_ref exists, against the reference itself:
+    every field of every node, every index, the statistics, for several scenes and option sets -- coordinates that do not
+    survive a round trip through float, so a float-precision split decision would show."""
+    from nanort_b200 import api, scenes as S
+    from oracle import orc
+
+    port = orc.Port64()
+    mode = orc.MODE_CPP11 if cpp11 else 0
+    flags = api.BUILD_REFERENCE_TREE | (0 if cpp11 else api.BUILD_REFERENCE_CPP03_ORDER)
+    cases = [(_scene64(seed=21), None), (_scene64(seed=22), orc.build_options_f64(min_leaf_primitives=1, bin_size=16)),
+             (_scene64(seed=23), orc.build_options_f64(max_tree_depth=6))]
+    v, f = S.make_scene("cornell")
+    cases.append(((v.astype(np.float64) * (1.0 + 1e-13), f), None))
+    v, f = S.sphere_grid(nx=6, nz=5)  # 30,000 triangles: above min_primitives_for_parallel_build -> joined node order
+    rng = np.random.default_rng(5)
+    cases.append(((v.astype(np.float64) + 1e-10 * rng.standard_normal(v.shape), f), None))
+    for (v64, f), opts in cases:
+        want_nodes, want_idx, _ = port.build(v64, f, opts, mode)
+        acc = api.BVHAccelF64()
+        assert acc.Build(len(f), v64, f, options=opts, flags=flags)
+        nodes, idx = acc.GetNodes(), acc.GetIndices()
+        assert len(nodes) == len(want_nodes), (len(nodes), len(want_nodes))
+        assert np.array_equal(idx, want_idx)
+        for k in ("bmin", "bmax", "flag", "data"):
+            assert nodes[k].tobytes() == want_nodes[k].tobytes(), k
+        br = nodes["flag"] == 0
+        assert np.array_equal(nodes["axis"][br], want_nodes["axis"][br])  # the reference leaves leaf.axis uninitialised
+        st = acc.GetStatistics()
+        assert st["num_leaf_nodes"] == int((nodes["flag"] == 1).sum()) and st["num_branch_nodes"] == int(br.sum())
+        if orc.Reference.available(cpp11):
+            racc = orc.ReferenceF64(cpp11).build(v64, f, opts)
+            rn = racc.nodes()
+            assert np.array_equal(racc.indices(), idx)
+            for k in ("bmin", "bmax", "flag", "data"):
+                assert rn[k].tobytes() == nodes[k].tobytes(), k
+        # and the conformance walk over it gives the oracle's records, ties included
+        rays = _rays64(v64, 5000, seed=31)
+        tf = 0 if cpp11 else api.TRAVERSE_CPP03_INVERSE
+        gh, gm = acc.Traverse(rays, flags=tf)
+        ph, pm = port.traverse(want_nodes, want_idx, v64, f, rays, cpp11=cpp11, threads=8)
+        assert np.array_equal(pm, gm)
+        for k in ("t", "u", "v", "prim_id"):
+            assert ph[k][pm == 1].tobytes() == gh[k][gm == 1].tobytes(), k

@@ -58,7 +58,7 @@ def _bounce_by_bounce(with_normals, scene="cornell"):
         ids = np.zeros(len(f), np.uint32)
         ids[l0:] = 1
         emissive = np.arange(l0, l0 + ln, dtype=np.uint32)
-        W, H, spp, bounces, seed = 128, 72, 2, 6, 3
+        W, H, spp, bounces, seed = 192, 108, 2, 6, 3
     ref = orc.ReferencePathTracer(v, f, ids, mats)  # face normals as the example's loader makes them (calcNormal)
     assert np.array_equal(ref.emissive_faces(), emissive), "MeshLight's emissive-face list != the list handed to the device"
     fvn = ref.fvn if with_normals else None
@@ -140,7 +140,11 @@ def _bounce_by_bounce(with_normals, scene="cornell"):
         assert _rel(gs_o[kg][:, :3], ro[kr]) <= 1e-5
         assert float(np.max(np.abs(gs_d[kg][:, :3] - want["shadow_dir"][shad][kr]))) <= 2e-5 if n_sh else True
         assert _rel(gs_d[kg][:, 3], want["shadow_max_t"][shad][kr]) <= 1e-5
-        assert _rel(gs_c[kg][:, :3], want["shadow_contrib"][shad][kr], floor=1e-6) <= 2e-5
+        # the contribution holds both cosines of the light sample: directions that agree to 2e-5 (sinf / cosf of CUDA vs
+        # glibc, asserted above) give cosines that agree to 2e-5 ABSOLUTE, i.e. to 2e-5 / cos relative -- grazing samples
+        # (cos ~ 0.05) legitimately differ by a few 1e-4; all but a per-mille of the samples sit within 2e-5
+        cd = np.abs(gs_c[kg][:, :3] - want["shadow_contrib"][shad][kr]) / np.maximum(np.abs(want["shadow_contrib"][shad][kr]), 1e-6)
+        assert (float(cd.max()) <= 1e-3 and float(np.quantile(cd, 0.999)) <= 2e-5) if n_sh else True
         # ---- what reached the frame: emission of this bounce + the light samples the device's shadow pass found visible
         sr = np.zeros(n_sh, S.RAY_DTYPE)
         sr["org"], sr["dir"], sr["min_t"], sr["max_t"] = gs_o[:, :3], gs_d[:, :3], gs_o[:, 3], gs_d[:, 3]
@@ -155,7 +159,7 @@ def _bounce_by_bounce(with_normals, scene="cornell"):
         # next bounce: the DEVICE's continuation queue
         pid = got_pid
         org, dirs = go[:, :3].copy(), gd[:, :3].copy()
-    assert total_checked > 15000 and ("shadow", True) in lobes_seen
+    assert total_checked > (15000 if scene == "cornell" else 25000) and ("shadow", True) in lobes_seen
     assert scene != "cornell" or ("emit", True) in lobes_seen  # the terrain's light is outside the camera's view
     return total_checked
 
@@ -173,7 +177,7 @@ def test_every_bounce_matches_the_reference_functions_with_loader_style_flat_nor
 
 def test_every_bounce_matches_the_reference_functions_on_the_1m_triangle_terrain():
     """BASELINE.json configs[2]'s scene (terrain + area light, diffuse): the same per-bounce comparison with the reference's
-    own shading code, at 2 spp on 128x72 pixels."""
+    own shading code, at 2 spp on 192x108 pixels."""
     _bounce_by_bounce(with_normals=False, scene="terrain")
 
 
