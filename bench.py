@@ -965,12 +965,30 @@ def config_c5_sharded(torch, dist, api, S, dev, local_rank, rank, world, comm, s
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     rays = float(tot[0].item() + tot[1].item())
+    parity = {"gathered_frame_identity": gate}
+    if rank == 0:
+        # a strided sample of this frame's camera rays and of the AO rays they spawn (host generators, same arithmetic as
+        # the device): production kernel == conformance kernel on every sampled ray, and == the unmodified reference
+        pix = np.arange(0, W * H, 193, dtype=np.int64)
+        prim = S.primary_rays(cam, W, H, spp=1, seed=1, pixels=pix, min_t=1e-3, max_t=1e30)
+        h, m = acc.Traverse(prim)
+        ao, _ = S.ao_rays(verts, faces, prim, h, m, seed=2, min_t=1e-3, max_t=0.25 * diag)
+        sample = np.concatenate([prim, ao])
+        d_s = torch.as_tensor(sample.view(np.uint8).reshape(-1), device=dev)
+        parity["sample_fast_vs_conformance"] = gate_fast_vs_conformance(torch, api, acc, d_s, len(sample), dev)
+        try:
+            ref = CpuReference(verts, faces)
+            gh, gm = acc.Traverse(sample)
+            rh, rm = ref.trav(sample)
+            parity["sample_vs_reference_cpu"] = compare_with_reference(S, None, gh, gm, rh, rm)
+        except Exception as e:  # the reference library is test infrastructure; its absence does not fail the config
+            parity["sample_vs_reference_cpu"] = {"skipped": repr(e)}
     acc.free()
     return {"name": "configs[4]_4k4k_256spp_sharded", "workload": f"1,002,528-triangle terrain, {W}x{H}x{spp} spp primary + AO, "
                                                                    f"64x64-pixel tiles round-robin over {world} GPUs, framebuffer all-gather",
             "rays_per_step": rays, "steps": steps, "ms_per_step": float(t.item()) / steps,
             "value": rays * steps / (float(t.item()) * 1e-3) / 1e6, "unit": UNIT, "clocks": sampler.window(t0, t1),
-            "parity": {"gathered_frame_identity": gate}, "parity_ok": gate["ok"]}
+            "parity": parity, "parity_ok": all(g.get("ok", True) for g in parity.values())}
 
 
 if __name__ == "__main__":

@@ -173,6 +173,7 @@ __global__ void ref_init_kernel(BNodeD *pool, RefCounters *ctr, uint32_t n, uint
   r.nleft = 0;
   r.slot = 0;
   r.pad = kInactive;
+  r.pad2[0] = r.pad2[1] = 0;
   ctr->pool = 1;
   ctr->n_fresh[0] = 1;
   ctr->n_fresh[1] = 0;
@@ -408,6 +409,7 @@ __global__ void ref_children_kernel(BNodeD *pool, RefCounters *ctr, const uint32
     c.nleft = 0;
     c.slot = fs + side;
     c.pad = kInactive;
+    c.pad2[0] = c.pad2[1] = 0;
     fresh_next[fs + side] = left + side;
     const uint32_t cn = c.r - c.l;
     if (!(cn <= min_leaf || c.depth >= max_depth)) {

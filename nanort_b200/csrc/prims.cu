@@ -363,6 +363,8 @@ int nrt_list_node_intersections(const nrt_accel *h, const void *rays_36B, size_t
   if (e == cudaSuccess) e = cudaMalloc(&d_hits, sizeof(NodeHit12) * n_rays * (size_t)max_intersections);
   if (e == cudaSuccess) e = cudaMalloc(&d_cnt, sizeof(uint32_t) * n_rays);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays_36B, sizeof(Ray36) * n_rays, cudaMemcpyHostToDevice, s);
+  // records beyond counts[ray] are never written by the kernel: hand the caller zeros, not device garbage
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_hits, 0, sizeof(NodeHit12) * n_rays * (size_t)max_intersections, s);
   if (e == cudaSuccess) {
     list_boxes_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, s>>>(a->d_nodes, a->d_indices, a->d_prim_boxes, d_rays, n_rays,
                                                                      max_intersections, d_hits, d_cnt, flags);

@@ -33,6 +33,11 @@ CASES = [
     ("sphere_grid", dict(nx=3, nz=3), dict(min_leaf_primitives=8, bin_size=8)),
     ("sphere_grid", dict(nx=3, nz=3), dict(max_tree_depth=5)),
     ("terrain", dict(n=96), dict(bin_size=16)),
+    ("terrain", dict(n=96), dict(bin_size=256)),          # largest bin count: 47 KB of shared memory in the middle phase
+    ("terrain", dict(n=30), {}),                          # 1,682 triangles: the root itself is a middle-phase node
+    ("terrain", dict(n=40), dict(min_leaf_primitives=1)),  # one level-synchronous pass, then middle-phase nodes; 1-primitive leaves
+    ("terrain", dict(n=96), dict(max_tree_depth=9)),      # the depth limit is reached inside the middle phase
+    ("terrain", dict(n=96), dict(max_tree_depth=13)),     # ... and inside the warp-built subtrees
     ("sphere_grid", {}, {}),
     ("deg:one", {}, {}),
     ("deg:five", {}, {}),

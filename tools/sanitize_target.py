@@ -44,3 +44,20 @@ print("f64 ok", int(m64.sum()))
 big_v, big_f = S.make_scene("terrain", n=96)
 big = api.BVHAccel(); big.Build(len(big_f), big_v, big_f)
 print("terrain build ok", big.GetStatistics()["num_leaf_nodes"])
+# round 2: middle phase + segmented small blocks at several sizes (one subtree, one mid node, level-synchronous + mid + subtrees)
+for n_side in (8, 30, 96):
+    tv, tf = S.make_scene("terrain", n=n_side)
+    for ml in (1, 4):
+        t = api.BVHAccel(); t.Build(len(tf), tv, tf, options=api.BVHBuildOptions(min_leaf_primitives=ml))
+        st = t.GetStatistics()
+        assert st["num_leaf_nodes"] == st["num_branch_nodes"] + 1
+print("builder sizes ok")
+c64 = api.BVHAccelF64(); c64.Build(len(f), v.astype(np.float64) * (1 + 1e-12), f, flags=api.BUILD_REFERENCE_TREE)
+h64b, m64b = c64.Traverse(r64)
+print("f64 conformance build ok", int(m64b.sum()), c64.GetStatistics()["max_tree_depth"])
+centers = np.random.default_rng(1).uniform(-1, 1, (500, 3)).astype(np.float32)
+sp = api.BVHAccel(); sp.BuildSpheres(centers, np.full(500, 0.05, np.float32))
+sph, spm = sp.Traverse(srays)
+bx = api.BVHAccel(); bx.BuildBoxes(np.concatenate([centers - 0.05, centers + 0.05], axis=1))
+lh, lc = bx.ListNodeIntersections(srays[:512], max_intersections=8)
+print("prims ok", int(spm.sum()), int(lc.sum()))
