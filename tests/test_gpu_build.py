@@ -131,3 +131,62 @@ def test_reference_traverses_gpu_built_tree(reference, port):
     adopted = reference.adopt(acc.GetNodes(), acc.GetIndices(), v, f)
     got_h, got_m = adopted.traverse(rays, threads=4)
     assert_parity(compare_hits(port, v, f, rays, got_h, got_m, want_h, want_m))
+
+
+def _random_soup(rng, n):
+    """Clustered triangle soup: cluster centres on very different scales, many coincident centroids, some slivers."""
+    k = int(rng.integers(1, 6))
+    centres = rng.normal(0, 10.0 ** rng.uniform(-2, 2), (k, 3))
+    which = rng.integers(0, k, n)
+    spread = 10.0 ** rng.uniform(-3, 0.5, k)
+    c = centres[which] + rng.normal(0, 1, (n, 3)) * spread[which][:, None]
+    dup = rng.random(n) < 0.15  # exact duplicates of another triangle's centroid position
+    c[dup] = c[rng.integers(0, n, int(dup.sum()))]
+    size = 10.0 ** rng.uniform(-3, 0, (n, 1, 1))
+    tri = c[:, None, :] + rng.normal(0, 1, (n, 3, 3)) * size
+    flat = rng.random(n) < 0.1  # axis-aligned flat triangles: zero-thickness boxes
+    tri[flat, :, int(rng.integers(0, 3))] = c[flat, int(rng.integers(0, 3))][:, None]
+    v = tri.reshape(-1, 3).astype(np.float32)
+    return v, np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_soups_and_options(port, seed):
+    """Sizes around every class boundary of the builder (one warp-built subtree <= 128 < one-CTA node <= 2048 <
+    level-synchronous), random leaf sizes / bin counts / depth limits, clustered and degenerate centroid distributions:
+    the tree is structurally valid (exact boxes, leaf rule, pre-order, statistics), deterministic, and walking it in the
+    reference's order on the device gives what the oracle finds walking the same arrays, bit for bit."""
+    from nanort_b200 import api, scenes as S
+
+    rng = np.random.default_rng(1000 + seed)
+    sizes = [2, 5, 31, 33, 64, 127, 128, 129, 400, 1000, 2047, 2048, 2049, 3000, 5000, 9000]
+    n = sizes[seed % len(sizes)] if seed < 16 else int(rng.integers(2, 12000))
+    v, f = _random_soup(rng, n)
+    okw = dict(min_leaf_primitives=int(rng.choice([1, 1, 2, 4, 4, 8, 13])), bin_size=int(rng.choice([2, 4, 8, 16, 64, 64, 128])),
+               max_tree_depth=int(rng.choice([3, 8, 20, 256, 256])))
+    opts = api.BVHBuildOptions(**okw)
+    acc = api.BVHAccel()
+    assert acc.Build(len(f), v, f, opts)
+    nodes, idx = acc.GetNodes(), acc.GetIndices()
+    st = check_tree_structure(nodes, idx, v, f, min_leaf=okw["min_leaf_primitives"], max_depth=okw["max_tree_depth"])
+    got = acc.GetStatistics()
+    for k in ("max_tree_depth", "num_leaf_nodes", "num_branch_nodes"):
+        assert got[k] == st[k], (k, got, st, n, okw)
+    acc2 = api.BVHAccel()
+    acc2.Build(len(f), v, f, opts)
+    assert np.array_equal(acc2.GetNodes().view(np.uint8), nodes.view(np.uint8)) and np.array_equal(acc2.GetIndices(), idx)
+    rays = S.incoherent_rays(v.min(axis=0) - 1, v.max(axis=0) + 1, 3000, seed=seed)
+    # aim half of them at triangles so that they hit something
+    tgt = v.reshape(-1, 3, 3).mean(axis=1)[rng.integers(0, n, 1500)]
+    d = tgt - rays["org"][:1500]
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+    rays["dir"][:1500] = d.astype(np.float32)
+    rays["max_t"][:1500] = 1e30
+    o_h, o_m = port.traverse(nodes, idx, v, f, rays, threads=8)
+    c_h, c_m = acc.Traverse(rays, flags=api.TRAVERSE_CONFORMANCE)
+    assert np.array_equal(c_m, o_m)
+    hit = o_m.astype(bool)
+    assert np.array_equal(c_h[hit].view(np.uint32), o_h[hit].view(np.uint32))
+    if st["max_tree_depth"] + 2 <= 512:
+        g_h, g_m = acc.Traverse(rays, flags=api.TRAVERSE_FAST)
+        assert_parity(compare_hits(port, v, f, rays, g_h, g_m, o_h, o_m))
