@@ -404,8 +404,14 @@ typedef FastPolicy<128, 10, 16, 8, 0, 0> OldDefaultPolicy;
 // 128-byte PairNode (no selects: they are issue bound); incoherent launches (AO, shadow and bounce rays) and trees
 // whose PairNode array would not stay L2-resident read the 64-byte WideNode (they are bound by the L1 data pipe and
 // by cache capacity, and the ALU pipe has room for the 12 selects).
-typedef Policy3<128, 10, 16, 8, true> DefaultPolicy;
-typedef Policy3<128, 10, 16, 8, false> IncoherentPolicy;
+// Leaf batching (profiles/r02_leaf_batching_sweep.md): after the first leaf round of an outer iteration another one
+// runs only while >= 8 (coherent) / >= 12 (incoherent) lanes hold a leaf -- a lane's second leaf otherwise costs a
+// round of its own at ~5 active lanes; the camera-ray launch, whose retire step spawns the AO ray (630 instructions),
+// also waits with the retire step until retired + empty lanes reach the refill threshold.
+typedef Policy3<128, 10, 16, 8, true, false, 8> DefaultPolicy;
+typedef Policy3<128, 10, 16, 8, true, false, 12, 1, true> CameraPolicy;
+typedef Policy3<128, 10, 16, 8, false, false, 12> IncoherentPolicy;
+typedef Policy3<128, 10, 16, 8, false, false, 12, 1, true> IncoherentCameraPolicy;
 // PairNode arrays above this size are not used (126 MB L2; the triangles want their share)
 constexpr size_t kPair128MaxBytes = (size_t)96 << 20;
 
@@ -505,6 +511,47 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
       NRT_VARIANT3(23, 128, 10, 16, 4, false)
       NRT_VARIANT3(19, 128, 10, 16, 8, true)  // PairNode regardless of the size cut-off
       NRT_VARIANT3(30, 128, 10, 16, 8, false, true)  // 2 x LDG.256 per node: measured 5-7 % slower than 4 loads
+      // leaf batching / retire batching knobs <.., leaf-again-min, leaf slots, deferred retire>; 4x/6x = PairNode, 5x/7x = WideNode
+      NRT_VARIANT3(40, 128, 10, 16, 8, true, false, 33, 1, false)
+      NRT_VARIANT3(41, 128, 10, 16, 8, true, false, 33, 2, false)
+      NRT_VARIANT3(42, 128, 10, 16, 8, true, false, 1, 1, true)
+      NRT_VARIANT3(43, 128, 10, 16, 8, true, false, 33, 1, true)
+      NRT_VARIANT3(44, 128, 10, 16, 8, true, false, 33, 2, true)
+      NRT_VARIANT3(45, 128, 10, 16, 8, true, false, 1, 2, false)
+      NRT_VARIANT3(46, 128, 10, 16, 12, true, false, 33, 1, false)
+      NRT_VARIANT3(47, 128, 10, 16, 16, true, false, 33, 1, false)
+      NRT_VARIANT3(48, 128, 10, 16, 12, true, false, 33, 2, false)
+      NRT_VARIANT3(49, 128, 10, 16, 16, true, false, 33, 2, false)
+      NRT_VARIANT3(50, 128, 10, 16, 8, false, false, 33, 1, false)
+      NRT_VARIANT3(51, 128, 10, 16, 8, false, false, 33, 2, false)
+      NRT_VARIANT3(52, 128, 10, 16, 8, false, false, 1, 1, true)
+      NRT_VARIANT3(53, 128, 10, 16, 8, false, false, 33, 1, true)
+      NRT_VARIANT3(54, 128, 10, 16, 8, false, false, 33, 2, true)
+      NRT_VARIANT3(55, 128, 10, 16, 8, false, false, 1, 2, false)
+      NRT_VARIANT3(56, 128, 10, 16, 12, false, false, 33, 1, false)
+      NRT_VARIANT3(57, 128, 10, 16, 16, false, false, 33, 1, false)
+      NRT_VARIANT3(58, 128, 10, 16, 12, false, false, 33, 2, false)
+      NRT_VARIANT3(59, 128, 10, 16, 16, false, false, 33, 2, false)
+      NRT_VARIANT3(60, 128, 10, 16, 8, true, false, 8, 1, false)
+      NRT_VARIANT3(61, 128, 10, 16, 8, true, false, 12, 1, false)
+      NRT_VARIANT3(62, 128, 10, 16, 8, true, false, 16, 1, false)
+      NRT_VARIANT3(63, 128, 10, 16, 8, true, false, 8, 2, false)
+      NRT_VARIANT3(64, 128, 10, 16, 8, true, false, 12, 2, false)
+      NRT_VARIANT3(65, 128, 10, 16, 8, true, false, 16, 2, false)
+      NRT_VARIANT3(66, 128, 10, 16, 8, true, false, 24, 2, false)
+      NRT_VARIANT3(67, 128, 10, 16, 8, true, false, 12, 2, true)
+      NRT_VARIANT3(68, 128, 10, 16, 12, true, false, 12, 2, false)
+      NRT_VARIANT3(69, 128, 10, 16, 4, true, false, 33, 2, false)
+      NRT_VARIANT3(70, 128, 10, 16, 8, false, false, 8, 1, false)
+      NRT_VARIANT3(71, 128, 10, 16, 8, false, false, 12, 1, false)
+      NRT_VARIANT3(72, 128, 10, 16, 8, false, false, 16, 1, false)
+      NRT_VARIANT3(73, 128, 10, 16, 8, false, false, 8, 2, false)
+      NRT_VARIANT3(74, 128, 10, 16, 8, false, false, 12, 2, false)
+      NRT_VARIANT3(75, 128, 10, 16, 8, false, false, 16, 2, false)
+      NRT_VARIANT3(76, 128, 10, 16, 8, false, false, 24, 2, false)
+      NRT_VARIANT3(77, 128, 10, 16, 8, false, false, 12, 2, true)
+      NRT_VARIANT3(78, 128, 10, 16, 12, false, false, 12, 2, false)
+      NRT_VARIANT3(79, 128, 10, 16, 4, false, false, 33, 2, false)
       default:
         set_error("nrt_traverse: unknown kernel variant in flags");
         return NRT_ERR_INVALID;
@@ -580,6 +627,35 @@ int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const
   return launch_fast<SoaRays, false>(a, r, capacity, d_hits, nullptr, opt, flags, nullptr, s, d_count);
 }
 
+// Experiment selector for the fused launches of the AO / path passes (tools/ao_exp_sweep.py): NRT_AO_EXP="<p><a><r><s>",
+// one digit each for the camera-ray launch, the AO launch, the path tracer's radiance launch and its shadow launch;
+// 0 = the default policy.  Read at every launch (cheap) so that one
+// process can sweep.
+//   1: one leaf round per outer iteration   2: a second round only with >= 12 leaves
+//   3: two leaf slots, one round            4: two leaf slots, second round with >= 12 leaves
+//   5: deferred retire                      6: (2) + deferred retire        7: (4) + deferred retire
+//   8: the policy before leaf batching (every leaf round runs, retire at once)
+static int ao_exp(int which) {
+  const char *e = getenv("NRT_AO_EXP");
+  if (!e || !e[0]) return 0;
+  for (int k = 0; k < which; ++k)
+    if (!e[k + 1]) return 0;
+  const int d = e[which] - '0';
+  return (d < 0 || d > 8) ? 0 : d;
+}
+#define NRT_AO_EXP_SWITCH(which, MINB, PAIR, CALL)                                    \
+  switch (ao_exp(which)) {                                                      \
+    case 1: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 33, 1, false> PX; return CALL; } \
+    case 2: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, false> PX; return CALL; } \
+    case 3: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 33, 2, false> PX; return CALL; } \
+    case 4: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 2, false> PX; return CALL; } \
+    case 5: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 1, 1, true> PX; return CALL; }   \
+    case 6: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, true> PX; return CALL; }  \
+    case 7: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 2, true> PX; return CALL; }  \
+    case 8: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 1, 1, false> PX; return CALL; }  \
+    default: break;                                                             \
+  }
+
 // Fused wavefront launches (render.cu): the retire step spawns the AO ray / accumulates visibility.
 template <class Epi, class P = DefaultPolicy, class Rays = SoaRays>
 static int launch_fused(const Accel *a, Rays rays, size_t n, const unsigned long long *n_ptr, Epi epi,
@@ -601,13 +677,22 @@ int launch_traverse_camera_fused(const Accel *a, const Wave &w, const nrt_ao_par
                                  const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   PrimaryToAoEpilogue<true> epi{p, slot0, w, a->d_verts, a->d_faces, d_accum, d_wave_counters};
   if (count == 0) return NRT_OK;
-  return launch_fast3_coherent<CameraRays, false>(a, CameraRays(p, slot0), count, epi, opt, flags, nullptr, nullptr, s);
+  if (a->n_wide * sizeof(PairNode) <= kPair128MaxBytes) {
+    NRT_AO_EXP_SWITCH(0, 10, true, (launch_fast3_any<CameraRays, false, PX>(a, CameraRays(p, slot0), count, epi, opt, flags,
+                                                                        nullptr, nullptr, s)))
+  }
+  if (a->n_wide * sizeof(PairNode) > kPair128MaxBytes)
+    return launch_fast3_any<CameraRays, false, IncoherentCameraPolicy>(a, CameraRays(p, slot0), count, epi, opt, flags, nullptr,
+                                                                       nullptr, s);
+  return launch_fast3_any<CameraRays, false, CameraPolicy>(a, CameraRays(p, slot0), count, epi, opt, flags, nullptr, nullptr, s);
 }
 
 int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long long *d_count, size_t capacity,
                              float *d_accum, unsigned long long *d_totals, const TraceOptions16 &opt, uint32_t flags,
                              cudaStream_t s) {
   AoAccumulateEpilogue epi{w.ao_pix, d_accum, d_totals};
+  NRT_AO_EXP_SWITCH(1, 10, false, (launch_fused<AoAccumulateEpilogue, PX>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity,
+                                                                      d_count, epi, opt, flags, s)))
   return launch_fused<AoAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count, epi,
                                                               opt, flags, s);
 }
@@ -615,7 +700,10 @@ int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long 
 int launch_traverse_path_radiance(const Accel *a, const PathShadeEpilogue &epi, const unsigned long long *d_count,
                                   size_t capacity, const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   // the shading block needs more registers than the plain traversal: 8 CTAs/SM (64 registers) instead of 10
-  return launch_fused<PathShadeEpilogue, Policy3<128, 8, 16, 8, false> >(
+  NRT_AO_EXP_SWITCH(2, 8, false, (launch_fused<PathShadeEpilogue, PX>(a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]},
+                                                                      capacity, d_count, epi, opt, flags, s)))
+  // its retire step IS the shading block: deferred retire (it runs with more lanes), profiles/r02_leaf_batching_sweep.md
+  return launch_fused<PathShadeEpilogue, Policy3<128, 8, 16, 8, false, false, 1, 1, true> >(
       a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]}, capacity, d_count, epi, opt, flags, s);
 }
 
@@ -623,6 +711,8 @@ int launch_traverse_path_shadow(const Accel *a, const PathQueues &q, const unsig
                                 size_t capacity, float *d_accum, const TraceOptions16 &opt, uint32_t flags,
                                 cudaStream_t s) {
   ShadowAccumulateEpilogue epi{q.sh_contrib_pix, d_accum};
+  NRT_AO_EXP_SWITCH(3, 10, false, (launch_fused<ShadowAccumulateEpilogue, PX>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity,
+                                                                           d_count, epi, opt, flags, s)))
   return launch_fused<ShadowAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity, d_count,
                                                                   epi, opt, flags, s);
 }

@@ -136,7 +136,8 @@ __device__ __forceinline__ void ldg256(const void *p, float4 &a, float4 &b) {
 
 constexpr int kNone3 = kEmptyLeaf;  // "no node": finished, or (with a non-empty stack) waiting for a pop
 
-template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_, bool PAIR128_ = true, bool LOAD256_ = false>
+template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_, bool PAIR128_ = true, bool LOAD256_ = false,
+          int LEAF_AGAIN_MIN_ = 1, int LEAF_SLOTS_ = 1, bool DEFER_RETIRE_ = false>
 struct Policy3 {
   static constexpr int kBlock = BLOCK_;
   static constexpr int kMinBlocks = MINB_;
@@ -147,6 +148,15 @@ struct Policy3 {
   static constexpr bool kPair128 = PAIR128_;
   // 64-byte node only: fetch it with two 256-bit loads instead of four (the L1 wavefront count of incoherent rays)
   static constexpr bool kLoad256 = LOAD256_;
+  // after the first leaf round of an outer iteration, another one runs only while at least this many lanes hold a
+  // leaf (1: until none is left; 33: one round) -- a lane's second leaf (found while the first was postponed) is
+  // otherwise tested in a round of its own with the few lanes that have one; carried over, it joins the next phase's
+  static constexpr int kLeafAgainMin = LEAF_AGAIN_MIN_;
+  // postponed leaves a lane may hold before it parks (1 or 2)
+  static constexpr int kLeafSlots = LEAF_SLOTS_;
+  // true: finished rays wait for the retire step until retired + empty lanes reach kRefillMin (or nothing else is
+  // left to do), so that the epilogue and the refill that follows run with more lanes
+  static constexpr bool kDeferRetire = DEFER_RETIRE_;
 };
 
 // DEPTH: capacity of the per-lane stack (entries); chosen by the launcher from the tree depth, so a push can
@@ -175,6 +185,7 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
   float min_t = 0.0f;
   bool alive = false;
   int cur = kNone3, leaf = kNone3;
+  int leaf2 = kNone3;  // second postponed leaf (P::kLeafSlots == 2 only; leaf2 != kNone3 implies leaf != kNone3)
   bool exhausted = false;
   unsigned long long n_boxes = 0, n_prims = 0;
   // COUNT only: lane-state histogram of the warp's iterations (nrt_traverse_lane_stats_device; lane 0 accumulates)
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
           sp = 0;
           cur = range_has_nan(min_t, max_t) ? kNone3 : 0;
           leaf = kNone3;
+          leaf2 = kNone3;
           if (COUNT) n_boxes += 1;
         }
       }
@@ -241,6 +253,9 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
             cur = (int)e.x;
             if (cur < 0 && leaf == kNone3) {
               leaf = cur;
+              cur = kNone3;
+            } else if (P::kLeafSlots == 2 && cur < 0 && leaf2 == kNone3) {
+              leaf2 = cur;
               cur = kNone3;
             }
           }
@@ -290,17 +305,22 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
           if (cur < 0 && cur != kNone3 && leaf == kNone3) {  // postpone the first leaf, keep descending
             leaf = cur;
             cur = kNone3;
+          } else if (P::kLeafSlots == 2 && cur < 0 && cur != kNone3 && leaf2 == kNone3) {
+            leaf2 = cur;
+            cur = kNone3;
           }
         }
       }
     }
 
     // ---- leaves
-    for (;;) {
-      if (!__any_sync(FULL_MASK, leaf != kNone3)) break;
+    for (bool first_round = true;; first_round = false) {
+      const unsigned with_leaf = __ballot_sync(FULL_MASK, leaf != kNone3);
+      if (with_leaf == 0u) break;
+      if (P::kLeafAgainMin > 1 && !first_round && __popc(with_leaf) < P::kLeafAgainMin) break;  // carried over
       if (COUNT) {
         st[7] += 1;                                                // leaf-phase rounds
-        st[8] += __popc(__ballot_sync(FULL_MASK, leaf != kNone3));  // lanes that enter a round with a leaf
+        st[8] += __popc(with_leaf);  // lanes that enter a round with a leaf
       }
       if (leaf != kNone3) {
         uint32_t slot = (uint32_t)(~leaf);
@@ -316,24 +336,42 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
           slot++;
         }
         leaf = kNone3;
-        if (cur < 0 && cur != kNone3) {  // a second leaf was waiting
-          leaf = cur;
-          cur = kNone3;
+        if (P::kLeafSlots == 2) {
+          leaf = leaf2;
+          leaf2 = kNone3;
+        }
+        if (cur < 0 && cur != kNone3) {  // a leaf was waiting in cur (the lane was parked)
+          if (leaf == kNone3) {
+            leaf = cur;
+            cur = kNone3;
+          } else if (P::kLeafSlots == 2) {  // leaf2 was just vacated
+            leaf2 = cur;
+            cur = kNone3;
+          }
         }
       }
     }
 
     // ---- retire: the epilogue (store the hit / spawn the AO ray / accumulate / shade) runs warp-wide
     const bool retiring = alive && cur == kNone3 && leaf == kNone3 && sp == 0;
+    bool retire_now;
+    if (P::kDeferRetire) {
+      // wait until the retire step and the refill behind it have enough lanes -- unless the ray set is exhausted
+      // (no refill will come) or no lane has anything else to do
+      const unsigned rm = __ballot_sync(FULL_MASK, retiring);
+      const unsigned idle = rm | __ballot_sync(FULL_MASK, !alive);
+      retire_now = rm != 0u && (exhausted || idle == FULL_MASK || __popc(idle) >= P::kRefillMin);
+    } else {
+      retire_now = __any_sync(FULL_MASK, retiring);
+    }
     if (COUNT) {
       st[12] += 1;  // outer iterations
-      const unsigned rm = __ballot_sync(FULL_MASK, retiring);
-      if (rm) {
-        st[10] += 1;           // retire events
-        st[11] += __popc(rm);  // lanes retiring
+      if (retire_now) {
+        st[10] += 1;                                              // retire events
+        st[11] += __popc(__ballot_sync(FULL_MASK, retiring));  // lanes retiring
       }
     }
-    if (__any_sync(FULL_MASK, retiring)) {
+    if (retire_now) {
       size_t ray_idx = 0;
       float max_t = 0.0f;
       uint32_t payload[PW > 0 ? PW : 1];
@@ -351,7 +389,7 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
       }
       epi(retiring, ray_idx, best.t, best.u, best.v, best.prim, max_t, payload);
     }
-    if (retiring) alive = false;
+    if (retiring && retire_now) alive = false;
   }
 
   if (COUNT) {

@@ -8,7 +8,7 @@ from nanort_b200 import api, scenes as S
 
 variants = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 2, 4, 5, 6, 8, 9, 10, 11, 21, 30, 40, 42]
 scenes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["sphere_grid", "terrain"]
-W, H, spp = 1920, 1080, 2
+W, H, spp = 1920, 1080, int(os.environ.get("NRT_SWEEP_SPP", "2"))
 for scene in scenes:
     v, f = S.make_scene(scene)
     acc = api.BVHAccel(); acc.Build(len(f), v, f)
