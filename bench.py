@@ -812,6 +812,36 @@ def main():
     sustained = {"value": rays_all * sus_steps / (ms_sus_max * 1e-3) / 1e6, "unit": UNIT, "steps": sus_steps,
                  "seconds": ms_sus_max * 1e-3}
 
+    # ---- opt-in extra, NOT part of `value`: the same pass with NRT_TRAVERSE_ANY_HIT on the AO launch (the occlusion
+    # rays stop at their first hit; nanort itself has no any-hit).  Same framebuffer bit for bit, fewer node visits.
+    extras = {}
+    if not distributed:
+        try:
+            p_any = ao_params(api, cam, WIDTH, HEIGHT, spp_total, diag, n_shards, shard, flags=api.TRAVERSE_ANY_HIT)
+            ref_frame = accum.clone()
+            any_frame = torch.zeros_like(accum)
+            for _ in range(2):
+                any_frame.zero_()
+                ra = acc.RenderAO(p_any, any_frame.data_ptr(), want_result=True)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(args.steps):
+                any_frame.zero_()
+                acc.RenderAO(p_any, any_frame.data_ptr(), want_result=False)
+            a1.record()
+            torch.cuda.synchronize(dev)
+            ms_any = a0.elapsed_time(a1)
+            extras["occlusion_any_hit"] = {
+                "value": rays_step * args.steps / (ms_any * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_any / args.steps,
+                "ao_launch_ms": float(ra.ao_traverse_ms), "closest_hit_ao_launch_ms": float(r.ao_traverse_ms),
+                "frame_identical_to_closest_hit": bool(torch.equal(any_frame, ref_frame)),
+                "occluded_identical": int(ra.ao_hits) == int(r.ao_hits),
+                "note": "opt-in (nrt_ao_params.flags |= NRT_TRAVERSE_ANY_HIT); the headline `value` is closest-hit on "
+                        "every ray, like the reference's Traverse"}
+            del ref_frame, any_frame
+        except Exception as e:
+            extras["occlusion_any_hit"] = {"error": str(e)}
+
     # ---- roofline of the dominant kernel
     counts = acc.CountDevice(d_primary.data_ptr(), n_primary) + acc.CountDevice(d_ao.data_ptr(), n_ao)
     roofline = traversal_roofline(api, r, n_primary, n_ao, counts, clocks, local_rank)
@@ -855,6 +885,39 @@ def main():
                "measured_pinned_copy_gbs": {"h2d": h2d, "d2h": d2h, "note": "nrt_probe_copy_gbs, 1 GiB, this rank alone"},
                "achieved_copy_gbs_per_gpu": {"h2d": 36 * per_gpu / 1e9, "d2h": 17 * per_gpu / 1e9},
                "bound": "PCIe / host memory: 36 B up + 17 B down per ray"}
+        # opt-in compact records (NRT_TRAVERSE_RAY32: the 32-byte ray without nanort::Ray::type, no hit flags: a miss is
+        # prim_id == 0xFFFFFFFF): same hits, 32 B up + 16 B down per ray.  NOT the headline: the reference's Ray is 36 B.
+        try:
+            r32 = np.dtype((np.void, 32))
+            hp32, ha32 = api.PinnedArray(n_primary, r32), api.PinnedArray(max(n_ao, 1), r32)
+            hp32.array.view(np.uint8).reshape(-1, 32)[:] = hp.array.view(np.uint8).reshape(-1, 36)[:, :32]
+            ha32.array.view(np.uint8).reshape(-1, 32)[:n_ao] = ha.array.view(np.uint8).reshape(-1, 36)[:n_ao, :32]
+            hits_p2 = api.PinnedArray(n_primary, S.HIT_DTYPE)
+
+            def compact_step():
+                acc.Traverse(hp32.array, hits=hits_p2.array, mask=False, flags=api.TRAVERSE_RAY32)
+                acc.Traverse(ha32.array[:n_ao], hits=hits_a.array[:n_ao], mask=False, flags=api.TRAVERSE_RAY32)
+
+            for _ in range(2):
+                compact_step()
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                compact_step()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            tc = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if distributed:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            same = bool(np.array_equal(hits_p2.array.view(np.uint32), hits_p.array.view(np.uint32)))
+            e2e["compact_records"] = {"value": rays_all * args.steps / float(tc.item()) / 1e6, "unit": UNIT,
+                                      "api": "nrt_traverse(..., hit_mask = NULL, NRT_TRAVERSE_RAY32)",
+                                      "h2d_bytes_per_step": int(32 * (n_primary + n_ao)),
+                                      "d2h_bytes_per_step": int(16 * (n_primary + n_ao)),
+                                      "hits_identical_to_the_36_byte_call": same}
+            del hp32, ha32, hits_p2
+        except Exception as e:  # a reporting extra: the bench line survives without it
+            e2e["compact_records"] = {"error": str(e)}
         # for comparison, the wavefront entry point end to end: camera parameters in (host struct), framebuffer out to
         # pinned host memory every step -- what a renderer pays when it hands the whole pass to the library
         fb_host = torch.empty(WIDTH * HEIGHT, dtype=torch.float32).pin_memory()
@@ -923,7 +986,7 @@ def main():
             "build": {"device_ms": stats["build_secs"] * 1e3, "wall_ms_incl_upload": build_wall_ms,
                       "nodes": stats["num_leaf_nodes"] + stats["num_branch_nodes"], "depth": stats["max_tree_depth"]},
             "rays_per_step": rays_all, "ao_occluded_fraction": float(r.ao_hits) / max(1, r.ao_rays),
-            "configs": configs,
+            "extras": extras, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if comm is not None:

@@ -41,6 +41,21 @@ extern "C" {
 #define NRT_TRAVERSE_CPP03_INVERSE 2u /* vsafe_inverse sign convention of the C++03 build (nanort.h:440-462:
                                         -0.0f -> +inf).  Default is the C++11 one (copysign, :418-439)   */
 
+/* nrt_traverse / nrt_traverse_device: the ray array holds 32-byte records {org[3], dir[3], min_t, max_t} -- nanort::Ray
+ * (nanort.h:474-496) without its `type` word, which Traverse never reads -- 16-byte aligned.  Opt-in for callers bound by
+ * the host link: 32 B up (+ 16 B down with hit_mask == NULL: a miss is prim_id == 0xFFFFFFFF) instead of 36 + 17 per ray.
+ * Same hits bit for bit.  Triangle accels only. */
+#define NRT_TRAVERSE_RAY32 4u
+
+/* Occlusion queries (opt-in; nanort itself has no any-hit, examples/path_tracer/main.cc:675-701 asks Traverse for the
+ * closest hit and looks at the bool): the ray stops at the first primitive it hits inside [min_t, max_t).
+ *   nrt_ao_params.flags / nrt_path_params.flags: the AO / shadow launches of the wavefront passes -- the framebuffer
+ *     is the same bit for bit (only "occluded or not" reaches it); camera and bounce rays stay closest-hit.
+ *   nrt_traverse / nrt_traverse_device: hit_mask (and prim_id != 0xFFFFFFFF) is the same; the RECORD of a hit ray is
+ *     that of some primitive on the ray, not necessarily the closest.
+ * Fast path only (ignored with NRT_TRAVERSE_CONFORMANCE).  Triangle accels only. */
+#define NRT_TRAVERSE_ANY_HIT 8u
+
 /* nrt_ao_params.flags only: run the AO stages as stand-alone kernels instead of fused into the traversal
  * kernel's retire step (A/B and equivalence tests; results are identical) */
 #define NRT_AO_UNFUSED 0x10000u

@@ -26,6 +26,8 @@ BUILD_REFERENCE_CPP03_ORDER = 2   # ... in the serial build's node order
 TRAVERSE_FAST = 0
 TRAVERSE_CONFORMANCE = 1
 TRAVERSE_CPP03_INVERSE = 2
+TRAVERSE_ANY_HIT = 8  # occlusion query: stop at the first hit inside [min_t, max_t) (see include/nanort_b200.h)
+TRAVERSE_RAY32 = 4  # 32-byte ray records {org[3], dir[3], min_t, max_t} (no `type` word), 16-byte aligned
 
 BUILD_OPT_DTYPE = np.dtype(
     [
@@ -393,12 +395,14 @@ class BVHAccel:
         """Batch of BVHAccel::Traverse calls on HOST arrays (nrt_traverse): returns (hits, mask);
         mask[i] is Traverse's bool, hits[i] = {u,v,t,prim_id} where mask[i] == 1."""
         rays = np.ascontiguousarray(rays)
-        assert rays.dtype.itemsize == 36
+        assert rays.dtype.itemsize == (32 if int(flags) & TRAVERSE_RAY32 else 36)
         n = len(rays)
         if hits is None:
             hits = np.zeros(n, HIT_DTYPE)
         if mask is None:
             mask = np.zeros(n, np.uint8)
+        elif mask is False:  # no hit flags wanted: a miss is prim_id == 0xFFFFFFFF
+            mask = None
         _check(lib().nrt_traverse(self._h, _p(rays), n, _p(hits), _p(mask), _p(options), int(flags)))
         return hits, mask
 

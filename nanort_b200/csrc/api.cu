@@ -467,6 +467,7 @@ int nrt_traverse(const nrt_accel *h, const void *rays_36B, size_t n_rays, void *
   chunk = std::min(n_rays, a->stage_rays);
   const char *src = static_cast<const char *>(rays_36B);
   char *dst = static_cast<char *>(hits_16B);
+  const size_t ray_bytes = (flags & NRT_TRAVERSE_RAY32) ? 32 : sizeof(Ray36);  // the staging slots hold 36 B per ray
   size_t done = 0;
   int slot = 0;
   cudaError_t e = cudaSuccess;
@@ -476,7 +477,7 @@ int nrt_traverse(const nrt_accel *h, const void *rays_36B, size_t n_rays, void *
     // the slot's previous chunk (3 iterations ago) must have drained before its buffers are reused
     e = cudaStreamSynchronize(s);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(a->d_stage_rays[slot], src + done * sizeof(Ray36), m * sizeof(Ray36), cudaMemcpyHostToDevice, s);
+      e = cudaMemcpyAsync(a->d_stage_rays[slot], src + done * ray_bytes, m * ray_bytes, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) break;
     rc = launch_traverse(a, static_cast<const Ray36 *>(a->d_stage_rays[slot]), m,
                          static_cast<Hit16 *>(a->d_stage_hits[slot]),

@@ -40,6 +40,24 @@ struct AosRays {
   }
 };
 
+// 32-byte ray records (NRT_TRAVERSE_RAY32): {org.xyz, dir.x} {dir.yz, min_t, max_t}, two 128-bit loads
+struct Aos32Rays {
+  static constexpr int kPayloadWords = 0;
+  const float4 *rays;
+  __device__ __forceinline__ void load(size_t i, float &ox, float &oy, float &oz, float &dx, float &dy,
+                                       float &dz, float &tmin, float &tmax, uint32_t * = nullptr) const {
+    const float4 a = __ldcs(rays + 2 * i), b = __ldcs(rays + 2 * i + 1);
+    ox = a.x;
+    oy = a.y;
+    oz = a.z;
+    dx = a.w;
+    dy = b.x;
+    dz = b.y;
+    tmin = b.z;
+    tmax = b.w;
+  }
+};
+
 struct SoaRays {
   static constexpr int kPayloadWords = 0;
   const float4 *org_tmin;
@@ -602,9 +620,25 @@ static int launch_conf(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
 int launch_traverse(const Accel *a, const Ray36 *d_rays, size_t n, Hit16 *d_hits, uint8_t *d_mask,
                     const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   if (n == 0) return NRT_OK;
+  if (flags & NRT_TRAVERSE_RAY32) {  // compact records: default policy only (the experiment variants read Ray36)
+    if (a->prim_kind != 0 || (reinterpret_cast<uintptr_t>(d_rays) & 15u) != 0) {
+      set_error("nrt_traverse: NRT_TRAVERSE_RAY32 needs a triangle accel and 16-byte aligned rays");
+      return NRT_ERR_INVALID;
+    }
+    Aos32Rays r32{reinterpret_cast<const float4 *>(d_rays)};
+    if (flags & NRT_TRAVERSE_CONFORMANCE)
+      return launch_conf<Aos32Rays, false>(a, r32, n, d_hits, d_mask, opt, flags, nullptr, s);
+    const StoreHitsEpilogue epi{d_hits, d_mask};
+    if (flags & NRT_TRAVERSE_ANY_HIT)
+      return launch_fast3_coherent<Aos32Rays, false>(a, r32, n, AnyHit<StoreHitsEpilogue>(epi), opt, flags, nullptr, nullptr, s);
+    return launch_fast3_coherent<Aos32Rays, false>(a, r32, n, epi, opt, flags, nullptr, nullptr, s);
+  }
   if (a->prim_kind != 0) return launch_traverse_prims(a, d_rays, n, d_hits, d_mask, opt, flags, s);  // spheres ...
   AosRays r{d_rays};
   if (flags & NRT_TRAVERSE_CONFORMANCE) return launch_conf<AosRays, false>(a, r, n, d_hits, d_mask, opt, flags, nullptr, s);
+  if (flags & NRT_TRAVERSE_ANY_HIT)  // occlusion query: default policy only
+    return launch_fast3_coherent<AosRays, false>(a, r, n, AnyHit<StoreHitsEpilogue>(StoreHitsEpilogue{d_hits, d_mask}), opt,
+                                                 flags, nullptr, nullptr, s);
   return launch_fast<AosRays, false>(a, r, n, d_hits, d_mask, opt, flags, nullptr, s);
 }
 
@@ -691,6 +725,9 @@ int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long 
                              float *d_accum, unsigned long long *d_totals, const TraceOptions16 &opt, uint32_t flags,
                              cudaStream_t s) {
   AoAccumulateEpilogue epi{w.ao_pix, d_accum, d_totals};
+  if (flags & NRT_TRAVERSE_ANY_HIT)
+    return launch_fused<AnyHit<AoAccumulateEpilogue>, IncoherentPolicy>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count,
+                                                                        AnyHit<AoAccumulateEpilogue>(epi), opt, flags, s);
   NRT_AO_EXP_SWITCH(1, 10, false, (launch_fused<AoAccumulateEpilogue, PX>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity,
                                                                       d_count, epi, opt, flags, s)))
   return launch_fused<AoAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count, epi,
@@ -711,6 +748,10 @@ int launch_traverse_path_shadow(const Accel *a, const PathQueues &q, const unsig
                                 size_t capacity, float *d_accum, const TraceOptions16 &opt, uint32_t flags,
                                 cudaStream_t s) {
   ShadowAccumulateEpilogue epi{q.sh_contrib_pix, d_accum};
+  if (flags & NRT_TRAVERSE_ANY_HIT)
+    return launch_fused<AnyHit<ShadowAccumulateEpilogue>, IncoherentPolicy>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity,
+                                                                            d_count, AnyHit<ShadowAccumulateEpilogue>(epi), opt,
+                                                                            flags, s);
   NRT_AO_EXP_SWITCH(3, 10, false, (launch_fused<ShadowAccumulateEpilogue, PX>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity,
                                                                            d_count, epi, opt, flags, s)))
   return launch_fused<ShadowAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity, d_count,

@@ -349,6 +349,14 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
             cur = kNone3;
           }
         }
+        // occlusion query (NRT_TRAVERSE_ANY_HIT): a hit inside [min_t, max_t) ends the ray.  A record accepted AT
+        // max_t is a miss (nanort.h:2552) and does not.
+        if (Epi::kAnyHit && best.prim != 0xFFFFFFFFu && best.t < __uint_as_float(lstk[DEPTH + 1].x)) {
+          sp = 0;
+          cur = kNone3;
+          leaf = kNone3;
+          leaf2 = kNone3;
+        }
       }
     }
 

@@ -240,6 +240,7 @@ __device__ __forceinline__ void make_ao_ray(const nrt_ao_params &p, uint32_t pix
 // ---- retire-step functors of traverse_fast2_kernel.  Called by ALL 32 lanes of a warp (`retiring` says
 // whether this lane's ray just finished), so they may use full-mask warp votes.
 struct StoreHitsEpilogue {
+  static constexpr bool kAnyHit = false;  // true: the kernel retires a ray at its first hit inside [min_t, max_t)
   Hit16 *hits;
   uint8_t *mask;
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
@@ -257,6 +258,7 @@ struct StoreHitsEpilogue {
 // GEN: the primary rays were generated in the kernel (CameraRays) -- pixel and ray are recomputed from the slot.
 template <bool GEN>
 struct PrimaryToAoEpilogue {
+  static constexpr bool kAnyHit = false;
   nrt_ao_params p;
   unsigned long long slot0;
   Wave w;
@@ -318,6 +320,7 @@ struct PrimaryToAoEpilogue {
 
 // AO rays: an unoccluded ray adds 1 to its pixel; nothing else is written
 struct AoAccumulateEpilogue {
+  static constexpr bool kAnyHit = false;
   const uint32_t *ao_pix;
   float *accum;
   unsigned long long *totals;  // [1] occluded AO rays
@@ -376,6 +379,7 @@ struct PathMaterial {
 // Radiance rays of bounce `bounce`: the retire step is the reference's per-hit shading block
 // (examples/path_tracer/main.cc:856-976): normal, material, Fresnel, lobe probabilities, lobe choice.
 struct PathShadeEpilogue {
+  static constexpr bool kAnyHit = false;
   nrt_path_params p;
   unsigned long long slot0;
   int in;  // which radiance queue is being traversed; (in ^ 1) receives the continuation rays
@@ -595,6 +599,7 @@ struct PathShadeEpilogue {
 
 // Shadow rays: an unoccluded light sample adds its contribution (CheckForOccluder returned false)
 struct ShadowAccumulateEpilogue {
+  static constexpr bool kAnyHit = false;
   const float4 *contrib_pix;
   float *accum;
   __device__ __forceinline__ void operator()(bool retiring, size_t ray_idx, float t, float u, float v, uint32_t prim,
@@ -610,6 +615,13 @@ struct ShadowAccumulateEpilogue {
       atomicAdd(accum + 3 * pix + 2, c.z);
     }
   }
+};
+
+// NRT_TRAVERSE_ANY_HIT: the same retire steps on rays the kernel stops at their first hit
+template <class E>
+struct AnyHit : E {
+  static constexpr bool kAnyHit = true;
+  __host__ __device__ explicit AnyHit(const E &e) : E(e) {}
 };
 
 }  // namespace nrt

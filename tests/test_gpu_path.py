@@ -247,3 +247,28 @@ def test_path_tracer_diffuse_only_energy_is_bounded():
         assert np.isfinite(got).all() and got.min() >= 0
         imgs.append(got.mean())
     assert imgs[0] <= imgs[1] + 1e-6 <= imgs[2] + 2e-6
+
+
+def test_any_hit_shadow_rays_give_the_same_image():
+    """NRT_TRAVERSE_ANY_HIT in nrt_path_params.flags: the shadow launches stop at the first occluder
+    (examples/path_tracer/main.cc:675-701 only looks at Traverse's bool) -- same ray counts, same image up to the order of
+    the float atomics."""
+    import torch
+    from nanort_b200 import api, scenes as S
+
+    v, f, mats, ids, emissive = S.cornell_with_materials()
+    W, H, spp, bounces, seed = 64, 48, 6, 7, 5
+    imgs, counts = [], []
+    for flags in (0, api.TRAVERSE_ANY_HIT):
+        acc, p, cam, keep = _setup(torch, api, S, v, f, mats, ids, emissive, None, W, H, spp, bounces, seed)
+        p.flags = flags
+        accum = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
+        r = acc.RenderPath(p, accum.data_ptr())
+        imgs.append(accum.cpu().numpy().astype(np.float64).reshape(-1, 3))
+        counts.append((r.camera_rays, r.radiance_rays, r.shadow_rays))
+    # same allowance as test_whole_pass_equals_the_sum_of_its_bounces: a radiance ray that hits two primitives at exactly
+    # the same t may pick either, run to run (queue compaction order)
+    assert counts[0][0] == counts[1][0] and counts[0][2] > 0
+    assert abs(counts[0][1] - counts[1][1]) <= 4 and abs(counts[0][2] - counts[1][2]) <= 4, counts
+    rel = np.max(np.abs(imgs[0] - imgs[1]) / np.maximum(np.abs(imgs[0]), 1.0), axis=1)
+    assert np.count_nonzero(rel > 1e-5) <= 4, np.count_nonzero(rel > 1e-5)

@@ -107,3 +107,45 @@ def test_tile_shards_add_up_to_the_single_shard_frame():
         rays += r.primary_rays + r.ao_rays
     assert torch.equal(total, full)
     assert rays == r_full.primary_rays + r_full.ao_rays
+
+
+@pytest.mark.parametrize("name,kw,W,H,spp", [("sphere_grid", dict(nx=4, nz=4), 200, 104, 4), ("terrain", dict(n=96), 160, 96, 3)])
+def test_any_hit_occlusion_rays_give_the_same_frame(name, kw, W, H, spp):
+    """NRT_TRAVERSE_ANY_HIT on the AO launch (nanort has only closest-hit, examples/path_tracer/main.cc:675-701 looks at
+    the bool): framebuffer and occluded count identical bit for bit; through nrt_traverse the hit flags are identical
+    and every record is a real hit at or behind the closest one."""
+    import torch
+    from nanort_b200 import api, scenes as S
+
+    v, f = S.make_scene(name, **kw)
+    acc = api.BVHAccel()
+    acc.Build(len(f), v, f)
+    bbox = acc.BoundingBox()
+    out = []
+    for flags in (0, api.TRAVERSE_ANY_HIT):
+        p, _ = _params(api, S, name, W, H, spp, bbox, flags=flags)
+        accum = torch.zeros(W * H, dtype=torch.float32, device="cuda")
+        r = acc.RenderAO(p, accum.data_ptr())
+        out.append((accum.cpu().numpy(), (r.primary_rays, r.ao_rays, r.ao_hits)))
+    assert out[0][1] == out[1][1] and out[0][1][2] > 0
+    assert np.array_equal(out[0][0], out[1][0])
+
+    p, _ = _params(api, S, name, W, H, spp, bbox)
+    n_slots = W * H * spp * 2
+    d_p = torch.empty(n_slots * 36, dtype=torch.uint8, device="cuda")
+    d_a = torch.empty(n_slots * 36, dtype=torch.uint8, device="cuda")
+    accum = torch.zeros(W * H, dtype=torch.float32, device="cuda")
+    n_p, n_a = acc.ExportAOWorkload(p, accum.data_ptr(), d_p.data_ptr(), d_a.data_ptr())
+    ao = d_a[: n_a * 36].cpu().numpy().view(S.RAY_DTYPE)
+    ch, cm = acc.Traverse(ao)
+    ah, am = acc.Traverse(ao, flags=api.TRAVERSE_ANY_HIT)
+    assert np.array_equal(am, cm)
+    hit = cm.astype(bool)
+    assert np.all(ah["prim_id"][~hit] == 0xFFFFFFFF) and np.all(ah["prim_id"][hit] < len(f))
+    assert np.all(ah["t"][hit] >= ch["t"][hit]) and np.all(ah["t"][hit] < ao["max_t"][hit]) and np.all(ah["t"][hit] >= ao["min_t"][hit])
+    # a record that differs from the closest one is a genuine hit of ITS triangle: re-trace with only that triangle allowed
+    other = np.flatnonzero(hit & (ah["prim_id"] != ch["prim_id"]))[:200]
+    for i in other:
+        o = api.BVHTraceOptions(prim_ids_range=(int(ah["prim_id"][i]), int(ah["prim_id"][i]) + 1))
+        h1, m1 = acc.Traverse(ao[i:i + 1], options=o)
+        assert m1[0] == 1 and h1.view(np.uint32).tolist() == ah[i:i + 1].view(np.uint32).tolist()

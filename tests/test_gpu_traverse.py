@@ -55,3 +55,34 @@ def test_adopted_tree_fast_path_matches_oracle(port, scene, kw, fix):
     got_h, got_m = acc.Traverse(rays, flags=api.TRAVERSE_FAST)
     res = compare_hits(port, v, f, rays, got_h, got_m, want_h, want_m)
     assert_parity(res)
+
+
+@pytest.mark.parametrize("conformance", [False, True])
+def test_compact_ray32_records_give_the_same_hits(conformance):
+    """NRT_TRAVERSE_RAY32: the 32-byte ray record {org, dir, min_t, max_t} (nanort::Ray without `type`, nanort.h:474-496)
+    and hit_mask == NULL give bit-identical hit records (misses: prim_id == 0xFFFFFFFF, t == max_t)."""
+    import torch
+    from nanort_b200 import api, scenes as S
+
+    v, f = S.make_scene("sphere_grid", nx=3, nz=3)
+    rays = _rays(S, "sphere_grid", v, f)
+    rays[::7]["max_t"] = 3.0  # some rays end before their hit
+    acc = api.BVHAccel()
+    acc.Build(len(f), v, f)
+    flags = api.TRAVERSE_CONFORMANCE if conformance else api.TRAVERSE_FAST
+    want_h, want_m = acc.Traverse(rays, flags=flags)
+    r32 = np.ascontiguousarray(rays.view(np.uint8).reshape(-1, 36)[:, :32]).view(np.float32).reshape(-1, 8)
+    # odd ray counts and more than one pipeline chunk's worth of bytes are covered by the sizes below
+    for n in (len(r32), 1, 33):
+        got_h, got_m = acc.Traverse(r32[:n].view(np.dtype((np.void, 32))).reshape(-1), flags=flags | api.TRAVERSE_RAY32, mask=False)
+        assert got_m is None
+        assert np.array_equal(got_h.view(np.uint32), want_h[:n].view(np.uint32))
+        assert np.array_equal(got_h["prim_id"] != 0xFFFFFFFF, want_m[:n].astype(bool))
+    # device-pointer form
+    d_r = torch.as_tensor(r32, device="cuda")
+    d_h = torch.zeros(len(r32) * 4, dtype=torch.int32, device="cuda")
+    acc.TraverseDevice(d_r.data_ptr(), len(r32), d_h.data_ptr(), flags=flags | api.TRAVERSE_RAY32)
+    assert np.array_equal(d_h.cpu().numpy().view(np.uint32).reshape(-1, 4), want_h.view(np.uint32).reshape(-1, 4))
+    # misaligned rays are refused, not mis-read
+    with pytest.raises(Exception):
+        acc.TraverseDevice(d_r.data_ptr() + 4, 8, d_h.data_ptr(), flags=flags | api.TRAVERSE_RAY32)
