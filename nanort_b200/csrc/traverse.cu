@@ -426,10 +426,11 @@ typedef FastPolicy<128, 10, 16, 8, 0, 0> OldDefaultPolicy;
 // runs only while >= 8 (coherent) / >= 12 (incoherent) lanes hold a leaf -- a lane's second leaf otherwise costs a
 // round of its own at ~5 active lanes; the camera-ray launch, whose retire step spawns the AO ray (630 instructions),
 // also waits with the retire step until retired + empty lanes reach the refill threshold.
-typedef Policy3<128, 10, 16, 8, true, false, 8> DefaultPolicy;
-typedef Policy3<128, 10, 16, 8, true, false, 12, 1, true> CameraPolicy;
-typedef Policy3<128, 10, 16, 8, false, false, 12> IncoherentPolicy;
-typedef Policy3<128, 10, 16, 8, false, false, 12, 1, true> IncoherentCameraPolicy;
+// Two node steps per evaluation of the node phase's exit conditions (+1.8 ... +2.8 %, same sweep file).
+typedef Policy3<128, 10, 16, 8, true, false, 8, 1, false, 2> DefaultPolicy;
+typedef Policy3<128, 10, 16, 8, true, false, 12, 1, true, 2> CameraPolicy;
+typedef Policy3<128, 10, 16, 8, false, false, 12, 1, false, 2> IncoherentPolicy;
+typedef Policy3<128, 10, 16, 8, false, false, 12, 1, true, 2> IncoherentCameraPolicy;
 // PairNode arrays above this size are not used (126 MB L2; the triangles want their share)
 constexpr size_t kPair128MaxBytes = (size_t)96 << 20;
 
@@ -570,6 +571,13 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
       NRT_VARIANT3(77, 128, 10, 16, 8, false, false, 12, 2, true)
       NRT_VARIANT3(78, 128, 10, 16, 12, false, false, 12, 2, false)
       NRT_VARIANT3(79, 128, 10, 16, 4, false, false, 33, 2, false)
+      // node steps per exit check (8x = PairNode, 9x = WideNode)
+      NRT_VARIANT3(80, 128, 10, 16, 8, true, false, 8, 1, false, 2)
+      NRT_VARIANT3(81, 128, 10, 16, 8, true, false, 8, 1, false, 3)
+      NRT_VARIANT3(82, 128, 10, 16, 8, true, false, 8, 1, false, 4)
+      NRT_VARIANT3(90, 128, 10, 16, 8, false, false, 12, 1, false, 2)
+      NRT_VARIANT3(91, 128, 10, 16, 8, false, false, 12, 1, false, 3)
+      NRT_VARIANT3(92, 128, 10, 16, 8, false, false, 12, 1, false, 4)
       default:
         set_error("nrt_traverse: unknown kernel variant in flags");
         return NRT_ERR_INVALID;
@@ -665,28 +673,30 @@ int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const
 // one digit each for the camera-ray launch, the AO launch, the path tracer's radiance launch and its shadow launch;
 // 0 = the default policy.  Read at every launch (cheap) so that one
 // process can sweep.
-//   1: one leaf round per outer iteration   2: a second round only with >= 12 leaves
-//   3: two leaf slots, one round            4: two leaf slots, second round with >= 12 leaves
+//   1: (2) + two node steps per exit check  2: a second round only with >= 12 leaves
+//   3: (6) + two node steps per exit check  4: two leaf slots, second round with >= 12 leaves
 //   5: deferred retire                      6: (2) + deferred retire        7: (4) + deferred retire
 //   8: the policy before leaf batching (every leaf round runs, retire at once)
+//   9: leaf batching + deferred retire, ONE node step per exit check
 static int ao_exp(int which) {
   const char *e = getenv("NRT_AO_EXP");
   if (!e || !e[0]) return 0;
   for (int k = 0; k < which; ++k)
     if (!e[k + 1]) return 0;
   const int d = e[which] - '0';
-  return (d < 0 || d > 8) ? 0 : d;
+  return (d < 0 || d > 9) ? 0 : d;
 }
 #define NRT_AO_EXP_SWITCH(which, MINB, PAIR, CALL)                                    \
   switch (ao_exp(which)) {                                                      \
-    case 1: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 33, 1, false> PX; return CALL; } \
+    case 1: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, false, 2> PX; return CALL; } \
     case 2: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, false> PX; return CALL; } \
-    case 3: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 33, 2, false> PX; return CALL; } \
+    case 3: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, true, 2> PX; return CALL; } \
     case 4: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 2, false> PX; return CALL; } \
     case 5: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 1, 1, true> PX; return CALL; }   \
     case 6: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, true> PX; return CALL; }  \
     case 7: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 2, true> PX; return CALL; }  \
     case 8: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 1, 1, false> PX; return CALL; }  \
+    case 9: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, true, 1> PX; return CALL; }  \
     default: break;                                                             \
   }
 
@@ -740,7 +750,7 @@ int launch_traverse_path_radiance(const Accel *a, const PathShadeEpilogue &epi, 
   NRT_AO_EXP_SWITCH(2, 8, false, (launch_fused<PathShadeEpilogue, PX>(a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]},
                                                                       capacity, d_count, epi, opt, flags, s)))
   // its retire step IS the shading block: deferred retire (it runs with more lanes), profiles/r02_leaf_batching_sweep.md
-  return launch_fused<PathShadeEpilogue, Policy3<128, 8, 16, 8, false, false, 1, 1, true> >(
+  return launch_fused<PathShadeEpilogue, Policy3<128, 8, 16, 8, false, false, 1, 1, true, 2> >(
       a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]}, capacity, d_count, epi, opt, flags, s);
 }
 

@@ -137,7 +137,7 @@ __device__ __forceinline__ void ldg256(const void *p, float4 &a, float4 &b) {
 constexpr int kNone3 = kEmptyLeaf;  // "no node": finished, or (with a non-empty stack) waiting for a pop
 
 template <int BLOCK_, int MINB_, int REFILL_MIN_, int NODE_EXIT_, bool PAIR128_ = true, bool LOAD256_ = false,
-          int LEAF_AGAIN_MIN_ = 1, int LEAF_SLOTS_ = 1, bool DEFER_RETIRE_ = false>
+          int LEAF_AGAIN_MIN_ = 1, int LEAF_SLOTS_ = 1, bool DEFER_RETIRE_ = false, int NODE_UNROLL_ = 1>
 struct Policy3 {
   static constexpr int kBlock = BLOCK_;
   static constexpr int kMinBlocks = MINB_;
@@ -157,6 +157,8 @@ struct Policy3 {
   // true: finished rays wait for the retire step until retired + empty lanes reach kRefillMin (or nothing else is
   // left to do), so that the epilogue and the refill that follows run with more lanes
   static constexpr bool kDeferRetire = DEFER_RETIRE_;
+  // node steps per evaluation of the node phase's exit conditions (two ballots + a population count per check)
+  static constexpr int kNodeUnroll = NODE_UNROLL_;
 };
 
 // DEPTH: capacity of the per-lane stack (entries); chosen by the launcher from the tree depth, so a push can
@@ -237,10 +239,13 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
 
     // ---- inner nodes.  A lane wants node work when it stands on a node, or stands nowhere but has stack entries.
     for (;;) {
-      const bool want = cur >= 0 || (cur == kNone3 && sp > 0);
+      bool want = cur >= 0 || (cur == kNone3 && sp > 0);
       const unsigned desc = __ballot_sync(FULL_MASK, want);
       if (desc == 0u) break;
       if (P::kNodeExit > 1 && __popc(desc) < P::kNodeExit && __any_sync(FULL_MASK, leaf != kNone3)) break;
+#pragma unroll
+      for (int rep = 0; rep < P::kNodeUnroll; ++rep) {
+      if (rep > 0) want = cur >= 0 || (cur == kNone3 && sp > 0);
       if (want) {
         // The one pop site.  Pops until the lane stands on a node again: entries that start behind the current best
         // are dropped without touching memory (same visit set as the reference's re-test at pop, nanort.h:2532), a
@@ -311,6 +316,7 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
           }
         }
       }
+      }  // rep
     }
 
     // ---- leaves
