@@ -23,6 +23,18 @@ p.ray_min_t, p.ray_max_t, p.ao_min_t, p.ao_max_t = 1e-3, 1e30, 1e-3, 2.0
 accum = torch.zeros(96 * 64, dtype=torch.float32, device="cuda")
 r = acc.RenderAO(p, accum.data_ptr())
 print("ao ok", r.primary_rays, r.ao_rays)
+# round 2, third session: any-hit occlusion rays (AO launch, nrt_traverse), 32-byte ray records
+p.flags = api.TRAVERSE_ANY_HIT
+accum2 = torch.zeros(96 * 64, dtype=torch.float32, device="cuda")
+r2 = acc.RenderAO(p, accum2.data_ptr())
+assert torch.equal(accum, accum2) and r2.ao_hits == r.ao_hits
+p.flags = 0
+ha, ma = acc.Traverse(rays, flags=api.TRAVERSE_ANY_HIT)
+assert np.array_equal(ma, m)
+r32 = np.ascontiguousarray(rays.view(np.uint8).reshape(-1, 36)[:, :32]).view(np.dtype((np.void, 32))).reshape(-1)
+h32, _ = acc.Traverse(r32, flags=api.TRAVERSE_RAY32, mask=False)
+assert np.array_equal(h32.view(np.uint32), acc.Traverse(rays)[0].view(np.uint32))
+print("any-hit / ray32 ok")
 insts = S.instances_mixed(7)
 accels, sc = {}, api.Scene()
 for iv, jf, x in insts:
