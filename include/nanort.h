@@ -764,8 +764,9 @@ class BVHAccel<float> {
 
 // ---- BVHAccel<double> ----------------------------------------------------------------------------
 // The fp64 instantiation (nrt_build_f64 / nrt_adopt_f64 / nrt_traverse_f64): same members as above.  The tree's
-// topology comes from the production builder, every node box is exact in double, Traverse computes in double in the
-// reference's visiting order -- t / u / v carry the reference's bits for the reported primitive.
+// topology comes from the production builder, every node box is exact in double, Traverse computes in double --
+// t / u / v carry the reference's bits for the reported primitive.  Traverse (one ray) walks in the reference's visiting
+// order; TraverseBatch uses the persistent-warp fast kernel (csrc/f64_fast.cuh) unless NANORT_B200_CONFORMANCE is defined.
 static_assert(sizeof(Ray<double>) == 72, "nanort::Ray<double> layout");
 static_assert(sizeof(BVHNode<double>) == 64, "nanort::BVHNode<double> layout");
 static_assert(sizeof(BVHBuildOptions<double>) == 32, "nanort::BVHBuildOptions<double> layout");
@@ -836,7 +837,8 @@ class BVHAccel<double> {
     if (!Ready(intersector)) return false;
     TriangleIntersection<double> rec;
     unsigned char hit = 0;
-    if (nrt_traverse_f64(handle_.get(), &ray, 1, &rec, &hit, &options, NANORT_B200_INVERSE_FLAG) != NRT_OK) {
+    // one ray: the reference-order kernel (a persistent-warp launch has nothing to amortise over)
+    if (nrt_traverse_f64(handle_.get(), &ray, 1, &rec, &hit, &options, NRT_TRAVERSE_CONFORMANCE | NANORT_B200_INVERSE_FLAG) != NRT_OK) {
       fprintf(stderr, "nanort_b200: Traverse<double> failed: %s\n", nrt_last_error());
       return false;
     }
@@ -860,7 +862,7 @@ class BVHAccel<double> {
       tmp.resize(n);
       hit_mask = tmp.data();
     }
-    if (nrt_traverse_f64(handle_.get(), rays, n, hits, hit_mask, &options, NANORT_B200_INVERSE_FLAG) != NRT_OK) {
+    if (nrt_traverse_f64(handle_.get(), rays, n, hits, hit_mask, &options, NANORT_B200_TRAVERSE_FLAGS) != NRT_OK) {
       fprintf(stderr, "nanort_b200: TraverseBatch<double> failed: %s\n", nrt_last_error());
       return static_cast<size_t>(-1);
     }

@@ -373,10 +373,17 @@ int nrt_scene_traverse_device(const nrt_scene *s, const void *d_rays_36B, size_t
  *   BVHAccel<double>::Build     nanort.h:1892-2149  -> nrt_build_f64: topology from the production builder over the
  *                               float-rounded geometry, then every node box refitted EXACTLY in double from the
  *                               double vertices (leaf = min/max of its triangles, branch = union of its children)
- *   BVHAccel<double>::Traverse  nanort.h:2487-2556  -> nrt_traverse_f64: the reference's visiting order with the double
- *                               specialisations (IntersectRayAABB<double> nanort.h:2327-2370, DBL_EPSILON in
- *                               vsafe_inverse) in double arithmetic; t / u / v are bit-identical to the reference's
- *                               for the reported primitive. */
+ *   BVHAccel<double>::Traverse  nanort.h:2487-2556  -> nrt_traverse_f64, two kernels like the float path, both with the
+ *                               double specialisations (IntersectRayAABB<double> nanort.h:2327-2370, DBL_EPSILON in
+ *                               vsafe_inverse) in double arithmetic, t / u / v bit-identical to the reference's for
+ *                               the reported primitive:
+ *                                 NRT_TRAVERSE_FAST (default)  persistent warps over a private 256-B child-pair /
+ *                                   96-B component-major triangle layout derived on first use (csrc/f64_fast.cuh);
+ *                                   near child first by entry distance, so WHICH of two primitives hit at exactly the
+ *                                   same t is reported may differ from the reference
+ *                                 NRT_TRAVERSE_CONFORMANCE     one thread per ray over the BVHNode<double> array in the
+ *                                   reference's visiting order: identical winners even for exact-t ties
+ *                               Host buffers; rays go up and records come back in chunks through three stream slots. */
 typedef struct nrt_accel_f64 nrt_accel_f64;
 int nrt_build_f64(const double *verts, size_t stride_bytes, size_t n_verts_or_0, const uint32_t *faces,
                   uint32_t n_prims, const void *build_opts_32B, nrt_accel_f64 **out);
@@ -396,7 +403,11 @@ int nrt_stats_f64(const nrt_accel_f64 *a, void *stats_16B);
 int nrt_bounding_box_f64(const nrt_accel_f64 *a, double bmin[3], double bmax[3]);
 int nrt_nodes_f64(nrt_accel_f64 *a, const void **nodes_64B, size_t *n_nodes, const uint32_t **indices,
                   size_t *n_indices);
-/* host pointers; hits[i] = {0, 0, max_t, ~0} and hit_mask[i] = 0 on a miss; flags: NRT_TRAVERSE_CPP03_INVERSE */
+/* host pointers; hits[i] = {0, 0, max_t, ~0} and hit_mask[i] = 0 on a miss;
+ * flags: NRT_TRAVERSE_FAST | NRT_TRAVERSE_CONFORMANCE, NRT_TRAVERSE_CPP03_INVERSE */
+/* (below) the same with DEVICE pointers, asynchronous on `stream` (at most 8 launches of one accel in flight) */
+int nrt_traverse_f64_device(const nrt_accel_f64 *a, const void *d_rays_72B, size_t n_rays, void *d_hits_32B,
+                            uint8_t *d_hit_mask, const void *trace_opts_16B, uint32_t flags, void *stream);
 int nrt_traverse_f64(const nrt_accel_f64 *a, const void *rays_72B, size_t n_rays, void *hits_32B, uint8_t *hit_mask,
                      const void *trace_opts_16B, uint32_t flags);
 

@@ -55,7 +55,7 @@ EXPORTS = [
     "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device", "nrt_render_path_device",
     "nrt_scene_commit", "nrt_scene_free", "nrt_scene_bounding_box", "nrt_scene_nodes", "nrt_scene_instance_state",
     "nrt_scene_traverse", "nrt_scene_traverse_device",
-    "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64",
+    "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64", "nrt_traverse_f64_device",
     "nrt_path_bounce_device", "nrt_build_prims", "nrt_list_node_intersections",
     "nrt_comm_unique_id", "nrt_comm_init", "nrt_comm_free", "nrt_comm_rank", "nrt_render_ao_sharded",
     "nrt_probe_read_gbs", "nrt_probe_copy_gbs", "nrt_traverse_lane_stats_device", "nrt_build_f64_ex",
@@ -165,6 +165,7 @@ def lib():
     L.nrt_bounding_box_f64.argtypes = [vp, vp, vp]
     L.nrt_nodes_f64.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
     L.nrt_traverse_f64.argtypes = [vp, vp, sz, vp, vp, vp, u32]
+    L.nrt_traverse_f64_device.argtypes = [vp, vp, sz, vp, vp, vp, u32, vp]
     L.nrt_path_bounce_device.argtypes = [vp, C.POINTER(PathParams), u32, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                          vp, u64p, u64p, C.c_int, vp]
     L.nrt_build_prims.argtypes = [u32, vp, sz, vp, u32, vp, C.POINTER(vp)]
@@ -678,10 +679,21 @@ class BVHAccelF64:
         idx = np.frombuffer((C.c_char * (ni.value * 4)).from_address(pi.value), np.uint32).copy()
         return nodes, idx
 
-    def Traverse(self, rays, options=None, flags=0):
+    def Traverse(self, rays, options=None, flags=0, hits=None, mask=None):
+        """Batch of BVHAccel<double>::Traverse calls on HOST arrays (nrt_traverse_f64).  flags: TRAVERSE_FAST (default,
+        persistent-warp kernel) or TRAVERSE_CONFORMANCE (the reference's visiting order), TRAVERSE_CPP03_INVERSE."""
         rays = np.ascontiguousarray(rays)
         assert rays.dtype.itemsize == 72
         n = len(rays)
-        hits, mask = np.zeros(n, HIT64_DTYPE), np.zeros(n, np.uint8)
+        if hits is None:
+            hits = np.zeros(n, HIT64_DTYPE)
+        if mask is None:
+            mask = np.zeros(n, np.uint8)
         _check(lib().nrt_traverse_f64(self._h, _p(rays), n, _p(hits), _p(mask), _p(options), int(flags)))
         return hits, mask
+
+    def TraverseDevice(self, d_rays_ptr, n, d_hits_ptr, d_mask_ptr=None, options=None, flags=0, stream=None):
+        """Device-pointer form (nrt_traverse_f64_device): 72-byte rays in, 32-byte records out."""
+        _check(lib().nrt_traverse_f64_device(self._h, C.c_void_p(d_rays_ptr), int(n), C.c_void_p(d_hits_ptr),
+                                             C.c_void_p(d_mask_ptr) if d_mask_ptr else None, _p(options), int(flags),
+                                             C.c_void_p(stream) if stream else None))

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace nrt {
 
@@ -69,8 +70,15 @@ struct AccelF64 {
   std::vector<uint32_t> h_indices;
   bool mirrors_valid = false;
   cudaStream_t stream = nullptr;
-  void *d_rays = nullptr, *d_hits = nullptr, *d_mask = nullptr;
+  // Traverse: three staging slots, each with its own stream (copy up / traverse / copy down overlap across chunks)
+  cudaStream_t tstream[3] = {nullptr, nullptr, nullptr};
+  void *d_rays[3] = {nullptr, nullptr, nullptr}, *d_hits[3] = {nullptr, nullptr, nullptr}, *d_mask[3] = {nullptr, nullptr, nullptr};
   size_t stage = 0;
+  // fast-path layout (f64_fast.cuh), derived on the first fast Traverse
+  void *d_pair = nullptr, *d_tris_fast = nullptr;
+  unsigned long long *d_cursor = nullptr;  // ring of 8 ray-pool cursors
+  unsigned cursor_next = 0;
+  bool fast_ready = false;
   std::mutex mu;
 };
 
@@ -81,9 +89,15 @@ void destroy_f64(AccelF64 *a) {
   cudaFree(a->d_indices);
   cudaFree(a->d_faces);
   cudaFree(a->d_verts);
-  cudaFree(a->d_rays);
-  cudaFree(a->d_hits);
-  cudaFree(a->d_mask);
+  for (int i = 0; i < 3; i++) {
+    cudaFree(a->d_rays[i]);
+    cudaFree(a->d_hits[i]);
+    cudaFree(a->d_mask[i]);
+    if (a->tstream[i]) cudaStreamDestroy(a->tstream[i]);
+  }
+  cudaFree(a->d_pair);
+  cudaFree(a->d_tris_fast);
+  cudaFree(a->d_cursor);
   if (a->stream) cudaStreamDestroy(a->stream);
   delete a;
 }
@@ -316,6 +330,64 @@ __global__ void __launch_bounds__(128)
   h.pad = 0;
   hits[i] = h;
   if (mask) mask[i] = hit ? 1 : 0;
+}
+
+#include "f64_fast.cuh"
+
+// PairNodeD / TriD arrays of the fast kernel from the BVHNode<double> array, indices_, faces and double vertices the
+// accel already holds on the device.  Called under a->mu.
+int derive_fast_layout_f64(AccelF64 *a) {
+  if (a->fast_ready) return NRT_OK;
+  const uint32_t nn = (uint32_t)a->n_nodes;
+  uint32_t *d_flags = nullptr, *d_widx = nullptr;
+  uint32_t n_branch = 0;
+  int rc = NRT_OK;
+  cudaStream_t s = a->stream;
+  cudaError_t e = cudaMalloc(&d_flags, sizeof(uint32_t) * (size_t)nn);
+  if (e == cudaSuccess) e = cudaMalloc(&d_widx, sizeof(uint32_t) * (size_t)nn);
+  if (e == cudaSuccess) {
+    f64_branch_flags_kernel<<<(nn + 255) / 256, 256, 0, s>>>(a->d_nodes, nn, d_flags);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) rc = exclusive_scan_u32(d_flags, d_widx, nn, &n_branch, s);
+  const size_t n_pair = n_branch > 0 ? n_branch : 1;
+  if (e == cudaSuccess && rc == NRT_OK) e = cudaMalloc(&a->d_pair, sizeof(PairNodeD) * n_pair);
+  if (e == cudaSuccess && rc == NRT_OK) e = cudaMalloc(&a->d_tris_fast, sizeof(TriD) * (size_t)a->n_prims);
+  if (e == cudaSuccess && rc == NRT_OK && !a->d_cursor) e = cudaMalloc(&a->d_cursor, sizeof(unsigned long long) * 8);
+  if (e == cudaSuccess && rc == NRT_OK) {
+    f64_tris_kernel<<<(a->n_prims + 255) / 256, 256, 0, s>>>(a->d_indices, a->d_faces, a->d_verts, a->n_prims,
+                                                            static_cast<TriD *>(a->d_tris_fast));
+    f64_pair_kernel<<<(nn + 255) / 256, 256, 0, s>>>(a->d_nodes, nn, d_widx, static_cast<PairNodeD *>(a->d_pair),
+                                                    static_cast<TriD *>(a->d_tris_fast));
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_flags);
+  cudaFree(d_widx);
+  if (e != cudaSuccess || rc != NRT_OK) {
+    cudaFree(a->d_pair);
+    cudaFree(a->d_tris_fast);
+    a->d_pair = a->d_tris_fast = nullptr;
+    return e != cudaSuccess ? cuda_fail(e, "derive_fast_layout_f64", __FILE__, __LINE__) : rc;
+  }
+  a->fast_ready = true;
+  return NRT_OK;
+}
+
+template <int DEPTH>
+cudaError_t launch_fast_f64(AccelF64 *a, const Ray72 *d_rays, size_t m, Hit32 *d_hits, uint8_t *d_mask,
+                            const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
+  unsigned long long *cursor = a->d_cursor + (a->cursor_next++ & 7u);
+  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  size_t grid = (size_t)device_sm_count(a->device) * kFastBlocksPerSmD;  // persistent: every SM holds its complement
+  const size_t need = ((m + 31) / 32 + kFastBlockD / 32 - 1) / (kFastBlockD / 32);
+  if (grid > need) grid = need;
+  if (grid == 0) grid = 1;
+  traverse_fast_f64_kernel<DEPTH><<<(unsigned)grid, kFastBlockD, 0, s>>>(
+      static_cast<const PairNodeD *>(a->d_pair), static_cast<const TriD *>(a->d_tris_fast), d_rays, m, d_hits, d_mask, opt,
+      flags, cursor);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -603,33 +675,90 @@ int nrt_traverse_f64(const nrt_accel_f64 *h, const void *rays_72B, size_t n_rays
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
   std::lock_guard<std::mutex> lock(a->mu);  // Traverse is const and thread-safe in the reference; staging is shared
   NRT_DEVICE(a->device);
-  const size_t chunk = std::min(n_rays, (size_t)1 << 20);
+  const bool fast = (flags & NRT_TRAVERSE_CONFORMANCE) == 0;
+  if (fast) {
+    const int rc = derive_fast_layout_f64(a);
+    if (rc != NRT_OK) return rc;
+  }
+  const size_t chunk = std::min(n_rays, (size_t)1 << 20);  // 1 Mi rays = 72 MiB up, 33 MiB down per chunk
   if (a->stage < chunk) {
-    cudaFree(a->d_rays);
-    cudaFree(a->d_hits);
-    cudaFree(a->d_mask);
-    a->d_rays = a->d_hits = a->d_mask = nullptr;
+    for (int i = 0; i < 3; i++) {
+      cudaFree(a->d_rays[i]);
+      cudaFree(a->d_hits[i]);
+      cudaFree(a->d_mask[i]);
+      a->d_rays[i] = a->d_hits[i] = a->d_mask[i] = nullptr;
+    }
     a->stage = 0;
-    NRT_CUDA(cudaMalloc(&a->d_rays, chunk * sizeof(Ray72)));
-    NRT_CUDA(cudaMalloc(&a->d_hits, chunk * sizeof(Hit32)));
-    NRT_CUDA(cudaMalloc(&a->d_mask, chunk));
+    for (int i = 0; i < 3; i++) {
+      if (!a->tstream[i]) NRT_CUDA(cudaStreamCreateWithFlags(&a->tstream[i], cudaStreamNonBlocking));
+      NRT_CUDA(cudaMalloc(&a->d_rays[i], chunk * sizeof(Ray72)));
+      NRT_CUDA(cudaMalloc(&a->d_hits[i], chunk * sizeof(Hit32)));
+      NRT_CUDA(cudaMalloc(&a->d_mask[i], chunk));
+    }
     a->stage = chunk;
   }
   const char *src = static_cast<const char *>(rays_72B);
   char *dst = static_cast<char *>(hits_32B);
-  for (size_t done = 0; done < n_rays; done += chunk) {
+  const bool deep = a->stats.max_tree_depth + 2 > 64u;  // adopted reference trees reach depth 256
+  cudaError_t e = cudaSuccess;
+  int slot = 0;
+  for (size_t done = 0; done < n_rays && e == cudaSuccess; done += chunk) {
     const size_t m = std::min(chunk, n_rays - done);
-    NRT_CUDA(cudaMemcpyAsync(a->d_rays, src + done * sizeof(Ray72), m * sizeof(Ray72), cudaMemcpyHostToDevice,
-                             a->stream));
-    traverse_f64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, a->stream>>>(
-        a->d_nodes, a->d_indices, a->d_faces, a->d_verts, static_cast<const Ray72 *>(a->d_rays), m,
-        static_cast<Hit32 *>(a->d_hits), static_cast<uint8_t *>(a->d_mask), opt, flags);
-    NRT_CUDA(cudaGetLastError());
-    NRT_CUDA(cudaMemcpyAsync(dst + done * sizeof(Hit32), a->d_hits, m * sizeof(Hit32), cudaMemcpyDeviceToHost,
-                             a->stream));
-    if (hit_mask) NRT_CUDA(cudaMemcpyAsync(hit_mask + done, a->d_mask, m, cudaMemcpyDeviceToHost, a->stream));
-    NRT_CUDA(cudaStreamSynchronize(a->stream));
+    cudaStream_t s = a->tstream[slot];
+    e = cudaStreamSynchronize(s);  // the slot's previous chunk (3 iterations ago) has drained
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(a->d_rays[slot], src + done * sizeof(Ray72), m * sizeof(Ray72), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) break;
+    const Ray72 *d_r = static_cast<const Ray72 *>(a->d_rays[slot]);
+    Hit32 *d_h = static_cast<Hit32 *>(a->d_hits[slot]);
+    uint8_t *d_m = static_cast<uint8_t *>(a->d_mask[slot]);
+    if (fast) {
+      e = deep ? launch_fast_f64<512>(a, d_r, m, d_h, d_m, opt, flags, s) : launch_fast_f64<64>(a, d_r, m, d_h, d_m, opt, flags, s);
+    } else {
+      traverse_f64_kernel<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(a->d_nodes, a->d_indices, a->d_faces, a->d_verts, d_r,
+                                                                      m, d_h, d_m, opt, flags);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst + done * sizeof(Hit32), d_h, m * sizeof(Hit32), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && hit_mask) e = cudaMemcpyAsync(hit_mask + done, d_m, m, cudaMemcpyDeviceToHost, s);
+    slot = (slot + 1) % 3;
   }
+  // success or not, nothing may still be writing into the caller's buffers when this call returns
+  for (int i = 0; i < 3; i++) {
+    const cudaError_t es = a->tstream[i] ? cudaStreamSynchronize(a->tstream[i]) : cudaSuccess;
+    if (e == cudaSuccess) e = es;
+  }
+  NRT_CUDA(e);
+  return NRT_OK;
+}
+
+int nrt_traverse_f64_device(const nrt_accel_f64 *h, const void *d_rays_72B, size_t n_rays, void *d_hits_32B,
+                            uint8_t *d_hit_mask, const void *trace_opts_16B, uint32_t flags, void *stream) {
+  if (!h || (n_rays && (!d_rays_72B || !d_hits_32B))) {
+    set_error("nrt_traverse_f64_device: NULL argument");
+    return NRT_ERR_INVALID;
+  }
+  if (n_rays == 0) return NRT_OK;
+  AccelF64 *a = const_cast<AccelF64 *>(reinterpret_cast<const AccelF64 *>(h));
+  TraceOptions16 opt = default_trace_options();
+  if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
+  std::lock_guard<std::mutex> lock(a->mu);  // lazy layout + the cursor ring
+  NRT_DEVICE(a->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Ray72 *d_r = static_cast<const Ray72 *>(d_rays_72B);
+  Hit32 *d_h = static_cast<Hit32 *>(d_hits_32B);
+  cudaError_t e;
+  if (flags & NRT_TRAVERSE_CONFORMANCE) {
+    traverse_f64_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, s>>>(a->d_nodes, a->d_indices, a->d_faces, a->d_verts, d_r,
+                                                                         n_rays, d_h, d_hit_mask, opt, flags);
+    e = cudaGetLastError();
+  } else {
+    const int rc = derive_fast_layout_f64(a);
+    if (rc != NRT_OK) return rc;
+    e = a->stats.max_tree_depth + 2 > 64u ? launch_fast_f64<512>(a, d_r, n_rays, d_h, d_hit_mask, opt, flags, s)
+                                          : launch_fast_f64<64>(a, d_r, n_rays, d_h, d_hit_mask, opt, flags, s);
+  }
+  NRT_CUDA(e);
   return NRT_OK;
 }
 

@@ -98,7 +98,7 @@ def test_f64_hits_match_the_reference(cpp11):
     rays = _rays64(v64, 60000, seed=4)
     acc = api.BVHAccelF64()
     acc.Build(len(f), v64, f)
-    flags = 0 if cpp11 else api.TRAVERSE_CPP03_INVERSE
+    flags = api.TRAVERSE_CONFORMANCE | (0 if cpp11 else api.TRAVERSE_CPP03_INVERSE)
     gh, gm = acc.Traverse(rays, flags=flags)
     # (1) the reference's own Build + Traverse in double: same hits; same bits for the same primitive
     racc = ref.build(v64, f)
@@ -140,7 +140,7 @@ def test_f64_adopted_reference_tree_is_bit_exact(cpp11):
     rh, rm = racc.traverse(rays, threads=8)
     acc = api.BVHAccelF64()
     assert acc.Adopt(racc.nodes(), racc.indices(), v64, f)
-    gh, gm = acc.Traverse(rays, flags=0 if cpp11 else api.TRAVERSE_CPP03_INVERSE)
+    gh, gm = acc.Traverse(rays, flags=api.TRAVERSE_CONFORMANCE | (0 if cpp11 else api.TRAVERSE_CPP03_INVERSE))
     assert rm.sum() > 3000 and np.array_equal(rm, gm)
     hit = rm == 1
     for k in ("t", "u", "v", "prim_id"):
@@ -165,7 +165,7 @@ def test_f64_against_the_c_restatement(cpp11):
     port = orc.Port64()
     v64, f = _scene64(seed=13)
     rays = _rays64(v64, 30000, seed=14)
-    flags = 0 if cpp11 else api.TRAVERSE_CPP03_INVERSE
+    flags = api.TRAVERSE_CONFORMANCE | (0 if cpp11 else api.TRAVERSE_CPP03_INVERSE)
     acc = api.BVHAccelF64()
     acc.Build(len(f), v64, f)
     gh, gm = acc.Traverse(rays, flags=flags)
@@ -224,9 +224,97 @@ def test_f64_conformance_build_writes_the_references_arrays(cpp11):
                 assert rn[k].tobytes() == nodes[k].tobytes(), k
         # and the conformance walk over it gives the oracle's records, ties included
         rays = _rays64(v64, 5000, seed=31)
-        tf = 0 if cpp11 else api.TRAVERSE_CPP03_INVERSE
+        tf = api.TRAVERSE_CONFORMANCE | (0 if cpp11 else api.TRAVERSE_CPP03_INVERSE)
         gh, gm = acc.Traverse(rays, flags=tf)
         ph, pm = port.traverse(want_nodes, want_idx, v64, f, rays, cpp11=cpp11, threads=8)
         assert np.array_equal(pm, gm)
         for k in ("t", "u", "v", "prim_id"):
             assert ph[k][pm == 1].tobytes() == gh[k][gm == 1].tobytes(), k
+
+
+def _assert_fast_equals_conformance(rays, fh, fm, ch, cm, max_tie_fraction=0.002):
+    """Same hit flags; the same primitive carries the same bits; a different primitive only at EXACTLY the same t."""
+    assert np.array_equal(fm, cm)
+    hit = cm == 1
+    same = hit & (fh["prim_id"] == ch["prim_id"])
+    for k in ("t", "u", "v"):
+        assert np.array_equal(fh[k][same].view(np.uint64), ch[k][same].view(np.uint64)), k
+    other = hit & ~same
+    assert other.sum() <= max_tie_fraction * max(1, hit.sum()), (int(other.sum()), int(hit.sum()))
+    assert np.array_equal(fh["t"][other].view(np.uint64), ch["t"][other].view(np.uint64))
+    miss = ~hit
+    assert np.all(fh["prim_id"][miss] == 0xFFFFFFFF)
+    assert np.array_equal(fh["t"][miss].view(np.uint64), ch["t"][miss].view(np.uint64))  # max_t, NaN payloads included
+
+
+@pytest.mark.parametrize("cpp11", [True, False])
+@pytest.mark.parametrize("tree", ["production", "reference", "adopted"])
+def test_f64_fast_kernel_matches_the_reference_order_kernel(cpp11, tree):
+    """nrt_traverse_f64 default (persistent warps over PairNodeD / TriD, csrc/f64_fast.cuh) against
+    NRT_TRAVERSE_CONFORMANCE on the same accel -- which the tests above pin to the reference's BVHAccel<double>: the
+    production tree, the reference's own tree built on the device (depth > 64: the deep-stack instantiation) and an
+    adopted CPU tree; trace options; hostile rays."""
+    from nanort_b200 import api
+    from oracle import orc
+
+    v64, f = _scene64(seed=21)
+    rays = _rays64(v64, 50000, seed=22)
+    # hostile rays: NaN / inverted ranges, zero and axis-parallel directions, huge and denormal components, min_t > 0
+    # (NaN / inf ray COMPONENTS make the reference's own answer depend on its visiting order: a NaN t is accepted and then
+    # poisons its box test; they are left to the reference-order kernel)
+    h = rays[:64].copy()
+    h["min_t"][0], h["max_t"][1] = np.nan, np.nan
+    h["min_t"][2], h["max_t"][2] = 5.0, 1.0
+    h["dir"][3] = 0.0
+    h["dir"][4] = (1.0, 0.0, 0.0)
+    h["dir"][5] = (0.0, -0.0, 1.0)
+    h["dir"][6] = (1e-320, 1.0, 0.0)
+    h["org"][7] = (1e300, 0.0, 0.0)
+    h["dir"][8] *= 1e-8
+    h["min_t"][9:20] = 0.75
+    h["max_t"][20:30] = 0.5
+    rays = np.concatenate([rays, h])
+    acc = api.BVHAccelF64()
+    if tree == "production":
+        assert acc.Build(len(f), v64, f)
+    elif tree == "reference":
+        assert acc.Build(len(f), v64, f, flags=api.BUILD_REFERENCE_TREE)
+    else:
+        port = orc.Port64()
+        nodes, idx, _ = port.build(v64, f, None, orc.MODE_CPP11 if cpp11 else 0)
+        assert acc.Adopt(nodes, idx, v64, f)
+    inv = 0 if cpp11 else api.TRAVERSE_CPP03_INVERSE
+    ch, cm = acc.Traverse(rays, flags=api.TRAVERSE_CONFORMANCE | inv)
+    fh, fm = acc.Traverse(rays, flags=api.TRAVERSE_FAST | inv)
+    assert cm.sum() > 3000
+    _assert_fast_equals_conformance(rays, fh, fm, ch, cm)
+    # trace options: back-face culling, a skipped primitive, a primitive id window
+    hit_prims = ch["prim_id"][cm == 1]
+    for o in (orc.trace_options(cull_back_face=1), orc.trace_options(skip_prim_id=int(hit_prims[0])),
+              orc.trace_options(prim_ids_range=(len(f) // 4, len(f) // 2))):
+        ch2, cm2 = acc.Traverse(rays[:12000], options=o, flags=api.TRAVERSE_CONFORMANCE | inv)
+        fh2, fm2 = acc.Traverse(rays[:12000], options=o, flags=inv)
+        _assert_fast_equals_conformance(rays[:12000], fh2, fm2, ch2, cm2)
+    # more rays than one pipeline chunk (three stream slots): every record lands in its place
+    big = np.tile(rays[:40000], 30)[: (1 << 20) + 12345]
+    bh, bm = acc.Traverse(big, flags=inv)
+    assert np.array_equal(bm[: len(fm[:40000])], fm[:40000]) and np.array_equal(bm[40000:80000], fm[:40000])
+    assert bh[1 << 20:].tobytes() == np.tile(fh[:40000], 30)[1 << 20: (1 << 20) + 12345].tobytes()
+
+
+def test_f64_fast_kernel_on_a_single_leaf_tree_and_empty_input():
+    from nanort_b200 import api
+
+    v64 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float64)
+    f = np.array([[0, 1, 2], [0, 1, 3]], np.uint32)
+    acc = api.BVHAccelF64()
+    assert acc.Build(len(f), v64, f)
+    rays = np.zeros(3, api.RAY64_DTYPE)
+    rays["org"] = [(0.2, 0.2, 1.0), (0.2, -1.0, 0.2), (5.0, 5.0, 5.0)]
+    rays["dir"] = [(0, 0, -1.0), (0, 1.0, 0), (0, 0, 1.0)]
+    rays["max_t"] = 1e30
+    fh, fm = acc.Traverse(rays)
+    ch, cm = acc.Traverse(rays, flags=api.TRAVERSE_CONFORMANCE)
+    assert fm.tolist() == [1, 1, 0] and fh.tobytes() == ch.tobytes()
+    eh, em = acc.Traverse(rays[:0])
+    assert len(eh) == 0
