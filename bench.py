@@ -877,12 +877,32 @@ def main():
             h2d, d2h = api.probe_copy_gbs(1 << 30, 0, device=local_rank), api.probe_copy_gbs(1 << 30, 1, device=local_rank)
         except Exception:
             h2d = d2h = None
+        # N > 1: the same copy probe on ALL ranks at once -- what each GPU's link gets while its neighbours' are busy
+        # (the ranks of one socket share its memory controllers and PCIe root: this, not a kernel, is why `e2e` stops
+        # scaling with N)
+        concurrent = None
+        if distributed:
+            try:
+                dist.barrier()
+                ch2d = api.probe_copy_gbs(1 << 30, 0, device=local_rank)
+                dist.barrier()
+                cd2h = api.probe_copy_gbs(1 << 30, 1, device=local_rank)
+                both = torch.tensor([ch2d, cd2h], dtype=torch.float64, device=dev)
+                lo, sm = both.clone(), both.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+                concurrent = {"h2d_min_per_gpu": float(lo[0].item()), "h2d_sum": float(sm[0].item()),
+                              "d2h_min_per_gpu": float(lo[1].item()), "d2h_sum": float(sm[1].item()),
+                              "note": "nrt_probe_copy_gbs, 1 GiB per rank, all ranks at the same time"}
+            except Exception as e:
+                concurrent = {"error": str(e)}
         e2e_rate = rays_all * args.steps / float(tt.item()) / 1e6
         per_gpu = e2e_rate / world * 1e6
         e2e = {"value": e2e_rate, "unit": UNIT,
                "h2d_bytes_per_step": int(36 * (n_primary + n_ao)), "d2h_bytes_per_step": int(17 * (n_primary + n_ao)),
                "api": "nrt_traverse (host rays -> host hits), pinned buffers, 2 calls per step",
                "measured_pinned_copy_gbs": {"h2d": h2d, "d2h": d2h, "note": "nrt_probe_copy_gbs, 1 GiB, this rank alone"},
+               "concurrent_pinned_copy_gbs": concurrent,
                "achieved_copy_gbs_per_gpu": {"h2d": 36 * per_gpu / 1e9, "d2h": 17 * per_gpu / 1e9},
                "bound": "PCIe / host memory: 36 B up + 17 B down per ray"}
         # opt-in compact records (NRT_TRAVERSE_RAY32: the 32-byte ray without nanort::Ray::type, no hit flags: a miss is

@@ -427,10 +427,16 @@ typedef FastPolicy<128, 10, 16, 8, 0, 0> OldDefaultPolicy;
 // round of its own at ~5 active lanes; the camera-ray launch, whose retire step spawns the AO ray (630 instructions),
 // also waits with the retire step until retired + empty lanes reach the refill threshold.
 // Two node steps per evaluation of the node phase's exit conditions (+1.8 ... +2.8 %, same sweep file).
-typedef Policy3<128, 10, 16, 8, true, false, 8, 1, false, 2> DefaultPolicy;
-typedef Policy3<128, 10, 16, 8, true, false, 12, 1, true, 2> CameraPolicy;
-typedef Policy3<128, 10, 16, 8, false, false, 12, 1, false, 2> IncoherentPolicy;
-typedef Policy3<128, 10, 16, 8, false, false, 12, 1, true, 2> IncoherentCameraPolicy;
+// Refill threshold (same file, "refill" section): with deferred retire the camera launch does best when a warp takes a
+// whole new 8x4-pixel packet only after ALL its lanes have finished (32) -- its rays have similar lengths, and the AO rays
+// it spawns then reach the AO queue in packets of neighbouring pixels, which speeds the AO launch up too; caller-supplied
+// rays 24; incoherent launches 20 (28 and more lose 10-50 % there).
+typedef Policy3<128, 10, 24, 8, true, false, 8, 1, false, 2> DefaultPolicy;
+// The camera launch runs 9 CTAs per SM (56 registers: its AO-spawn retire step spills at 48) and, like the incoherent
+// launches, three node steps per exit check.
+typedef Policy3<128, 9, 32, 8, true, false, 12, 1, true, 3> CameraPolicy;
+typedef Policy3<128, 10, 20, 8, false, false, 12, 1, false, 3> IncoherentPolicy;
+typedef Policy3<128, 9, 32, 8, false, false, 12, 1, true, 3> IncoherentCameraPolicy;
 // PairNode arrays above this size are not used (126 MB L2; the triangles want their share)
 constexpr size_t kPair128MaxBytes = (size_t)96 << 20;
 
@@ -575,6 +581,11 @@ static int launch_fast(const Accel *a, Rays rays, size_t n, Hit16 *d_hits, uint8
       NRT_VARIANT3(80, 128, 10, 16, 8, true, false, 8, 1, false, 2)
       NRT_VARIANT3(81, 128, 10, 16, 8, true, false, 8, 1, false, 3)
       NRT_VARIANT3(82, 128, 10, 16, 8, true, false, 8, 1, false, 4)
+      NRT_VARIANT3(83, 128, 10, 24, 8, true, false, 8, 1, false, 2)
+      NRT_VARIANT3(84, 128, 10, 32, 8, true, false, 8, 1, false, 2)
+      NRT_VARIANT3(85, 128, 10, 32, 8, true, false, 8, 1, true, 2)
+      NRT_VARIANT3(93, 128, 10, 24, 8, false, false, 12, 1, false, 2)
+      NRT_VARIANT3(94, 128, 10, 32, 8, false, false, 12, 1, false, 2)
       NRT_VARIANT3(90, 128, 10, 16, 8, false, false, 12, 1, false, 2)
       NRT_VARIANT3(91, 128, 10, 16, 8, false, false, 12, 1, false, 3)
       NRT_VARIANT3(92, 128, 10, 16, 8, false, false, 12, 1, false, 4)
@@ -673,11 +684,8 @@ int launch_traverse_soa_devcount(const Accel *a, const float4 *d_org_tmin, const
 // one digit each for the camera-ray launch, the AO launch, the path tracer's radiance launch and its shadow launch;
 // 0 = the default policy.  Read at every launch (cheap) so that one
 // process can sweep.
-//   1: (2) + two node steps per exit check  2: a second round only with >= 12 leaves
-//   3: (6) + two node steps per exit check  4: two leaf slots, second round with >= 12 leaves
-//   5: deferred retire                      6: (2) + deferred retire        7: (4) + deferred retire
-//   8: the policy before leaf batching (every leaf round runs, retire at once)
-//   9: leaf batching + deferred retire, ONE node step per exit check
+//   variations of the launch's default policy:  1 / 2: node-phase exit below 6 / 12   3 / 4: leaf-again-min 8 / 16
+//   5: three node steps per exit check   6 / 7: one / two CTAs per SM less   8: refill at 16   9: (5) + (6)
 static int ao_exp(int which) {
   const char *e = getenv("NRT_AO_EXP");
   if (!e || !e[0]) return 0;
@@ -686,18 +694,18 @@ static int ao_exp(int which) {
   const int d = e[which] - '0';
   return (d < 0 || d > 9) ? 0 : d;
 }
-#define NRT_AO_EXP_SWITCH(which, MINB, PAIR, CALL)                                    \
-  switch (ao_exp(which)) {                                                      \
-    case 1: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, false, 2> PX; return CALL; } \
-    case 2: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, false> PX; return CALL; } \
-    case 3: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, true, 2> PX; return CALL; } \
-    case 4: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 2, false> PX; return CALL; } \
-    case 5: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 1, 1, true> PX; return CALL; }   \
-    case 6: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, true> PX; return CALL; }  \
-    case 7: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 2, true> PX; return CALL; }  \
-    case 8: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 1, 1, false> PX; return CALL; }  \
-    case 9: { typedef Policy3<128, MINB, 16, 8, PAIR, false, 12, 1, true, 1> PX; return CALL; }  \
-    default: break;                                                             \
+#define NRT_AO_EXP_SWITCH(which, MINB, REFILL, PAIR, AGAIN, DEFER, CALL)                                         \
+  switch (ao_exp(which)) {                                                                                     \
+    case 1: { typedef Policy3<128, MINB, REFILL, 6, PAIR, false, AGAIN, 1, DEFER, 2> PX; return CALL; }          \
+    case 2: { typedef Policy3<128, MINB, REFILL, 12, PAIR, false, AGAIN, 1, DEFER, 2> PX; return CALL; }         \
+    case 3: { typedef Policy3<128, MINB, REFILL, 8, PAIR, false, 8, 1, DEFER, 2> PX; return CALL; }              \
+    case 4: { typedef Policy3<128, MINB, REFILL, 8, PAIR, false, 16, 1, DEFER, 2> PX; return CALL; }             \
+    case 5: { typedef Policy3<128, MINB, REFILL, 8, PAIR, false, AGAIN, 1, DEFER, 3> PX; return CALL; }          \
+    case 6: { typedef Policy3<128, MINB - 1, REFILL, 8, PAIR, false, AGAIN, 1, DEFER, 2> PX; return CALL; }      \
+    case 7: { typedef Policy3<128, MINB - 2, REFILL, 8, PAIR, false, AGAIN, 1, DEFER, 2> PX; return CALL; }      \
+    case 8: { typedef Policy3<128, MINB, 16, 8, PAIR, false, AGAIN, 1, DEFER, 2> PX; return CALL; }              \
+    case 9: { typedef Policy3<128, MINB - 1, REFILL, 8, PAIR, false, AGAIN, 1, DEFER, 3> PX; return CALL; }      \
+    default: break;                                                                                            \
   }
 
 // Fused wavefront launches (render.cu): the retire step spawns the AO ray / accumulates visibility.
@@ -722,7 +730,7 @@ int launch_traverse_camera_fused(const Accel *a, const Wave &w, const nrt_ao_par
   PrimaryToAoEpilogue<true> epi{p, slot0, w, a->d_verts, a->d_faces, d_accum, d_wave_counters};
   if (count == 0) return NRT_OK;
   if (a->n_wide * sizeof(PairNode) <= kPair128MaxBytes) {
-    NRT_AO_EXP_SWITCH(0, 10, true, (launch_fast3_any<CameraRays, false, PX>(a, CameraRays(p, slot0), count, epi, opt, flags,
+    NRT_AO_EXP_SWITCH(0, 9, 32, true, 12, true, (launch_fast3_any<CameraRays, false, PX>(a, CameraRays(p, slot0), count, epi, opt, flags,
                                                                         nullptr, nullptr, s)))
   }
   if (a->n_wide * sizeof(PairNode) > kPair128MaxBytes)
@@ -738,7 +746,7 @@ int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long 
   if (flags & NRT_TRAVERSE_ANY_HIT)
     return launch_fused<AnyHit<AoAccumulateEpilogue>, IncoherentPolicy>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count,
                                                                         AnyHit<AoAccumulateEpilogue>(epi), opt, flags, s);
-  NRT_AO_EXP_SWITCH(1, 10, false, (launch_fused<AoAccumulateEpilogue, PX>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity,
+  NRT_AO_EXP_SWITCH(1, 10, 20, false, 12, false, (launch_fused<AoAccumulateEpilogue, PX>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity,
                                                                       d_count, epi, opt, flags, s)))
   return launch_fused<AoAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{w.ao_org_tmin, w.ao_dir_tmax}, capacity, d_count, epi,
                                                               opt, flags, s);
@@ -747,10 +755,10 @@ int launch_traverse_ao_fused(const Accel *a, const Wave &w, const unsigned long 
 int launch_traverse_path_radiance(const Accel *a, const PathShadeEpilogue &epi, const unsigned long long *d_count,
                                   size_t capacity, const TraceOptions16 &opt, uint32_t flags, cudaStream_t s) {
   // the shading block needs more registers than the plain traversal: 8 CTAs/SM (64 registers) instead of 10
-  NRT_AO_EXP_SWITCH(2, 8, false, (launch_fused<PathShadeEpilogue, PX>(a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]},
+  NRT_AO_EXP_SWITCH(2, 8, 24, false, 8, true, (launch_fused<PathShadeEpilogue, PX>(a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]},
                                                                       capacity, d_count, epi, opt, flags, s)))
   // its retire step IS the shading block: deferred retire (it runs with more lanes), profiles/r02_leaf_batching_sweep.md
-  return launch_fused<PathShadeEpilogue, Policy3<128, 8, 16, 8, false, false, 1, 1, true, 2> >(
+  return launch_fused<PathShadeEpilogue, Policy3<128, 8, 24, 8, false, false, 8, 1, true, 2> >(
       a, SoaRays{epi.q.org_tmin[epi.in], epi.q.dir_tmax[epi.in]}, capacity, d_count, epi, opt, flags, s);
 }
 
@@ -762,7 +770,7 @@ int launch_traverse_path_shadow(const Accel *a, const PathQueues &q, const unsig
     return launch_fused<AnyHit<ShadowAccumulateEpilogue>, IncoherentPolicy>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity,
                                                                             d_count, AnyHit<ShadowAccumulateEpilogue>(epi), opt,
                                                                             flags, s);
-  NRT_AO_EXP_SWITCH(3, 10, false, (launch_fused<ShadowAccumulateEpilogue, PX>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity,
+  NRT_AO_EXP_SWITCH(3, 10, 20, false, 12, false, (launch_fused<ShadowAccumulateEpilogue, PX>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity,
                                                                            d_count, epi, opt, flags, s)))
   return launch_fused<ShadowAccumulateEpilogue, IncoherentPolicy>(a, SoaRays{q.sh_org_tmin, q.sh_dir_tmax}, capacity, d_count,
                                                                   epi, opt, flags, s);
