@@ -53,6 +53,7 @@ for kind, r, n in zip(("primary", "ao"), rows[2:4], rays):
                  "l2_bytes_per_ray": 32.0 * val(r, "lts__t_sectors.sum") / n,  # 32-byte sectors through the L2 tag stage
                  "dram_bytes_per_ray": (val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / n,
                  "l1_wavefront_pct": val(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
-                 "duration_ms_under_ncu": val(r, "gpu__time_duration.sum") * (1e-6 if units[hdr.index("gpu__time_duration.sum")] == "ns" else 1)}
+                 "duration_ms_under_ncu": val(r, "gpu__time_duration.sum") *
+                 {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], 1.0)}
 json.dump(res, open(os.path.join(out, f"{tag}_traverse_counters.json"), "w"), indent=1)
 print(json.dumps(res, indent=1))
