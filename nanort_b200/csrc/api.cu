@@ -59,6 +59,10 @@ static void destroy(Accel *a) {
     cudaFree(a->d_stage_mask[i]);
     if (a->streams[i]) cudaStreamDestroy(a->streams[i]);
   }
+  for (int i = 0; i < Accel::kSmallSlots; i++) {
+    if (a->small[i].h) cudaFreeHost(a->small[i].h);
+    if (a->small[i].s) cudaStreamDestroy(a->small[i].s);
+  }
   delete a;
 }
 
@@ -204,6 +208,49 @@ static int ensure_staging(Accel *a, size_t chunk) {
     NRT_CUDA(cudaMalloc(&a->d_stage_mask[i], chunk));
   }
   a->stage_rays = chunk;
+  return NRT_OK;
+}
+
+// nrt_traverse for a handful of rays (the facade's per-ray Traverse, small packets from worker threads): see
+// Accel::SmallSlot.  The traversal kernels dereference the pinned host pointers directly (unified addressing).
+static int traverse_small(Accel *a, const void *rays, size_t n, void *hits_16B, uint8_t *hit_mask, const TraceOptions16 &opt,
+                          uint32_t flags) {
+  const size_t ray_bytes = (flags & NRT_TRAVERSE_RAY32) ? 32 : sizeof(Ray36);
+  const size_t off_hits = Accel::kSmallRays * sizeof(Ray36), off_mask = off_hits + Accel::kSmallRays * sizeof(Hit16);
+  int idx = -1;
+  {
+    std::unique_lock<std::mutex> lk(a->small_mu);
+    for (;;) {
+      for (int i = 0; i < Accel::kSmallSlots && idx < 0; i++)
+        if (!a->small[i].busy) idx = i;
+      if (idx >= 0) break;
+      a->small_cv.wait(lk);
+    }
+    a->small[idx].busy = true;
+  }
+  Accel::SmallSlot &sl = a->small[idx];
+  int rc = NRT_OK;
+  cudaError_t e = cudaSuccess;
+  if (!sl.h) e = cudaHostAlloc(&sl.h, off_mask + Accel::kSmallRays, cudaHostAllocPortable | cudaHostAllocMapped);
+  if (e == cudaSuccess && !sl.s) e = cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    char *hb = static_cast<char *>(sl.h);
+    memcpy(hb, rays, n * ray_bytes);
+    rc = launch_traverse(a, reinterpret_cast<const Ray36 *>(hb), n, reinterpret_cast<Hit16 *>(hb + off_hits),
+                         hit_mask ? reinterpret_cast<uint8_t *>(hb + off_mask) : nullptr, opt, flags, sl.s);
+    e = cudaStreamSynchronize(sl.s);  // also on a failed launch: nothing of this call may be left in flight
+    if (rc == NRT_OK && e == cudaSuccess) {
+      memcpy(hits_16B, hb + off_hits, n * sizeof(Hit16));
+      if (hit_mask) memcpy(hit_mask, hb + off_mask, n);
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(a->small_mu);
+    sl.busy = false;
+  }
+  a->small_cv.notify_one();
+  if (rc != NRT_OK) return rc;
+  NRT_CUDA(e);
   return NRT_OK;
 }
 
@@ -458,6 +505,10 @@ int nrt_traverse(const nrt_accel *h, const void *rays_36B, size_t n_rays, void *
   Accel *a = const_cast<Accel *>(reinterpret_cast<const Accel *>(h));
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
+  if (n_rays <= Accel::kSmallRays) {  // low-latency path, not serialised with other host threads
+    NRT_DEVICE(a->device);
+    return traverse_small(a, rays_36B, n_rays, hits_16B, hit_mask, opt, flags);
+  }
   std::lock_guard<std::mutex> lock(a->host_mu);
   NRT_DEVICE(a->device);
   const size_t kChunk = (size_t)1 << 20;  // 1 Mi rays = 36 MiB up, 17 MiB down per chunk

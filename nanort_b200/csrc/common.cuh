@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -148,6 +149,19 @@ struct Accel {
   // the reference's Traverse may be called from many host threads at once (examples/path_tracer/main.cc:787-799);
   // the staging slots of the host-pointer path are shared, so those calls are serialised per accel
   std::mutex host_mu;
+  // Small calls (<= kSmallRays rays, e.g. the facade's one-ray Traverse): a pool of slots, each a pinned host buffer the
+  // kernel reads the rays from and writes the records to directly (zero copy) and a stream of its own -- no staging
+  // copies, one synchronisation, and calls from different host threads run side by side instead of queueing on host_mu.
+  static constexpr int kSmallSlots = 16;
+  static constexpr size_t kSmallRays = 64;
+  struct SmallSlot {
+    void *h = nullptr;  // rays (kSmallRays x 36 B) | hits (x 16 B) | flags (x 1 B)
+    cudaStream_t s = nullptr;
+    bool busy = false;
+  };
+  SmallSlot small[kSmallSlots];
+  std::mutex small_mu;
+  std::condition_variable small_cv;
   // wavefront pass scratch (render.cu)
   void *d_wave = nullptr;
   size_t wave_bytes = 0;

@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -80,6 +81,17 @@ struct AccelF64 {
   unsigned cursor_next = 0;
   bool fast_ready = false;
   std::mutex mu;
+  // small reference-order calls (the facade's one-ray Traverse): zero-copy slots as in Accel::SmallSlot
+  static constexpr int kSmallSlots = 8;
+  static constexpr size_t kSmallRays = 64;
+  struct SmallSlot {
+    void *h = nullptr;  // rays (kSmallRays x 72 B) | records (x 32 B) | flags (x 1 B)
+    cudaStream_t s = nullptr;
+    bool busy = false;
+  };
+  SmallSlot small[kSmallSlots];
+  std::mutex small_mu;
+  std::condition_variable small_cv;
 };
 
 void destroy_f64(AccelF64 *a) {
@@ -94,6 +106,10 @@ void destroy_f64(AccelF64 *a) {
     cudaFree(a->d_hits[i]);
     cudaFree(a->d_mask[i]);
     if (a->tstream[i]) cudaStreamDestroy(a->tstream[i]);
+  }
+  for (int i = 0; i < AccelF64::kSmallSlots; i++) {
+    if (a->small[i].h) cudaFreeHost(a->small[i].h);
+    if (a->small[i].s) cudaStreamDestroy(a->small[i].s);
   }
   cudaFree(a->d_pair);
   cudaFree(a->d_tris_fast);
@@ -673,6 +689,48 @@ int nrt_traverse_f64(const nrt_accel_f64 *h, const void *rays_72B, size_t n_rays
   AccelF64 *a = const_cast<AccelF64 *>(reinterpret_cast<const AccelF64 *>(h));
   TraceOptions16 opt = default_trace_options();
   if (trace_opts_16B) memcpy(&opt, trace_opts_16B, sizeof(opt));
+  if (n_rays <= AccelF64::kSmallRays && (flags & NRT_TRAVERSE_CONFORMANCE)) {
+    // low-latency path of the facade's per-ray Traverse: the kernel reads the rays from and writes the records to a
+    // pinned host slot (zero copy), one synchronisation, host threads side by side
+    NRT_DEVICE(a->device);
+    const size_t off_hits = AccelF64::kSmallRays * sizeof(Ray72), off_mask = off_hits + AccelF64::kSmallRays * sizeof(Hit32);
+    int idx = -1;
+    {
+      std::unique_lock<std::mutex> lk(a->small_mu);
+      for (;;) {
+        for (int i = 0; i < AccelF64::kSmallSlots && idx < 0; i++)
+          if (!a->small[i].busy) idx = i;
+        if (idx >= 0) break;
+        a->small_cv.wait(lk);
+      }
+      a->small[idx].busy = true;
+    }
+    AccelF64::SmallSlot &sl = a->small[idx];
+    cudaError_t e = cudaSuccess;
+    if (!sl.h) e = cudaHostAlloc(&sl.h, off_mask + AccelF64::kSmallRays, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e == cudaSuccess && !sl.s) e = cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+      char *hb = static_cast<char *>(sl.h);
+      memcpy(hb, rays_72B, n_rays * sizeof(Ray72));
+      traverse_f64_kernel<<<1, 64, 0, sl.s>>>(a->d_nodes, a->d_indices, a->d_faces, a->d_verts,
+                                             reinterpret_cast<const Ray72 *>(hb), n_rays, reinterpret_cast<Hit32 *>(hb + off_hits),
+                                             hit_mask ? reinterpret_cast<uint8_t *>(hb + off_mask) : nullptr, opt, flags);
+      e = cudaGetLastError();
+      const cudaError_t es = cudaStreamSynchronize(sl.s);
+      if (e == cudaSuccess) e = es;
+      if (e == cudaSuccess) {
+        memcpy(hits_32B, hb + off_hits, n_rays * sizeof(Hit32));
+        if (hit_mask) memcpy(hit_mask, hb + off_mask, n_rays);
+      }
+    }
+    {
+      std::lock_guard<std::mutex> lk(a->small_mu);
+      sl.busy = false;
+    }
+    a->small_cv.notify_one();
+    NRT_CUDA(e);
+    return NRT_OK;
+  }
   std::lock_guard<std::mutex> lock(a->mu);  // Traverse is const and thread-safe in the reference; staging is shared
   NRT_DEVICE(a->device);
   const bool fast = (flags & NRT_TRAVERSE_CONFORMANCE) == 0;

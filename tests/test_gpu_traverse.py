@@ -86,3 +86,43 @@ def test_compact_ray32_records_give_the_same_hits(conformance):
     # misaligned rays are refused, not mis-read
     with pytest.raises(Exception):
         acc.TraverseDevice(d_r.data_ptr() + 4, 8, d_h.data_ptr(), flags=flags | api.TRAVERSE_RAY32)
+
+
+def test_small_calls_take_the_zero_copy_path_and_agree_with_the_batch():
+    """nrt_traverse with <= 64 rays (the facade's per-ray Traverse) reads the rays from / writes the records to a pinned
+    host slot directly and is not serialised with other host threads: same records as the batched call, for every small n,
+    both kernels, with and without hit flags, from several threads at once."""
+    import threading
+    from nanort_b200 import api, scenes as S
+
+    v, f = S.make_scene("sphere_grid", nx=3, nz=3)
+    rays = _rays(S, "sphere_grid", v, f)[:4096]
+    acc = api.BVHAccel()
+    acc.Build(len(f), v, f)
+    for flags in (api.TRAVERSE_FAST, api.TRAVERSE_CONFORMANCE):
+        want_h, want_m = acc.Traverse(rays, flags=flags)
+        for n in (1, 2, 31, 32, 33, 63, 64, 65):
+            for off in (0, 777):
+                h, m = acc.Traverse(rays[off:off + n], flags=flags)
+                assert np.array_equal(m, want_m[off:off + n])
+                assert np.array_equal(h.view(np.uint32), want_h[off:off + n].view(np.uint32))
+        h, m = acc.Traverse(rays[5:6], flags=flags, mask=False)
+        assert m is None and np.array_equal(h.view(np.uint32), want_h[5:6].view(np.uint32))
+    want_h, want_m = acc.Traverse(rays)
+    errors = []
+
+    def worker(k):
+        try:
+            for i in range(k, len(rays), 8):
+                h, m = acc.Traverse(rays[i:i + 1])
+                if m[0] != want_m[i] or h.view(np.uint32).tolist() != want_h[i:i + 1].view(np.uint32).tolist():
+                    errors.append(i)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
