@@ -51,8 +51,19 @@ print("scene ok", int(sm.sum()))
 a64 = api.BVHAccelF64(); a64.Build(len(f), v.astype(np.float64), f)
 r64 = np.zeros(2048, api.RAY64_DTYPE)
 r64["org"], r64["dir"], r64["min_t"], r64["max_t"] = rays["org"][:2048], rays["dir"][:2048], 0.0, 1e30
-h64, m64 = a64.Traverse(r64)
+r64b = np.zeros(4096, api.RAY64_DTYPE)
+r64b["org"], r64b["dir"], r64b["min_t"], r64b["max_t"] = rays["org"][-4096:], rays["dir"][-4096:], 0.0, 1e30
+for rr in (r64, r64b):
+    h64, m64 = a64.Traverse(rr)  # fast kernel (f64_fast.cuh) + lazily derived PairNodeD / TriD layout
+    c64h, c64m = a64.Traverse(rr, flags=api.TRAVERSE_CONFORMANCE)
+    assert np.array_equal(m64, c64m) and np.array_equal(h64["t"], c64h["t"])
 print("f64 ok", int(m64.sum()))
+# zero-copy small-call path (<= 64 rays): float fast / conformance, fp64 reference order
+for n in (1, 33, 64):
+    for fl in (api.TRAVERSE_FAST, api.TRAVERSE_CONFORMANCE):
+        hs, ms = acc.Traverse(rays[-n:], flags=fl)
+    hs64, ms64 = a64.Traverse(r64b[-n:], flags=api.TRAVERSE_CONFORMANCE)
+print("small calls ok", int(ms.sum()), int(ms64.sum()))
 big_v, big_f = S.make_scene("terrain", n=96)
 big = api.BVHAccel(); big.Build(len(big_f), big_v, big_f)
 print("terrain build ok", big.GetStatistics()["num_leaf_nodes"])
