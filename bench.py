@@ -882,20 +882,23 @@ def main():
         # scaling with N)
         concurrent = None
         if distributed:
-            try:
-                dist.barrier()
-                ch2d = api.probe_copy_gbs(1 << 30, 0, device=local_rank)
-                dist.barrier()
-                cd2h = api.probe_copy_gbs(1 << 30, 1, device=local_rank)
-                both = torch.tensor([ch2d, cd2h], dtype=torch.float64, device=dev)
-                lo, sm = both.clone(), both.clone()
-                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-                dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-                concurrent = {"h2d_min_per_gpu": float(lo[0].item()), "h2d_sum": float(sm[0].item()),
-                              "d2h_min_per_gpu": float(lo[1].item()), "d2h_sum": float(sm[1].item()),
-                              "note": "nrt_probe_copy_gbs, 1 GiB per rank, all ranks at the same time"}
-            except Exception as e:
-                concurrent = {"error": str(e)}
+            # every rank reaches every collective below whatever its own probe does (a failed probe reports NaN)
+            def probe(direction):
+                try:
+                    return float(api.probe_copy_gbs(1 << 30, direction, device=local_rank))
+                except Exception:
+                    return float("nan")
+            dist.barrier()
+            ch2d = probe(0)
+            dist.barrier()
+            cd2h = probe(1)
+            both = torch.tensor([ch2d, cd2h], dtype=torch.float64, device=dev)
+            lo, sm = both.clone(), both.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            concurrent = {"h2d_min_per_gpu": float(lo[0].item()), "h2d_sum": float(sm[0].item()),
+                          "d2h_min_per_gpu": float(lo[1].item()), "d2h_sum": float(sm[1].item()),
+                          "note": "nrt_probe_copy_gbs, 1 GiB per rank, all ranks at the same time"}
         e2e_rate = rays_all * args.steps / float(tt.item()) / 1e6
         per_gpu = e2e_rate / world * 1e6
         e2e = {"value": e2e_rate, "unit": UNIT,
@@ -907,6 +910,8 @@ def main():
                "bound": "PCIe / host memory: 36 B up + 17 B down per ray"}
         # opt-in compact records (NRT_TRAVERSE_RAY32: the 32-byte ray without nanort::Ray::type, no hit flags: a miss is
         # prim_id == 0xFFFFFFFF): same hits, 32 B up + 16 B down per ray.  NOT the headline: the reference's Ray is 36 B.
+        # (every rank reaches the collectives below whatever happens to its own leg)
+        c_dt, c_same, c_err = float("nan"), False, None
         try:
             r32 = np.dtype((np.void, 32))
             hp32, ha32 = api.PinnedArray(n_primary, r32), api.PinnedArray(max(n_ao, 1), r32)
@@ -920,24 +925,30 @@ def main():
 
             for _ in range(2):
                 compact_step()
-            sync_all()
+            torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 compact_step()
             torch.cuda.synchronize(dev)
-            dt = time.perf_counter() - t0
-            tc = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if distributed:
-                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-            same = bool(np.array_equal(hits_p2.array.view(np.uint32), hits_p.array.view(np.uint32)))
+            c_dt = time.perf_counter() - t0
+            c_same = bool(np.array_equal(hits_p2.array.view(np.uint32), hits_p.array.view(np.uint32)))
+            del hp32, ha32, hits_p2
+        except Exception as e:  # a reporting extra: the bench line survives without it
+            c_err = str(e)
+        c_ok = c_err is None and c_dt == c_dt
+        tc = torch.tensor([c_dt if c_ok else 0.0], dtype=torch.float64, device=dev)
+        tok = torch.tensor([1.0 if c_ok else 0.0], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tok, op=dist.ReduceOp.MIN)
+        if tok.item() == 1.0:
             e2e["compact_records"] = {"value": rays_all * args.steps / float(tc.item()) / 1e6, "unit": UNIT,
                                       "api": "nrt_traverse(..., hit_mask = NULL, NRT_TRAVERSE_RAY32)",
                                       "h2d_bytes_per_step": int(32 * (n_primary + n_ao)),
                                       "d2h_bytes_per_step": int(16 * (n_primary + n_ao)),
-                                      "hits_identical_to_the_36_byte_call": same}
-            del hp32, ha32, hits_p2
-        except Exception as e:  # a reporting extra: the bench line survives without it
-            e2e["compact_records"] = {"error": str(e)}
+                                      "hits_identical_to_the_36_byte_call": c_same}
+        else:
+            e2e["compact_records"] = {"error": c_err or "failed on another rank"}
         # for comparison, the wavefront entry point end to end: camera parameters in (host struct), framebuffer out to
         # pinned host memory every step -- what a renderer pays when it hands the whole pass to the library
         fb_host = torch.empty(WIDTH * HEIGHT, dtype=torch.float32).pin_memory()
