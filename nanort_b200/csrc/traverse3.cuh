@@ -245,78 +245,78 @@ __global__ void __launch_bounds__(P::kBlock, P::kMinBlocks)
       if (P::kNodeExit > 1 && __popc(desc) < P::kNodeExit && __any_sync(FULL_MASK, leaf != kNone3)) break;
 #pragma unroll
       for (int rep = 0; rep < P::kNodeUnroll; ++rep) {
-      if (rep > 0) want = cur >= 0 || (cur == kNone3 && sp > 0);
-      if (want) {
-        // The one pop site.  Pops until the lane stands on a node again: entries that start behind the current best
-        // are dropped without touching memory (same visit set as the reference's re-test at pop, nanort.h:2532), a
-        // popped leaf goes into the free leaf slot and the popping continues -- so that every lane that still has
-        // inner nodes to visit takes a node step in THIS iteration (a lane that only pops is a wasted warp step).
-        while (cur == kNone3 && sp > 0) {
-          --sp;
-          const uint2 e = lstk[sp];
-          if (__uint_as_float(e.y) <= best.t) {
-            cur = (int)e.x;
-            if (cur < 0 && leaf == kNone3) {
+        if (rep > 0) want = cur >= 0 || (cur == kNone3 && sp > 0);
+        if (want) {
+          // The one pop site.  Pops until the lane stands on a node again: entries that start behind the current best
+          // are dropped without touching memory (same visit set as the reference's re-test at pop, nanort.h:2532), a
+          // popped leaf goes into the free leaf slot and the popping continues -- so that every lane that still has
+          // inner nodes to visit takes a node step in THIS iteration (a lane that only pops is a wasted warp step).
+          while (cur == kNone3 && sp > 0) {
+            --sp;
+            const uint2 e = lstk[sp];
+            if (__uint_as_float(e.y) <= best.t) {
+              cur = (int)e.x;
+              if (cur < 0 && leaf == kNone3) {
+                leaf = cur;
+                cur = kNone3;
+              } else if (P::kLeafSlots == 2 && cur < 0 && leaf2 == kNone3) {
+                leaf2 = cur;
+                cur = kNone3;
+              }
+            }
+          }
+        }
+        if (COUNT) {  // who does what in this warp step
+          const bool fin = alive && cur == kNone3 && leaf == kNone3 && sp == 0;
+          st[2] += 1;                                                  // node-phase warp steps
+          st[3] += __popc(__ballot_sync(FULL_MASK, cur >= 0));          // lanes testing a child pair
+          st[4] += __popc(__ballot_sync(FULL_MASK, !alive));            // lanes without a ray
+          st[5] += __popc(__ballot_sync(FULL_MASK, fin));               // lanes whose ray is finished (waits for the retire step)
+          st[6] += __popc(__ballot_sync(FULL_MASK, alive && !fin && cur < 0));  // lanes parked on leaves
+        }
+        if (want) {
+          if (cur >= 0) {
+            bool h0, h1;
+            float t0, t1;
+            int2 R;
+            if (P::kPair128) {
+              const uint32_t n8 = (uint32_t)cur * 8u;
+              const float4 X = __ldg(pair4 + (n8 + c.nx));
+              const float4 Y = __ldg(pair4 + (n8 + c.ny));
+              const float4 Z = __ldg(pair4 + (n8 + c.nz));
+              R = __ldg(reinterpret_cast<const int2 *>(pair4 + (n8 + 6u)));
+              slab_pair(c, X, Y, Z, min_t, best.t, h0, h1, t0, t1);
+            } else if (P::kLoad256) {
+              const float4 *q = pair4 + (uint32_t)cur * 4u;
+              float4 q0, q1, q2, q3;
+              ldg256(q, q0, q1);
+              ldg256(q + 2, q2, q3);
+              R = make_int2(__float_as_int(q3.x), __float_as_int(q3.y));
+              slab_pair_sel(c, q0, q1, q2, min_t, best.t, h0, h1, t0, t1);
+            } else {
+              const float4 *q = pair4 + (uint32_t)cur * 4u;
+              const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+              R = __ldg(reinterpret_cast<const int2 *>(q + 3));
+              slab_pair_sel(c, q0, q1, q2, min_t, best.t, h0, h1, t0, t1);
+            }
+            if (COUNT) n_boxes += 2;
+            const bool swap = t1 < t0;
+            const bool both = h0 & h1;
+            if (both) {
+              lstk[sp] = make_uint2((uint32_t)(swap ? R.x : R.y), __float_as_uint(swap ? t0 : t1));
+              sp++;
+            }
+            cur = both ? (swap ? R.y : R.x) : (h0 ? R.x : (h1 ? R.y : kNone3));
+            if (cur < 0 && cur != kNone3 && leaf == kNone3) {  // postpone the first leaf, keep descending
               leaf = cur;
               cur = kNone3;
-            } else if (P::kLeafSlots == 2 && cur < 0 && leaf2 == kNone3) {
+            } else if (P::kLeafSlots == 2 && cur < 0 && cur != kNone3 && leaf2 == kNone3) {
               leaf2 = cur;
               cur = kNone3;
             }
           }
         }
       }
-      if (COUNT) {  // who does what in this warp step
-        const bool fin = alive && cur == kNone3 && leaf == kNone3 && sp == 0;
-        st[2] += 1;                                                  // node-phase warp steps
-        st[3] += __popc(__ballot_sync(FULL_MASK, cur >= 0));          // lanes testing a child pair
-        st[4] += __popc(__ballot_sync(FULL_MASK, !alive));            // lanes without a ray
-        st[5] += __popc(__ballot_sync(FULL_MASK, fin));               // lanes whose ray is finished (waits for the retire step)
-        st[6] += __popc(__ballot_sync(FULL_MASK, alive && !fin && cur < 0));  // lanes parked on leaves
-      }
-      if (want) {
-        if (cur >= 0) {
-          bool h0, h1;
-          float t0, t1;
-          int2 R;
-          if (P::kPair128) {
-            const uint32_t n8 = (uint32_t)cur * 8u;
-            const float4 X = __ldg(pair4 + (n8 + c.nx));
-            const float4 Y = __ldg(pair4 + (n8 + c.ny));
-            const float4 Z = __ldg(pair4 + (n8 + c.nz));
-            R = __ldg(reinterpret_cast<const int2 *>(pair4 + (n8 + 6u)));
-            slab_pair(c, X, Y, Z, min_t, best.t, h0, h1, t0, t1);
-          } else if (P::kLoad256) {
-            const float4 *q = pair4 + (uint32_t)cur * 4u;
-            float4 q0, q1, q2, q3;
-            ldg256(q, q0, q1);
-            ldg256(q + 2, q2, q3);
-            R = make_int2(__float_as_int(q3.x), __float_as_int(q3.y));
-            slab_pair_sel(c, q0, q1, q2, min_t, best.t, h0, h1, t0, t1);
-          } else {
-            const float4 *q = pair4 + (uint32_t)cur * 4u;
-            const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-            R = __ldg(reinterpret_cast<const int2 *>(q + 3));
-            slab_pair_sel(c, q0, q1, q2, min_t, best.t, h0, h1, t0, t1);
-          }
-          if (COUNT) n_boxes += 2;
-          const bool swap = t1 < t0;
-          const bool both = h0 & h1;
-          if (both) {
-            lstk[sp] = make_uint2((uint32_t)(swap ? R.x : R.y), __float_as_uint(swap ? t0 : t1));
-            sp++;
-          }
-          cur = both ? (swap ? R.y : R.x) : (h0 ? R.x : (h1 ? R.y : kNone3));
-          if (cur < 0 && cur != kNone3 && leaf == kNone3) {  // postpone the first leaf, keep descending
-            leaf = cur;
-            cur = kNone3;
-          } else if (P::kLeafSlots == 2 && cur < 0 && cur != kNone3 && leaf2 == kNone3) {
-            leaf2 = cur;
-            cur = kNone3;
-          }
-        }
-      }
-      }  // rep
     }
 
     // ---- leaves
