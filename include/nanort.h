@@ -162,6 +162,16 @@ inline real3<T> vnormalize(const real3<T> &a) {  // nanort.h:387-398: unchanged 
   }
   return r;
 }
+// nanort.h:1235-1243: the reference's public min / max helpers (its slab test's NaN rule: a NaN FIRST operand loses);
+// callers such as examples/nanosg/nanosg.h:624-628 use them in their own intersectors
+template <class T>
+inline const T &safemin(const T &a, const T &b) {
+  return (a < b) ? a : b;
+}
+template <class T>
+inline const T &safemax(const T &a, const T &b) {
+  return (a > b) ? a : b;
+}
 // nanort.h:414-465: 1 / v with +-inf for |v| < epsilon; the sign convention follows NANORT_USE_CPP11_FEATURE
 template <typename T>
 inline real3<T> vsafe_inverse(const real3<T> v) {

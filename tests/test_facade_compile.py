@@ -74,3 +74,16 @@ def test_reference_path_tracer_links_against_the_library(tmp_path):
                         f"-I{REF}/examples/common", os.path.join(d, "main.cc"), os.path.join(d, "tiny_obj_loader.cc"),
                         "-pthread", "-o", str(out), f"-L{LIB}", "-lnanort_b200"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_reference_scene_graph_header_compiles_on_top_of_the_facade():
+    """examples/nanosg/nanosg.h of the reference (unmodified: custom Prim / Pred / Intersector classes for node boxes,
+    nanort::safemin / safemax, ListNodeIntersections, one Traverse per node) against include/nanort.h; the GPU run of the
+    same build is tests/test_gpu_dropin.py::test_reference_nanosg_header_on_top_of_the_facade_is_identical."""
+    d = os.path.join(REF, "examples", "nanosg")
+    if not os.path.isdir(d):
+        pytest.skip("reference tree not present")
+    r = subprocess.run(["g++", "-fsyntax-only", "-w", "-std=c++11", "-DNANORT_USE_CPP11_FEATURE", "-DNANORT_B200_CONFORMANCE",
+                        "-pthread", f"-I{d}", f"-I{INC}", os.path.join(ROOT, "examples", "nanosg_check.cc")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

@@ -89,6 +89,17 @@ def test_nanosg_drop_in_conformance_is_identical():
     assert len(want) > 2000 and got == want
 
 
+def test_reference_nanosg_header_on_top_of_the_facade_is_identical():
+    """The reference's OWN scene-graph header (examples/nanosg/nanosg.h, unmodified: NodeBBoxGeometry / NodeBBoxPred /
+    NodeBBoxIntersector handed to BVHAccel::Build / ListNodeIntersections, one BVHAccel::Traverse per pierced node)
+    compiled against include/nanort.h with -DNANORT_B200_CONFORMANCE: the same output as against the reference's nanort.h."""
+    if not os.path.exists(os.path.join(BIN, "nanosg_check_mixed_conf")):
+        pytest.skip("examples/bin/nanosg_check_mixed_conf not built (needs /root/reference at build time)")
+    got = _run("nanosg_check_mixed_conf")
+    want = _nanosg_golden()
+    assert got == want
+
+
 def test_nanosg_drop_in_fast_mode_same_hits():
     """Default (fast) mode: same lines except where two surfaces lie at exactly the same distance."""
     if not os.path.exists(os.path.join(BIN, "nanosg_check_b200")):
