@@ -489,6 +489,13 @@ struct prim_tag {
   typedef typename std::conditional<std::is_same<Prim, TriangleMesh<float> >::value, triangle_tag,
                                     typename std::conditional<DeviceSpheres<Prim>::value, sphere_tag, boxes_tag>::type>::type type;
 };
+// examples/cylinder_primitive/main.cc names its members exactly like the sphere example (`vertices_`, `radiuss_`) but
+// stores TWO end points and radii per primitive and tests caps: its intersector is recognised by `test_cap_` and refused
+// (cylinders are not a device kind) instead of being walked as spheres
+template <class I, class Enable = void>
+struct is_cylinder_like : std::false_type {};
+template <class I>
+struct is_cylinder_like<I, decltype((void)std::declval<const I &>().test_cap_, void())> : std::true_type {};
 template <class I>
 struct is_triangle_intersector : std::false_type {};
 template <class H>
@@ -721,6 +728,12 @@ class BVHAccel<float> {
   }
   template <class I>
   bool ReadyFor(const I &, std::false_type) const {
+    if (detail::is_cylinder_like<I>::value) {
+      fprintf(stderr, "nanort_b200: this intersector (a `test_cap_` member: the cylinder model of "
+                      "examples/cylinder_primitive) is not a primitive kind the device knows; spheres, boxes and "
+                      "triangles are\n");
+      return false;
+    }
     if (handle_ && kind_ == (int)NRT_PRIM_SPHERES) return true;
     fprintf(stderr, "nanort_b200: Traverse with a user-defined intersector needs an accel of a kind the device knows "
                     "(spheres: see DeviceSpheres in nanort.h); this accel has kind %d\n", kind_);

@@ -87,3 +87,21 @@ def test_reference_scene_graph_header_compiles_on_top_of_the_facade():
                         "-pthread", f"-I{d}", f"-I{INC}", os.path.join(ROOT, "examples", "nanosg_check.cc")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_cylinder_like_intersectors_are_recognised_and_refused(tmp_path):
+    """examples/cylinder_primitive names its members like the sphere example (`vertices_`, `radiuss_`); the facade must not
+    walk such an accel as spheres: the intersector's `test_cap_` member marks it (detail::is_cylinder_like) and Traverse
+    refuses it with a message."""
+    src = tmp_path / "t.cc"
+    src.write_text('''
+#include "nanort.h"
+struct SphereLike { const float *vertices_; const float *radiuss_; };
+struct CylinderLike { const float *vertices_; const float *radiuss_; const bool test_cap_; };
+static_assert(!nanort::detail::is_cylinder_like<SphereLike>::value, "sphere intersector");
+static_assert(nanort::detail::is_cylinder_like<CylinderLike>::value, "cylinder intersector");
+static_assert(!nanort::detail::is_cylinder_like<nanort::TriangleIntersector<> >::value, "triangle intersector");
+int main() { return 0; }
+''')
+    r = subprocess.run(["g++", "-fsyntax-only", "-std=c++11", f"-I{INC}", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
