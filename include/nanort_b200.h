@@ -360,6 +360,15 @@ int nrt_scene_instance_state(const nrt_scene *s, uint32_t instance, float out76[
  * NRT_TRAVERSE_CPP03_INVERSE */
 int nrt_scene_traverse(const nrt_scene *s, const void *rays_36B, size_t n_rays, void *hits_32B, uint8_t *hit_mask,
                        uint32_t flags);
+/* Primary + 1-bounce AO over the scene: nrt_render_ao_device's pass (same nrt_ao_params, same tile / shard slot order,
+ * same camera rays and cosine directions, d_accum as there) with Scene::Traverse as its traversal step, as stand-alone
+ * stage kernels.  Two differences follow from nanosg's semantics (nanosg.h:831-836: an instance is walked with the local
+ * range {0, FLT_MAX}): the AO ray starts ao_min_t above the surface along the viewer-facing geometric normal (computed
+ * from the hit triangle moved to world space by the instance's matrix), and it counts as occluded iff the reported world
+ * distance is below ao_max_t.  NRT_AO_PACKED_TILES is not supported.  Triangle instances only.  Synchronous per wave
+ * (the AO ray count is read on the host); res may be NULL. */
+int nrt_scene_render_ao_device(const nrt_scene *s, const nrt_ao_params *params, float *d_accum, nrt_ao_result *res,
+                               void *stream);
 /* the same with DEVICE pointers, asynchronous on `stream` */
 int nrt_scene_traverse_device(const nrt_scene *s, const void *d_rays_36B, size_t n_rays, void *d_hits_32B,
                               uint8_t *d_hit_mask, uint32_t flags, void *stream);

@@ -54,7 +54,7 @@ EXPORTS = [
     "nrt_bounding_box", "nrt_nodes", "nrt_traverse", "nrt_traverse_device", "nrt_traverse_count_device",
     "nrt_host_alloc", "nrt_host_free", "nrt_render_ao_device", "nrt_ao_workload_device", "nrt_render_path_device",
     "nrt_scene_commit", "nrt_scene_free", "nrt_scene_bounding_box", "nrt_scene_nodes", "nrt_scene_instance_state",
-    "nrt_scene_traverse", "nrt_scene_traverse_device",
+    "nrt_scene_traverse", "nrt_scene_traverse_device", "nrt_scene_render_ao_device",
     "nrt_build_f64", "nrt_adopt_f64", "nrt_free_f64", "nrt_stats_f64", "nrt_bounding_box_f64", "nrt_nodes_f64", "nrt_traverse_f64", "nrt_traverse_f64_device",
     "nrt_path_bounce_device", "nrt_build_prims", "nrt_list_node_intersections",
     "nrt_comm_unique_id", "nrt_comm_init", "nrt_comm_free", "nrt_comm_rank", "nrt_render_ao_sharded",
@@ -156,6 +156,7 @@ def lib():
     L.nrt_scene_instance_state.argtypes = [vp, u32, vp]
     L.nrt_scene_traverse.argtypes = [vp, vp, sz, vp, vp, u32]
     L.nrt_scene_traverse_device.argtypes = [vp, vp, sz, vp, vp, u32, vp]
+    L.nrt_scene_render_ao_device.argtypes = [vp, vp, vp, vp, vp]
     L.nrt_build_f64.argtypes = [vp, sz, sz, vp, u32, vp, C.POINTER(vp)]
     L.nrt_build_f64_ex.argtypes = [vp, sz, sz, vp, u32, vp, u32, C.POINTER(vp)]
     L.nrt_adopt_f64.argtypes = [vp, sz, vp, sz, vp, sz, sz, vp, u32, C.POINTER(vp)]
@@ -592,6 +593,14 @@ class Scene:
         _check(lib().nrt_scene_traverse_device(self._h, C.c_void_p(d_rays_ptr), int(n), C.c_void_p(d_hits_ptr),
                                                C.c_void_p(d_mask_ptr) if d_mask_ptr else None, int(flags),
                                                C.c_void_p(stream) if stream else None))
+
+    def RenderAO(self, params: "AoParams", d_accum_ptr, stream=None):
+        """Primary + 1-bounce AO over the two-level scene (nrt_scene_render_ao_device); same parameters as
+        BVHAccel.RenderAO."""
+        res = AoResult()
+        _check(lib().nrt_scene_render_ao_device(self._h, C.byref(params), C.c_void_p(d_accum_ptr), C.byref(res),
+                                                C.c_void_p(stream) if stream else None))
+        return res
 
 
 # ------------------------------------------------------------------ BVHAccel<double>

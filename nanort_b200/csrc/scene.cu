@@ -49,11 +49,11 @@ struct InstanceDev {
   Mat43 inv33;  // world -> local, directions
   Mat43 xf;     // local -> world
   float bmin[3], bmax[3];  // world box
-  uint32_t pad[2];
+  const float *verts;      // the instance accel's packed float3 vertices / faces (the AO pass needs the hit triangle)
   const WideNode *wide;
   const PackedTri *tris;
   const Node40 *nodes;
-  uint64_t pad2;
+  const uint32_t *faces;
 };
 static_assert(sizeof(InstanceDev) == 208, "InstanceDev");
 
@@ -149,11 +149,11 @@ __device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b 
 struct InstanceIn {  // host -> device
   float xform[16];
   float lbmin[3], lbmax[3];
-  uint32_t pad[2];
+  const float *verts;
   const WideNode *wide;
   const PackedTri *tris;
   const Node40 *nodes;
-  uint64_t pad2;
+  const uint32_t *faces;
 };
 
 // Node::Update for scene roots: xform = identity x local; world box; inverse; inverse of the 3x3 part.
@@ -205,11 +205,11 @@ __global__ void instance_setup_kernel(const InstanceIn *__restrict__ in, uint32_
     boxes6[6 * (size_t)i + k] = bmin[k];
     boxes6[6 * (size_t)i + 3 + k] = bmax[k];
   }
-  o.pad[0] = o.pad[1] = 0;
+  o.verts = I.verts;
   o.wide = I.wide;
   o.tris = I.tris;
   o.nodes = I.nodes;
-  o.pad2 = 0;
+  o.faces = I.faces;
   out[i] = o;
   if (state76) {
     float *s = state76 + 76 * (size_t)i;
@@ -855,6 +855,8 @@ int nrt_scene_commit(const nrt_instance *instances, uint32_t n_instances, uint32
       h[i].wide = a->d_wide;
       h[i].tris = a->d_tris;
       h[i].nodes = a->d_nodes;
+      h[i].verts = a->d_verts;
+      h[i].faces = a->d_faces;
       sc->max_blas_depth = std::max(sc->max_blas_depth, a->stats.max_tree_depth);
     }
     e = cudaMemcpyAsync(d_in, h.data(), sizeof(InstanceIn) * (size_t)n_instances, cudaMemcpyHostToDevice, sc->stream);
@@ -985,3 +987,244 @@ int nrt_scene_traverse(const nrt_scene *s, const void *rays_36B, size_t n_rays, 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Primary + 1-bounce AO over a two-level scene (nrt_scene_render_ao_device): the wavefront pass of render.cu with
+// nrt_scene_traverse_device as its traversal step.  Same composition from the reference's pieces (render.cu header):
+// camera ray main.cc:809-817, hit point = the scene record's P (nanosg.h:846-850), geometric normal of the hit triangle
+// in WORLD space (its vertices moved by the instance's local->world matrix, then main.cc:306-312) flipped towards the
+// viewer, cosine direction main.cc:216-250, occlusion query = a closest-hit Scene::Traverse from the hit point lifted by
+// ao_min_t along the normal, occluded iff the reported distance is below ao_max_t (see scene_gen_ao_kernel).
+// Stand-alone stage kernels (the scene walk has no retire-step functor); one host read of the AO count per wave.
+#include "wavefront.cuh"
+
+namespace nrt {
+namespace {
+
+__global__ void __launch_bounds__(256)
+    scene_gen_primary_kernel(nrt_ao_params p, unsigned long long slot0, uint32_t count, Ray36 *__restrict__ rays,
+                             uint32_t *__restrict__ pix_out, unsigned long long *counters /* [1] valid primaries */) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = false;
+  if (i < count) {
+    uint32_t pix, smp;
+    Ray36 r;
+    r.org[0] = p.cam[0], r.org[1] = p.cam[1], r.org[2] = p.cam[2];
+    r.type = 0;
+    if (!slot_to_pixel(p, slot0 + i, pix, smp)) {
+      pix = 0xFFFFFFFFu;
+      r.dir[0] = 0.0f, r.dir[1] = 0.0f, r.dir[2] = -1.0f;
+      r.min_t = 0.0f, r.max_t = -1.0f;  // max_t < min_t: misses at the root
+    } else {
+      valid = true;
+      camera_ray(p.cam, p.width, p.height, p.seed, pix, smp + p.sample0, r.dir[0], r.dir[1], r.dir[2]);
+      r.min_t = p.ray_min_t, r.max_t = p.ray_max_t;
+    }
+    rays[i] = r;
+    pix_out[i] = pix;
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(counters + 1, (unsigned long long)__popc(m));
+}
+
+// one AO ray per primary hit, compacted with one atomic per warp; primary misses count as unoccluded
+__global__ void __launch_bounds__(256)
+    scene_gen_ao_kernel(nrt_ao_params p, unsigned long long slot0, uint32_t count, const Ray36 *__restrict__ rays,
+                        const uint32_t *__restrict__ pix_in, const SceneHit32 *__restrict__ hits,
+                        const uint8_t *__restrict__ mask, const InstanceDev *__restrict__ inst, Ray36 *__restrict__ ao_rays,
+                        uint32_t *__restrict__ ao_pix, float *__restrict__ accum, unsigned long long *counters /* [0] */) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool make = false;
+  Ray36 ao;
+  uint32_t pix = 0xFFFFFFFFu;
+  if (i < count) {
+    pix = pix_in[i];
+    if (pix != 0xFFFFFFFFu) {
+      if (!mask[i]) {
+        atomicAdd(accum + pix, 1.0f);
+      } else {
+        const SceneHit32 h = hits[i];
+        const InstanceDev *I = inst + h.node_id;
+        const Mat43 xf = load_mat(&I->xf);
+        const uint32_t *f = I->faces + 3 * (size_t)h.prim_id;
+        const float *v0 = I->verts + 3 * (size_t)f[0], *v1 = I->verts + 3 * (size_t)f[1], *v2 = I->verts + 3 * (size_t)f[2];
+        float ax, ay, az, bx, by, bz, cx, cy, cz;
+        multv(xf, v0[0], v0[1], v0[2], ax, ay, az);
+        multv(xf, v1[0], v1[1], v1[2], bx, by, bz);
+        multv(xf, v2[0], v2[1], v2[2], cx, cy, cz);
+        const float e1x = bx - ax, e1y = by - ay, e1z = bz - az;
+        const float e2x = cx - ax, e2y = cy - ay, e2z = cz - az;
+        float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+        float ln = sqrtf(nx * nx + ny * ny + nz * nz);
+        ln = ln > 0.0f ? 1.0f / ln : 0.0f;
+        nx *= ln, ny *= ln, nz *= ln;
+        const Ray36 r = rays[i];
+        if (nx * r.dir[0] + ny * r.dir[1] + nz * r.dir[2] > 0.0f) nx = -nx, ny = -ny, nz = -nz;
+        // orthonormal basis around n + cosine-weighted direction: make_ao_ray() of wavefront.cuh, same arithmetic
+        const uint32_t smp = slot_sample(p, slot0 + i);
+        const float sg = nz >= 0.0f ? 1.0f : -1.0f;
+        const float a = -1.0f / (sg + nz), b = nx * ny * a;
+        const float t1x = 1.0f + sg * nx * nx * a, t1y = sg * b, t1z = -sg * nx;
+        const float t2x = b, t2y = sg + ny * ny * a, t2z = -ny;
+        const float u1 = rand_ps(pix, smp, 2, p.seed), u2 = rand_ps(pix, smp, 3, p.seed);
+        const float rr = sqrtf(u1), ph = 6.28318530718f * u2;
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        const float lx = rr * cs, ly = rr * sn, lz = sqrtf(fmaxf(0.0f, 1.0f - u1));
+        const float wx = t1x * lx + t2x * ly + nx * lz, wy = t1y * lx + t2y * ly + ny * lz, wz = t1z * lx + t2z * ly + nz * lz;
+        const float il = 1.0f / sqrtf(wx * wx + wy * wy + wz * wz);
+        // Scene::Traverse walks an instance with the LOCAL range {0, FLT_MAX} (nanosg.h:831-836): min_t cannot keep the
+        // ray off the surface it starts on, so the origin is lifted by ao_min_t along the (viewer-facing) normal, and
+        // max_t only gates the top-level walk -- the accumulate step applies the radius to the reported distance
+        ao.org[0] = h.P[0] + nx * p.ao_min_t, ao.org[1] = h.P[1] + ny * p.ao_min_t, ao.org[2] = h.P[2] + nz * p.ao_min_t;
+        ao.dir[0] = wx * il, ao.dir[1] = wy * il, ao.dir[2] = wz * il;
+        ao.min_t = 0.0f, ao.max_t = p.ao_max_t;
+        ao.type = 0;
+        make = true;
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, make);
+  if (m == 0u) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(counters + 0, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (make) {
+    const unsigned long long j = base + __popc(m & ((1u << lane) - 1u));
+    ao_rays[j] = ao;
+    ao_pix[j] = pix;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    scene_accumulate_ao_kernel(const uint8_t *__restrict__ ao_mask, const SceneHit32 *__restrict__ ao_hits,
+                               const uint32_t *__restrict__ ao_pix, unsigned long long n, float max_t,
+                               float *__restrict__ accum, unsigned long long *totals /* [1] occluded AO rays */) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool occluded = false;
+  if (i < n) {
+    occluded = ao_mask[i] != 0 && ao_hits[i].t < max_t;
+    if (!occluded) atomicAdd(accum + ao_pix[i], 1.0f);
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, occluded);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(totals + 1, (unsigned long long)__popc(m));
+}
+
+struct SceneWave {
+  Ray36 *rays = nullptr, *ao_rays = nullptr;
+  uint32_t *pix = nullptr, *ao_pix = nullptr;
+  SceneHit32 *hits = nullptr;
+  uint8_t *mask = nullptr;
+  unsigned long long *counters = nullptr;  // [0] AO rays of the wave, [1] valid primaries; [4..6] totals
+  void release() {
+    cudaFree(rays), cudaFree(ao_rays), cudaFree(pix), cudaFree(ao_pix), cudaFree(hits), cudaFree(mask), cudaFree(counters);
+  }
+};
+
+}  // namespace
+}  // namespace nrt
+
+extern "C" int nrt_scene_render_ao_device(const nrt_scene *s, const nrt_ao_params *params, float *d_accum, nrt_ao_result *res,
+                                          void *stream) {
+  if (!s || !params || !d_accum) {
+    set_error("nrt_scene_render_ao_device: NULL argument");
+    return NRT_ERR_INVALID;
+  }
+  const nrt_ao_params p = *params;
+  if (p.width == 0 || p.height == 0 || p.spp == 0 || p.tile_w == 0 || p.tile_h == 0 || (p.tile_w % 8) || (p.tile_h % 4) ||
+      p.n_shards == 0 || p.shard >= p.n_shards || (p.flags & NRT_AO_PACKED_TILES)) {
+    set_error("nrt_scene_render_ao_device: bad parameters (tiles are multiples of 8x4 pixels; no packed tiles)");
+    return NRT_ERR_INVALID;
+  }
+  Scene *sc = const_cast<Scene *>(reinterpret_cast<const Scene *>(s));
+  NRT_DEVICE(sc->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t trav_flags = p.flags & 0xFFFFu;
+  // this shard's ray slots: whole tiles, dealt round-robin (render.cu: run_ao_pass)
+  const unsigned long long tiles_x = (p.width + p.tile_w - 1) / p.tile_w, tiles_y = (p.height + p.tile_h - 1) / p.tile_h;
+  const unsigned long long n_tiles = tiles_x * tiles_y;
+  const unsigned long long my_tiles = n_tiles > p.shard ? (n_tiles - p.shard + p.n_shards - 1) / p.n_shards : 0;
+  const unsigned long long per_tile = (unsigned long long)p.tile_w * p.tile_h * p.spp;
+  const unsigned long long slots = my_tiles * per_tile;
+  unsigned long long wave = std::max<unsigned long long>(per_tile, (((unsigned long long)1 << 22) / per_tile) * per_tile);
+  if (wave > slots) wave = slots;
+  if (wave > 0xFFFFFFF0ull) {
+    set_error("nrt_scene_render_ao_device: a tile holds too many ray slots");
+    return NRT_ERR_INVALID;
+  }
+  SceneWave w;
+  unsigned long long h_tot[3] = {0, 0, 0};
+  uint32_t launches = 0, trav_launches = 0;
+  int rc = NRT_OK;
+  cudaError_t e = cudaSuccess;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (slots > 0) {
+    e = cudaMalloc(&w.rays, sizeof(Ray36) * wave);
+    if (e == cudaSuccess) e = cudaMalloc(&w.ao_rays, sizeof(Ray36) * wave);
+    if (e == cudaSuccess) e = cudaMalloc(&w.pix, sizeof(uint32_t) * wave);
+    if (e == cudaSuccess) e = cudaMalloc(&w.ao_pix, sizeof(uint32_t) * wave);
+    if (e == cudaSuccess) e = cudaMalloc(&w.hits, sizeof(SceneHit32) * wave);
+    if (e == cudaSuccess) e = cudaMalloc(&w.mask, wave);
+    if (e == cudaSuccess) e = cudaMalloc(&w.counters, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 8, st);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+    if (e == cudaSuccess) e = cudaEventRecord(ev0, st);
+  }
+  for (unsigned long long slot0 = 0; slot0 < slots && e == cudaSuccess && rc == NRT_OK; slot0 += wave) {
+    const uint32_t count = (uint32_t)std::min(wave, slots - slot0);
+    const unsigned blocks = (count + 255) / 256;
+    e = cudaMemsetAsync(w.counters, 0, sizeof(unsigned long long) * 2, st);
+    if (e != cudaSuccess) break;
+    scene_gen_primary_kernel<<<blocks, 256, 0, st>>>(p, slot0, count, w.rays, w.pix, w.counters);
+    rc = scene_launch(sc, w.rays, count, w.hits, w.mask, trav_flags, st);
+    if (rc != NRT_OK) break;
+    scene_gen_ao_kernel<<<blocks, 256, 0, st>>>(p, slot0, count, w.rays, w.pix, w.hits, w.mask, sc->d_inst, w.ao_rays, w.ao_pix,
+                                                d_accum, w.counters);
+    unsigned long long h_cnt[2] = {0, 0};
+    e = cudaMemcpyAsync(h_cnt, w.counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the scene walk takes its ray count from the host
+    if (e != cudaSuccess) break;
+    launches += 3;
+    trav_launches += 1;
+    h_tot[0] += h_cnt[0];
+    h_tot[2] += h_cnt[1];
+    if (h_cnt[0] > 0) {
+      rc = scene_launch(sc, w.ao_rays, (size_t)h_cnt[0], w.hits, w.mask, trav_flags, st);
+      if (rc != NRT_OK) break;
+      scene_accumulate_ao_kernel<<<(unsigned)((h_cnt[0] + 255) / 256), 256, 0, st>>>(w.mask, w.hits, w.ao_pix, h_cnt[0], p.ao_max_t,
+                                                                                       d_accum, w.counters + 4);
+      launches += 2;
+      trav_launches += 1;
+    }
+    e = cudaGetLastError();
+  }
+  float total_ms = 0.0f;
+  if (slots > 0 && e == cudaSuccess && rc == NRT_OK) {
+    e = cudaEventRecord(ev1, st);
+    unsigned long long h_occ = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_occ, w.counters + 5, sizeof(h_occ), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&total_ms, ev0, ev1);
+    h_tot[1] = h_occ;
+  } else if (slots > 0) {
+    cudaStreamSynchronize(st);  // nothing of a failed pass may still be running on the buffers freed below
+  }
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  w.release();
+  if (rc != NRT_OK) return rc;
+  NRT_CUDA(e);
+  if (res) {
+    res->primary_rays = h_tot[2];
+    res->ao_rays = h_tot[0];
+    res->ao_hits = h_tot[1];
+    res->total_ms = total_ms;
+    res->traverse_ms = 0.0f;  // not split: the scene walk is timed as part of the pass
+    res->primary_traverse_ms = res->ao_traverse_ms = 0.0f;
+    res->launches = launches;
+    res->traverse_launches = trav_launches;
+  }
+  return NRT_OK;
+}

@@ -161,3 +161,73 @@ def test_device_pointer_scene_traverse_and_empty_commit():
     torch.cuda.synchronize()
     assert np.array_equal(d_mask.cpu().numpy(), hm)
     assert d_hits.cpu().numpy().tobytes() == hh.tobytes()
+
+
+def _ao_params(api, cam, W, H, spp, radius, shard=0, n_shards=1):
+    p = api.AoParams()
+    for i in range(12):
+        p.cam[i] = float(cam[i])
+    p.width, p.height, p.spp, p.sample0, p.seed = W, H, spp, 0, 1
+    p.tile_w, p.tile_h, p.shard, p.n_shards = 64, 8, shard, n_shards
+    p.ray_min_t, p.ray_max_t, p.ao_min_t, p.ao_max_t = 1e-3, 1e30, 1e-3, radius
+    p.flags = 0
+    return p
+
+
+def test_scene_ao_pass_against_the_flattened_scene():
+    """nrt_scene_render_ao_device: the wavefront primary + AO pass with Scene::Traverse as its traversal step.  Against the
+    same triangles flattened into one soup and rendered by nrt_render_ao_device: the same camera rays hit the same
+    surfaces (primary hit counts equal up to grazing rays), frame.sum() == primary - occluded exactly, and the
+    visibility images agree (the scene pass lifts the AO origin by ao_min_t along the normal and works in world space,
+    so pixels may differ by a sample here and there, not systematically); tile shards add up to the whole frame."""
+    import torch
+    from nanort_b200 import api, scenes as S
+
+    base = S.sphere_grid(nx=3, nz=3)
+    insts = [(base[0], base[1], S.xform(translate=(-6.0, 0.0, 0.0))),
+             (base[0], base[1], S.xform(translate=(6.0, 0.5, 1.0), yaw=0.6)),
+             (base[0], base[1], S.xform(translate=(0.0, 0.0, -9.0), scale=(1.5, 1.0, 0.75), pitch=0.2))]
+    sc = _gpu_scene(insts, api.BUILD_FAST, api.BUILD_FAST)
+    vs, fs = [], []
+    for i, (v, f, x) in enumerate(insts):
+        x64 = x.astype(np.float64)
+        vs.append((v.astype(np.float64) @ x64[:3, :3] + x64[3, :3]).astype(np.float32))
+        fs.append(f + np.uint32(i * len(v)))
+    vs, fs = np.concatenate(vs), np.concatenate(fs).astype(np.uint32)
+    flat = api.BVHAccel()
+    flat.Build(len(fs), vs, fs)
+    W, H, spp = 320, 176, 4
+    cam = S.look_at((0.0, 12.0, 26.0), (0.0, 0.0, -2.0), aspect=W / H)
+    radius = 4.0
+    p = _ao_params(api, cam, W, H, spp, radius)
+    a_flat = torch.zeros(W * H, dtype=torch.float32, device="cuda")
+    r_flat = flat.RenderAO(p, a_flat.data_ptr())
+    a_sc = torch.zeros(W * H, dtype=torch.float32, device="cuda")
+    r_sc = sc.RenderAO(p, a_sc.data_ptr())
+    assert r_sc.primary_rays == r_flat.primary_rays == W * H * spp
+    assert abs(int(r_sc.ao_rays) - int(r_flat.ao_rays)) <= 1e-4 * r_flat.ao_rays + 4, (r_sc.ao_rays, r_flat.ao_rays)
+    assert r_sc.ao_hits > 0.05 * r_sc.ao_rays  # something is occluded
+    fsum = float(a_sc.double().sum().item())
+    assert fsum == float(r_sc.primary_rays - r_sc.ao_hits)
+    f_flat, f_sc = a_flat.cpu().numpy() / spp, a_sc.cpu().numpy() / spp
+    assert abs(f_sc.mean() - f_flat.mean()) < 2e-3, (f_sc.mean(), f_flat.mean())
+    differ = np.abs(f_sc - f_flat) > 1e-6
+    assert differ.mean() < 0.01, differ.mean()
+    assert np.abs(f_sc - f_flat).max() <= 2.0 / spp + 1e-6
+    # conformance walk of the scene (the reference's list algorithm): the same frame up to exact-distance ties
+    pc = _ao_params(api, cam, W, H, spp, radius)
+    pc.flags = api.TRAVERSE_CONFORMANCE
+    a_c = torch.zeros(W * H, dtype=torch.float32, device="cuda")
+    r_c = sc.RenderAO(pc, a_c.data_ptr())
+    assert r_c.primary_rays == r_sc.primary_rays and abs(int(r_c.ao_rays) - int(r_sc.ao_rays)) <= 4
+    assert float((a_c != a_sc).double().mean().item()) < 1e-3
+    # shards
+    total = torch.zeros(W * H, dtype=torch.float32, device="cuda")
+    rays = 0
+    for shard in range(3):
+        ps = _ao_params(api, cam, W, H, spp, radius, shard=shard, n_shards=3)
+        part = torch.zeros(W * H, dtype=torch.float32, device="cuda")
+        r = sc.RenderAO(ps, part.data_ptr())
+        total += part
+        rays += r.primary_rays
+    assert rays == W * H * spp and torch.equal(total, a_sc)

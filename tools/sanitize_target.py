@@ -48,6 +48,16 @@ srays["min_t"] = 0.0
 for fl in (api.TRAVERSE_FAST, api.TRAVERSE_CONFORMANCE):
     sh, sm = sc.Traverse(srays, flags=fl)
 print("scene ok", int(sm.sum()))
+ps = api.AoParams()
+scam = S.look_at((0.0, 6.0, 14.0), (0.0, 0.0, 0.0), aspect=96 / 64)
+for i in range(12): ps.cam[i] = float(scam[i])
+ps.width, ps.height, ps.spp, ps.sample0, ps.seed = 96, 64, 2, 0, 1
+ps.tile_w, ps.tile_h, ps.shard, ps.n_shards = 64, 8, 0, 1
+ps.ray_min_t, ps.ray_max_t, ps.ao_min_t, ps.ao_max_t = 1e-3, 1e30, 1e-3, 2.0
+saccum = torch.zeros(96 * 64, dtype=torch.float32, device="cuda")
+rs = sc.RenderAO(ps, saccum.data_ptr())
+assert float(saccum.double().sum().item()) == float(rs.primary_rays - rs.ao_hits)
+print("scene ao ok", rs.primary_rays, rs.ao_rays, rs.ao_hits)
 a64 = api.BVHAccelF64(); a64.Build(len(f), v.astype(np.float64), f)
 r64 = np.zeros(2048, api.RAY64_DTYPE)
 r64["org"], r64["dir"], r64["min_t"], r64["max_t"] = rays["org"][:2048], rays["dir"][:2048], 0.0, 1e30
