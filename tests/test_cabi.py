@@ -55,3 +55,28 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liborc" not in txt, fn
+
+
+def test_python_mirror_constants_equal_the_header_defines():
+    """The ctypes mirror's flag constants are the header's #defines (a drifted constant would silently select another
+    kernel or record layout), and the mirrored structs have the header's sizes."""
+    import ctypes as C
+    from nanort_b200 import api
+
+    src = open(os.path.join(ROOT, "include", "nanort_b200.h")).read()
+    defs = {m.group(1): int(m.group(2).rstrip("u"), 0) for m in re.finditer(r"#define\s+(NRT_[A-Z0-9_]+)\s+(-?(?:0x[0-9A-Fa-f]+|\d+)u?)\b", src)}
+    pairs = {"NRT_TRAVERSE_FAST": api.TRAVERSE_FAST, "NRT_TRAVERSE_CONFORMANCE": api.TRAVERSE_CONFORMANCE,
+             "NRT_TRAVERSE_CPP03_INVERSE": api.TRAVERSE_CPP03_INVERSE, "NRT_TRAVERSE_RAY32": api.TRAVERSE_RAY32,
+             "NRT_TRAVERSE_ANY_HIT": api.TRAVERSE_ANY_HIT, "NRT_AO_UNFUSED": api.AO_UNFUSED,
+             "NRT_AO_PACKED_TILES": api.AO_PACKED_TILES, "NRT_BUILD_FAST": api.BUILD_FAST,
+             "NRT_BUILD_REFERENCE_TREE": api.BUILD_REFERENCE_TREE, "NRT_PRIM_SPHERES": api.PRIM_SPHERES,
+             "NRT_PRIM_BOXES": api.PRIM_BOXES}
+    for name, value in pairs.items():
+        assert name in defs, name
+        assert defs[name] == value, (name, defs[name], value)
+    # the traverse flag bits do not collide with each other or with the experiment selector (bits 8..15)
+    bits = [defs[n] for n in ("NRT_TRAVERSE_CONFORMANCE", "NRT_TRAVERSE_CPP03_INVERSE", "NRT_TRAVERSE_RAY32", "NRT_TRAVERSE_ANY_HIT")]
+    assert len(set(bits)) == 4 and all(b & (b - 1) == 0 and b < 0x100 for b in bits)
+    assert defs["NRT_AO_UNFUSED"] > 0xFFFF and defs["NRT_AO_PACKED_TILES"] > 0xFFFF
+    # struct sizes the header documents
+    assert C.sizeof(api.AoResult) == 48 and C.sizeof(api.AoParams) == 104
