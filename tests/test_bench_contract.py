@@ -37,3 +37,16 @@ def test_reference_arm_prints_the_contract_line():
 
 def test_reference_arm_other_ranks_stay_silent():
     assert _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_every_tool_script_and_the_bench_parse():
+    """tools/*.py, bench.py and __graft_entry__.py at least compile (they only run on the GPU box)."""
+    import glob
+    import py_compile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "tools", "*.py"))) + [os.path.join(root, "bench.py"),
+                                                                       os.path.join(root, "__graft_entry__.py")]
+    assert len(files) > 20
+    for f in files:
+        py_compile.compile(f, doraise=True)
